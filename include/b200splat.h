@@ -1,0 +1,244 @@
+/*
+ * b200splat.h — C ABI of libb200splat.so, the sm_100a replacement for the native
+ * entry points of the gsplat fork used by inuex35/splat_one.
+ *
+ * Every function is `extern "C"`, takes plain device pointers + explicit sizes + a
+ * `cudaStream_t` (passed as `void*`), owns no memory and keeps no global state
+ * (re-entrant: splat_one calls from a training thread and the Qt thread at once,
+ * SURVEY.md §7 H7).  All floating tensors are fp32, row-major, densely packed.
+ * Return value: 0 on success, non-zero on failure; the message is available from
+ * `b200splat_last_error()` (thread-local).
+ *
+ * Path shorthand for the citations:  CS/ = /root/reference/submodules/gsplat/gsplat/cuda/csrc/
+ * Each entry point names the reference pybind11 symbol (CS/ext.cpp:11-56) and the
+ * C++ signature (CS/bindings.h) it replaces.
+ *
+ * Data-dependent sizes (`nnz`, `n_isects`) use two-phase calls: a `*_count` call writes
+ * the total into device memory, the host reads one integer, allocates, and calls
+ * `*_fill`.
+ */
+#ifndef B200SPLAT_H
+#define B200SPLAT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define B200SPLAT_API __attribute__((visibility("default")))
+#else
+#define B200SPLAT_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* CS/bindings.h:34-40 `enum CameraModelType` (pybind: CS/ext.cpp:4-9). */
+enum b200splat_camera_model {
+    B200SPLAT_PINHOLE = 0,
+    B200SPLAT_ORTHO = 1,
+    B200SPLAT_FISHEYE = 2,
+    B200SPLAT_SPHERICAL = 3
+};
+
+/* ABI version of this header (bumped on any signature change). */
+B200SPLAT_API int b200splat_abi_version(void);
+/* Thread-local message of the last failing call on this thread ("" if none). */
+B200SPLAT_API const char *b200splat_last_error(void);
+/* Compile-time facts, for diagnostics: returns "sm_100a". */
+B200SPLAT_API const char *b200splat_arch(void);
+
+/* ------------------------------------------------------------------------------------
+ * a2  fully_fused_projection_fwd        CS/bindings.h:95-116, kernel
+ *     CS/fully_fused_projection_fwd.cu:20-216.
+ * covars [N,6] XOR (quats [N,4], scales [N,3]).  compensations may be NULL.
+ * Outputs [C,N,...]; entries with radii==0 are left untouched except radii.
+ * ---------------------------------------------------------------------------------- */
+B200SPLAT_API int b200splat_projection_fwd(
+    uint32_t C, uint32_t N,
+    const float *means, const float *covars, const float *quats, const float *scales,
+    const float *viewmats, const float *Ks,
+    uint32_t image_width, uint32_t image_height,
+    float eps2d, float near_plane, float far_plane, float radius_clip,
+    int camera_model,
+    int32_t *radii, float *means2d, float *depths, float *conics, float *compensations,
+    void *stream);
+
+/* a3  fully_fused_projection_bwd        CS/bindings.h:118-146, kernel
+ *     CS/fully_fused_projection_bwd.cu:20-271.
+ * v_means/v_covars/v_quats/v_scales are OVERWRITTEN (no pre-zeroing needed): one thread
+ * owns one Gaussian and loops over the C cameras, so there are no atomics and the
+ * result is deterministic.  v_viewmats [C,4,4] (optional, may be NULL) must be zeroed by
+ * the caller; it is accumulated with block-reduced atomics.
+ * compensations / v_compensations may be NULL. */
+B200SPLAT_API int b200splat_projection_bwd(
+    uint32_t C, uint32_t N,
+    const float *means, const float *covars, const float *quats, const float *scales,
+    const float *viewmats, const float *Ks,
+    uint32_t image_width, uint32_t image_height, float eps2d, int camera_model,
+    const int32_t *radii, const float *conics, const float *compensations,
+    const float *v_means2d, const float *v_depths, const float *v_conics,
+    const float *v_compensations,
+    float *v_means, float *v_covars, float *v_quats, float *v_scales, float *v_viewmats,
+    void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * a4  fully_fused_projection_packed_fwd  CS/bindings.h:254-278, kernel
+ *     CS/fully_fused_projection_packed_fwd.cu:20-267 (two launches + cumsum + .item()).
+ * Phase 1 (`_count`): block_cnts[C*blocks_per_row] (blocks_per_row = ceil(N/256)),
+ *   then an inclusive scan into block_accum (same length, int32) and the total into
+ *   *nnz_out (device int32).  Host reads nnz_out.
+ * Phase 2 (`_fill`): writes the COO outputs in (camera, gaussian) row-major order and
+ *   indptr[C+1].
+ * ---------------------------------------------------------------------------------- */
+B200SPLAT_API int b200splat_projection_packed_count(
+    uint32_t C, uint32_t N,
+    const float *means, const float *covars, const float *quats, const float *scales,
+    const float *viewmats, const float *Ks,
+    uint32_t image_width, uint32_t image_height,
+    float eps2d, float near_plane, float far_plane, float radius_clip, int camera_model,
+    int32_t *block_accum, /* [C*ceil(N/256)] out: inclusive scan of per-block counts */
+    int32_t *nnz_out,     /* [1] device */
+    void *stream);
+
+B200SPLAT_API int b200splat_projection_packed_fill(
+    uint32_t C, uint32_t N,
+    const float *means, const float *covars, const float *quats, const float *scales,
+    const float *viewmats, const float *Ks,
+    uint32_t image_width, uint32_t image_height,
+    float eps2d, float near_plane, float far_plane, float radius_clip, int camera_model,
+    const int32_t *block_accum,
+    int32_t *indptr, int64_t *camera_ids, int64_t *gaussian_ids,
+    int32_t *radii, float *means2d, float *depths, float *conics, float *compensations,
+    void *stream);
+
+/* a4  fully_fused_projection_packed_bwd  CS/bindings.h:280-310, kernel
+ *     CS/fully_fused_projection_packed_bwd.cu:20-310.
+ * sparse_grad != 0: v_* are [nnz,·] rows, overwritten.  sparse_grad == 0: v_* are
+ * [N,·], must be zeroed by the caller, accumulated with atomics (rows of one Gaussian
+ * from different cameras are not adjacent in COO order). v_viewmats as in a3. */
+B200SPLAT_API int b200splat_projection_packed_bwd(
+    uint32_t C, uint32_t N, uint32_t nnz,
+    const float *means, const float *covars, const float *quats, const float *scales,
+    const float *viewmats, const float *Ks,
+    uint32_t image_width, uint32_t image_height, float eps2d, int camera_model,
+    const int64_t *camera_ids, const int64_t *gaussian_ids,
+    const float *conics, const float *compensations,
+    const float *v_means2d, const float *v_depths, const float *v_conics,
+    const float *v_compensations,
+    int sparse_grad,
+    float *v_means, float *v_covars, float *v_quats, float *v_scales, float *v_viewmats,
+    void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * a5  compute_sh_fwd / compute_sh_bwd    CS/bindings.h:235-249, kernels
+ *     CS/compute_sh_fwd.cu:12-38, CS/compute_sh_bwd.cu:13-49, math
+ *     CS/spherical_harmonics.cuh:17-366.
+ * n_elems directions; coeffs has `n_coeff_rows` rows of [K,3]; element e reads row
+ * (e % n_coeff_rows) — n_coeff_rows == n_elems is the reference layout, n_coeff_rows ==
+ * N with n_elems == C*N evaluates a [N,K,3] table for C cameras without materialising
+ * the `expand(C,...)` copy (rendering.py:386, _wrapper.py:71-73).
+ * masks (uint8/bool, may be NULL): masked elements are left untouched in `colors`.
+ * Unlike the reference (legacy default stream, CS/compute_sh_fwd.cu:58-61) the kernels
+ * run on `stream`.
+ * bwd: v_coeffs [n_elems,K,3] is fully OVERWRITTEN (zeros for masked rows and for bases
+ * above the active degree); v_dirs (may be NULL) [n_elems,3] fully overwritten. */
+B200SPLAT_API int b200splat_sh_fwd(
+    uint32_t n_elems, uint32_t n_coeff_rows, uint32_t K, uint32_t degrees_to_use,
+    const float *dirs, const float *coeffs, const uint8_t *masks,
+    float *colors, void *stream);
+
+B200SPLAT_API int b200splat_sh_bwd(
+    uint32_t n_elems, uint32_t n_coeff_rows, uint32_t K, uint32_t degrees_to_use,
+    const float *dirs, const float *coeffs, const uint8_t *masks,
+    const float *v_colors,
+    float *v_coeffs, float *v_dirs, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * a6  isect_tiles                         CS/bindings.h:148-160, kernel
+ *     CS/isect_tiles.cu:17-105, host :107-307.
+ * Phase 1 (`_count`): tiles_per_gauss [n_elems] int32, cum_tiles [n_elems] int64
+ *   (inclusive scan) and *n_isects_out (device int64).
+ * Phase 2 (`_fill`): unsorted keys `cam | tile | depth bits` + flat indices.
+ * Phase 3 (`_sort`): stable LSD radix sort of (key,value) on bits [0, end_bit) over a
+ *   pair of ping-pong buffers (the reference's cub::DoubleBuffer, CS/isect_tiles.cu:262-299);
+ *   `*selector_out` says which buffer holds the result.  Workspace size from
+ *   `_sort_workspace_bytes`.
+ * packed != 0: n_elems = nnz and camera_ids [nnz] int64 gives the camera of each row;
+ * packed == 0: n_elems = C*N, camera = idx / N.
+ * ---------------------------------------------------------------------------------- */
+B200SPLAT_API int b200splat_isect_count(
+    int packed, uint32_t C, uint32_t N, uint32_t nnz,
+    const float *means2d, const int32_t *radii,
+    uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+    int32_t *tiles_per_gauss, int64_t *cum_tiles, int64_t *n_isects_out,
+    void *scan_workspace, size_t scan_workspace_bytes,
+    void *stream);
+
+B200SPLAT_API size_t b200splat_scan_workspace_bytes(uint64_t n_elems);
+
+B200SPLAT_API int b200splat_isect_fill(
+    int packed, uint32_t C, uint32_t N, uint32_t nnz,
+    const int64_t *camera_ids,
+    const float *means2d, const int32_t *radii, const float *depths,
+    const int64_t *cum_tiles,
+    uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+    int64_t *isect_ids, int32_t *flatten_ids,
+    void *stream);
+
+B200SPLAT_API size_t b200splat_sort_workspace_bytes(uint64_t n_isects);
+
+B200SPLAT_API int b200splat_isect_sort(
+    uint64_t n_isects, uint32_t end_bit,
+    int64_t *keys_a, int32_t *vals_a,   /* input, clobbered */
+    int64_t *keys_b, int32_t *vals_b,   /* alternate buffers */
+    void *workspace, size_t workspace_bytes,
+    int *selector_out,                  /* HOST int: 0 => result in *_a, 1 => in *_b */
+    void *stream);
+
+/* a7  isect_offset_encode                 CS/bindings.h:162-167, kernel
+ *     CS/isect_tiles.cu:309-355.  offsets [C*n_tiles] int32 fully written
+ *     (all zeros when n_isects == 0). */
+B200SPLAT_API int b200splat_isect_offset_encode(
+    uint64_t n_isects, const int64_t *isect_ids,
+    uint32_t C, uint32_t tile_width, uint32_t tile_height,
+    int32_t *offsets, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * a8  rasterize_to_pixels_fwd            CS/bindings.h:169-185, kernel
+ *     CS/rasterize_to_pixels_fwd.cu:16-186.
+ * n_gauss = C*N (unpacked) or nnz (packed): number of rows of means2d/conics/colors/
+ * opacities.  channels: any 1..64 (the Python wrapper chunks above that).
+ * backgrounds [C,channels] / masks [C,tile_h,tile_w] (uint8/bool) may be NULL.
+ * ---------------------------------------------------------------------------------- */
+B200SPLAT_API int b200splat_rasterize_fwd(
+    uint32_t C, uint32_t n_gauss, uint64_t n_isects, uint32_t channels,
+    const float *means2d, const float *conics, const float *colors, const float *opacities,
+    const float *backgrounds, const uint8_t *masks,
+    uint32_t image_width, uint32_t image_height,
+    uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+    const int32_t *tile_offsets, const int32_t *flatten_ids,
+    float *render_colors, float *render_alphas, int32_t *last_ids,
+    void *stream);
+
+/* a9  rasterize_to_pixels_bwd            CS/bindings.h:187-216, kernel
+ *     CS/rasterize_to_pixels_bwd.cu:16-277.
+ * v_means2d, v_conics, v_colors, v_opacities (and v_means2d_abs if not NULL) must be
+ * zeroed by the caller; they are accumulated with reduced atomics. */
+B200SPLAT_API int b200splat_rasterize_bwd(
+    uint32_t C, uint32_t n_gauss, uint64_t n_isects, uint32_t channels,
+    const float *means2d, const float *conics, const float *colors, const float *opacities,
+    const float *backgrounds, const uint8_t *masks,
+    uint32_t image_width, uint32_t image_height,
+    uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+    const int32_t *tile_offsets, const int32_t *flatten_ids,
+    const float *render_alphas, const int32_t *last_ids,
+    const float *v_render_colors, const float *v_render_alphas,
+    float *v_means2d_abs, float *v_means2d, float *v_conics, float *v_colors,
+    float *v_opacities,
+    void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SPLAT_H */

@@ -1,0 +1,31 @@
+"""splat_one_b200 — B200-native (sm_100a) rasterization hot path behind the gsplat API
+that inuex35/splat_one calls (`gsplat.rasterization` and the five operators under it).
+
+    from splat_one_b200 import rasterization            # == gsplat.rendering.rasterization
+    from splat_one_b200 import (fully_fused_projection, isect_tiles, isect_offset_encode,
+                                rasterize_to_pixels, spherical_harmonics)
+
+The compute lives in libb200splat.so (hand-written CUDA, C ABI in include/b200splat.h);
+there is no CPU / PyTorch fallback.
+"""
+from .rendering import rasterization
+from .wrapper import (
+    fully_fused_projection,
+    isect_offset_encode,
+    isect_tiles,
+    rasterize_to_pixels,
+    spherical_harmonics,
+    spherical_harmonics_table,
+)
+
+__version__ = "0.1.0"
+
+__all__ = [
+    "rasterization",
+    "fully_fused_projection",
+    "isect_tiles",
+    "isect_offset_encode",
+    "rasterize_to_pixels",
+    "spherical_harmonics",
+    "spherical_harmonics_table",
+]

@@ -1,0 +1,261 @@
+// raster_bwd.cu — backward of the tile rasterizer (a9).
+// Replaces CS/rasterize_to_pixels_bwd.cu:16-277.  Semantics kept exactly: back-to-front
+// replay from T_final = 1 - alpha_out, T <- T/(1-alpha); pairs behind last_ids skipped;
+// same accept rules as the forward; v_rgb = alpha·T·v_out; v_alpha as in :203-219;
+// conic / mean / opacity gradients only when opac·vis <= 0.999; absgrad = |v_xy|.
+//
+// Design (B200): the reference reduces each of the 9(+2) per-pair gradient values with
+// its own 5-step shuffle tree (45–55 SHFL per pair per warp) and then issues 9–11
+// scalar atomics from lane 0.  Here the values are reduced with a transposed
+// (reduce-scatter) butterfly — 16 SHFL for up to 16 values — which leaves value k in
+// lane 2k, so a single RED instruction with <= 16 active lanes commits all of them.
+#include "raster_common.cuh"
+
+namespace b2s {
+
+// Reduce-scatter over the warp: on return, lane l holds sum over lanes of v[l / (32/P)].
+// P is a power of two <= 32.
+template <int P>
+__device__ __forceinline__ float warp_reduce_scatter(float (&v)[P], const unsigned lane) {
+    if (P == 1) return warp_sum(v[0]);
+    int o = 16;
+#pragma unroll
+    for (int h = P / 2; h >= 1; h /= 2) {
+        const bool upper = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+            const float keep = upper ? v[i + h] : v[i];
+            const float send = upper ? v[i] : v[i + h];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+        o >>= 1;
+    }
+    float r = v[0];
+    for (; o >= 1; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    return r;
+}
+
+constexpr int next_pow2(int n) { return n <= 1 ? 1 : n <= 2 ? 2 : n <= 4 ? 4 : n <= 8 ? 8 : n <= 16 ? 16 : 32; }
+
+// Reduce NV per-lane values across the warp and hand value k (k = 0..NV-1) to `commit`
+// on exactly one lane.  Values are processed in chunks of <= 32.
+template <int NV, int OFF = 0, typename Commit>
+__device__ __forceinline__ void warp_reduce_commit(const float *v, const unsigned lane, Commit &&commit) {
+    constexpr int CH = (NV - OFF) > 32 ? 32 : (NV - OFF);
+    constexpr int P = next_pow2(CH);
+    float w[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) w[i] = (i < CH) ? v[OFF + i] : 0.f;
+    const float r = warp_reduce_scatter<P>(w, lane);
+    constexpr int stride = 32 / P;
+    const int k = (int)lane / stride;
+    if ((lane % stride) == 0 && k < CH) commit(OFF + k, r);
+    if constexpr (OFF + CH < NV) warp_reduce_commit<NV, OFF + CH>(v, lane, commit);
+}
+
+template <int CDIM, bool ABS, int MAXT>
+__global__ void __launch_bounds__(MAXT)
+raster_bwd_kernel(uint32_t C, uint64_t n_isects, uint32_t channels, const float2 *__restrict__ means2d,
+                  const float *__restrict__ conics, const float *__restrict__ colors,
+                  const float *__restrict__ opacities, const float *__restrict__ backgrounds,
+                  const uint8_t *__restrict__ masks, uint32_t W, uint32_t H, uint32_t tile_size, uint32_t tile_width,
+                  uint32_t tile_height, const int32_t *__restrict__ tile_offsets,
+                  const int32_t *__restrict__ flatten_ids, const float *__restrict__ render_alphas,
+                  const int32_t *__restrict__ last_ids, const float *__restrict__ v_render_colors,
+                  const float *__restrict__ v_render_alphas, float *__restrict__ v_means2d_abs,
+                  float *__restrict__ v_means2d, float *__restrict__ v_conics, float *__restrict__ v_colors,
+                  float *__restrict__ v_opacities) {
+    constexpr int NV = CDIM + 6 + (ABS ? 2 : 0);
+    const TileCoord tc = tile_coord(tile_size, tile_width, tile_height, W, H);
+    const uint32_t n_tiles_total = C * tile_width * tile_height;
+    if (masks != nullptr && !masks[tc.tile_lin]) return;
+    const bool inside = tc.inside;
+    const size_t pix = ((size_t)tc.cam * H + tc.i) * W + tc.j;
+    const float px = (float)tc.j + 0.5f, py = (float)tc.i + 0.5f;
+
+    const int32_t range_start = tile_offsets[tc.tile_lin];
+    const int32_t range_end =
+        (tc.tile_lin == n_tiles_total - 1) ? (int32_t)n_isects : tile_offsets[tc.tile_lin + 1];
+    const int32_t block_size = (int32_t)blockDim.x;
+    const int32_t num_batches = (range_end - range_start + block_size - 1) / block_size;
+
+    extern __shared__ float4 smem4[];
+    float4 *rec_a = smem4;                   // {x, y, opacity, conic.a}
+    float4 *rec_b = smem4 + block_size;      // {conic.b, conic.c, id (bits), -}
+    float *rgbs = reinterpret_cast<float *>(smem4 + 2 * block_size);  // [block_size * CDIM]
+
+    float T_final = 1.f, v_render_a = 0.f;
+    float v_render_c[CDIM], buffer[CDIM];
+    int32_t bin_final = 0;
+#pragma unroll
+    for (int k = 0; k < CDIM; ++k) { v_render_c[k] = 0.f; buffer[k] = 0.f; }
+    float bg_dot = 0.f;  // sum_k background_k * v_render_c_k
+    if (inside) {
+        T_final = 1.f - render_alphas[pix];
+        bin_final = last_ids[pix];
+        v_render_a = v_render_alphas[pix];
+#pragma unroll
+        for (int k = 0; k < CDIM; ++k)
+            if (k < (int)channels) v_render_c[k] = v_render_colors[pix * channels + k];
+        if (backgrounds != nullptr) {
+#pragma unroll
+            for (int k = 0; k < CDIM; ++k)
+                if (k < (int)channels) bg_dot += backgrounds[(size_t)tc.cam * channels + k] * v_render_c[k];
+        }
+    }
+    float T = T_final;
+    const int32_t tr = (int32_t)threadIdx.x;
+    const unsigned lane = threadIdx.x & 31;
+    const int32_t warp_bin_final = warp_max(bin_final);
+
+    for (int32_t b = 0; b < num_batches; ++b) {
+        __syncthreads();
+        const int32_t batch_end = range_end - 1 - block_size * b;
+        const int32_t batch_size = min(block_size, batch_end + 1 - range_start);
+        const int32_t idx = batch_end - tr;
+        if (idx >= range_start) {
+            const int32_t g = flatten_ids[idx];
+            const float2 xy = __ldg(means2d + g);
+            const float opac = __ldg(opacities + g);
+            const float ca = __ldg(conics + 3 * (size_t)g), cb = __ldg(conics + 3 * (size_t)g + 1),
+                        cc = __ldg(conics + 3 * (size_t)g + 2);
+            rec_a[tr] = make_float4(xy.x, xy.y, opac, ca);
+            rec_b[tr] = make_float4(cb, cc, __int_as_float(g), 0.f);
+#pragma unroll
+            for (int k = 0; k < CDIM; ++k)
+                rgbs[tr * CDIM + k] = (k < (int)channels) ? __ldg(colors + (size_t)g * channels + k) : 0.f;
+        }
+        __syncthreads();
+        for (int32_t t = max(0, batch_end - warp_bin_final); t < batch_size; ++t) {
+            bool valid = inside && (batch_end - t <= bin_final);
+            float alpha = 0.f, opac = 0.f, vis = 0.f, dx = 0.f, dy = 0.f, ca = 0.f, cb = 0.f, cc = 0.f;
+            if (valid) {
+                const float4 ra = rec_a[t];
+                const float4 rb = rec_b[t];
+                opac = ra.z; ca = ra.w; cb = rb.x; cc = rb.y;
+                dx = ra.x - px; dy = ra.y - py;
+                const float sigma = 0.5f * (ca * dx * dx + cc * dy * dy) + cb * dx * dy;
+                vis = __expf(-sigma);
+                alpha = fminf(kAlphaMax, opac * vis);
+                if (sigma < 0.f || alpha < kAlphaMin) valid = false;
+            }
+            if (!__any_sync(0xffffffffu, valid)) continue;
+            float v[NV];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) v[k] = 0.f;
+            if (valid) {
+                const float ra_ = 1.f / (1.f - alpha);
+                T *= ra_;
+                const float fac = alpha * T;
+                float v_alpha = 0.f;
+#pragma unroll
+                for (int k = 0; k < CDIM; ++k) {
+                    const float c = rgbs[t * CDIM + k];
+                    v[k] = fac * v_render_c[k];
+                    v_alpha += (c * T - buffer[k] * ra_) * v_render_c[k];
+                    buffer[k] += c * fac;
+                }
+                v_alpha += T_final * ra_ * v_render_a;
+                if (backgrounds != nullptr) v_alpha += -T_final * ra_ * bg_dot;
+                if (opac * vis <= kAlphaMax) {
+                    const float v_sigma = -opac * vis * v_alpha;
+                    v[CDIM + 0] = 0.5f * v_sigma * dx * dx;
+                    v[CDIM + 1] = v_sigma * dx * dy;
+                    v[CDIM + 2] = 0.5f * v_sigma * dy * dy;
+                    const float vx = v_sigma * (ca * dx + cb * dy);
+                    const float vy = v_sigma * (cb * dx + cc * dy);
+                    v[CDIM + 3] = vx;
+                    v[CDIM + 4] = vy;
+                    v[CDIM + 5] = vis * v_alpha;
+                    if (ABS) { v[CDIM + 6] = fabsf(vx); v[CDIM + 7] = fabsf(vy); }
+                }
+            }
+            const int32_t g = __float_as_int(rec_b[t].z);
+            warp_reduce_commit<NV>(v, lane, [&](int k, float val) {
+                float *dst;
+                if (k < CDIM) {
+                    if (k >= (int)channels) return;
+                    dst = v_colors + (size_t)g * channels + k;
+                } else if (k < CDIM + 3) dst = v_conics + 3 * (size_t)g + (k - CDIM);
+                else if (k < CDIM + 5) dst = v_means2d + 2 * (size_t)g + (k - CDIM - 3);
+                else if (k == CDIM + 5) dst = v_opacities + g;
+                else dst = v_means2d_abs + 2 * (size_t)g + (k - CDIM - 6);
+                atomicAdd(dst, val);
+            });
+        }
+    }
+}
+
+template <int CDIM, bool ABS>
+static void launch_bwd(uint32_t C, uint64_t n_isects, uint32_t channels, const float *means2d, const float *conics,
+                       const float *colors, const float *opacities, const float *backgrounds, const uint8_t *masks,
+                       uint32_t W, uint32_t H, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+                       const int32_t *tile_offsets, const int32_t *flatten_ids, const float *render_alphas,
+                       const int32_t *last_ids, const float *v_render_colors, const float *v_render_alphas,
+                       float *v_means2d_abs, float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
+                       cudaStream_t st) {
+    const uint32_t threads = ((tile_size * tile_size + 31) / 32) * 32;
+    const uint32_t grid = C * tile_width * tile_height;
+    const size_t smem = (size_t)threads * (2 * sizeof(float4) + CDIM * sizeof(float));
+    if (threads <= 256) {
+        auto kern = raster_bwd_kernel<CDIM, ABS, 256>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<grid, threads, smem, st>>>(C, n_isects, channels, reinterpret_cast<const float2 *>(means2d), conics,
+                                          colors, opacities, backgrounds, masks, W, H, tile_size, tile_width,
+                                          tile_height, tile_offsets, flatten_ids, render_alphas, last_ids,
+                                          v_render_colors, v_render_alphas, v_means2d_abs, v_means2d, v_conics,
+                                          v_colors, v_opacities);
+    } else {
+        auto kern = raster_bwd_kernel<CDIM, ABS, 1024>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<grid, threads, smem, st>>>(C, n_isects, channels, reinterpret_cast<const float2 *>(means2d), conics,
+                                          colors, opacities, backgrounds, masks, W, H, tile_size, tile_width,
+                                          tile_height, tile_offsets, flatten_ids, render_alphas, last_ids,
+                                          v_render_colors, v_render_alphas, v_means2d_abs, v_means2d, v_conics,
+                                          v_colors, v_opacities);
+    }
+}
+
+}  // namespace b2s
+
+using namespace b2s;
+
+extern "C" int b200splat_rasterize_bwd(uint32_t C, uint32_t n_gauss, uint64_t n_isects, uint32_t channels,
+                                       const float *means2d, const float *conics, const float *colors,
+                                       const float *opacities, const float *backgrounds, const uint8_t *masks,
+                                       uint32_t W, uint32_t H, uint32_t tile_size, uint32_t tile_width,
+                                       uint32_t tile_height, const int32_t *tile_offsets, const int32_t *flatten_ids,
+                                       const float *render_alphas, const int32_t *last_ids,
+                                       const float *v_render_colors, const float *v_render_alphas,
+                                       float *v_means2d_abs, float *v_means2d, float *v_conics, float *v_colors,
+                                       float *v_opacities, void *stream) {
+    const char *where = "b200splat_rasterize_bwd";
+    (void)n_gauss;
+    B2S_REQUIRE(tile_size >= 1 && tile_size <= 32, where, "tile_size must be in [1, 32]");
+    B2S_REQUIRE(n_isects <= 0x7fffffffull, where, "n_isects exceeds int32 offsets");
+    const int cdim = pick_cdim(channels);
+    B2S_REQUIRE(channels >= 1 && cdim > 0, where, "unsupported number of color channels (1..33)");
+    if ((uint64_t)C * tile_width * tile_height == 0 || n_isects == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool absgrad = v_means2d_abs != nullptr;
+#define B2S_BWD(D)                                                                                                  \
+    case D:                                                                                                         \
+        if (absgrad)                                                                                                \
+            launch_bwd<D, true>(C, n_isects, channels, means2d, conics, colors, opacities, backgrounds, masks, W, H, \
+                                tile_size, tile_width, tile_height, tile_offsets, flatten_ids, render_alphas,       \
+                                last_ids, v_render_colors, v_render_alphas, v_means2d_abs, v_means2d, v_conics,     \
+                                v_colors, v_opacities, st);                                                         \
+        else                                                                                                        \
+            launch_bwd<D, false>(C, n_isects, channels, means2d, conics, colors, opacities, backgrounds, masks, W,  \
+                                 H, tile_size, tile_width, tile_height, tile_offsets, flatten_ids, render_alphas,   \
+                                 last_ids, v_render_colors, v_render_alphas, v_means2d_abs, v_means2d, v_conics,    \
+                                 v_colors, v_opacities, st);                                                        \
+        break;
+    switch (cdim) {
+        B2S_BWD(1) B2S_BWD(2) B2S_BWD(3) B2S_BWD(4) B2S_BWD(5) B2S_BWD(8) B2S_BWD(9) B2S_BWD(16) B2S_BWD(17)
+        B2S_BWD(32) B2S_BWD(33)
+    }
+#undef B2S_BWD
+    B2S_CHECK_LAUNCH(where);
+    return 0;
+}

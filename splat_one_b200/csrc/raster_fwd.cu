@@ -1,0 +1,182 @@
+// raster_fwd.cu — per-tile front-to-back alpha compositing (a8).
+// Replaces CS/rasterize_to_pixels_fwd.cu:16-186.  Semantics kept exactly: pixel centre
+// (j+0.5, i+0.5); sigma = 0.5(a dx² + c dy²) + b dx dy; alpha = min(0.999, o·exp(-sigma));
+// skip when sigma < 0 or alpha < 1/255; stop (exclusive) when T(1-alpha) <= 1e-4;
+// alpha_out = 1-T; colour += T·background; last_ids = sorted index of the last
+// contributor; masked tiles write background only.
+//
+// Design (B200): one CTA per tile, one thread per pixel.  Each batch of Gaussians is
+// gathered once per CTA into shared memory as two 16-byte records (+ one for the colour
+// when D <= 4), so the per-pair inner loop is two/three broadcast LDS.128 instead of the
+// reference's 7 scalar LDS + a dependent global colour read, and `flatten_ids` is
+// consumed with coalesced loads.  The loop body is the fp32/MUFU critical path; see
+// DESIGN.md for the measured limits.
+#include "raster_common.cuh"
+
+namespace b2s {
+
+template <int CDIM, int MAXT>
+__global__ void __launch_bounds__(MAXT)
+raster_fwd_kernel(uint32_t C, uint64_t n_isects, uint32_t channels, const float2 *__restrict__ means2d,
+                  const float *__restrict__ conics, const float *__restrict__ colors,
+                  const float *__restrict__ opacities, const float *__restrict__ backgrounds,
+                  const uint8_t *__restrict__ masks, uint32_t W, uint32_t H, uint32_t tile_size, uint32_t tile_width,
+                  uint32_t tile_height, const int32_t *__restrict__ tile_offsets,
+                  const int32_t *__restrict__ flatten_ids, float *__restrict__ render_colors,
+                  float *__restrict__ render_alphas, int32_t *__restrict__ last_ids) {
+    constexpr bool kStageColor = CDIM <= 4;
+    const TileCoord tc = tile_coord(tile_size, tile_width, tile_height, W, H);
+    const uint32_t n_tiles_total = C * tile_width * tile_height;
+    const bool inside = tc.inside;
+    const size_t pix = ((size_t)tc.cam * H + tc.i) * W + tc.j;
+    const float px = (float)tc.j + 0.5f, py = (float)tc.i + 0.5f;
+    if (backgrounds != nullptr) backgrounds += (size_t)tc.cam * channels;
+
+    if (masks != nullptr && !masks[tc.tile_lin]) {
+        // masked tile: background only; alpha / last_ids untouched (CS/...fwd.cu:71-77)
+        if (inside) {
+            for (uint32_t k = 0; k < channels; ++k)
+                render_colors[pix * channels + k] = backgrounds == nullptr ? 0.f : backgrounds[k];
+        }
+        return;
+    }
+
+    const int32_t range_start = tile_offsets[tc.tile_lin];
+    const int32_t range_end =
+        (tc.tile_lin == n_tiles_total - 1) ? (int32_t)n_isects : tile_offsets[tc.tile_lin + 1];
+    const uint32_t block_size = blockDim.x;
+    const uint32_t num_batches = (uint32_t)(range_end - range_start + block_size - 1) / block_size;
+
+    extern __shared__ float4 smem4[];
+    float4 *rec_a = smem4;                  // {x, y, opacity, conic.a}
+    float4 *rec_b = smem4 + block_size;     // {conic.b, conic.c, id (bits), -}
+    float4 *rec_c = smem4 + 2 * block_size; // colour (only when kStageColor)
+
+    float T = 1.f;
+    uint32_t cur_idx = 0;
+    bool done = !inside;
+    const uint32_t tr = threadIdx.x;
+    float pix_out[CDIM];
+#pragma unroll
+    for (int k = 0; k < CDIM; ++k) pix_out[k] = 0.f;
+
+    for (uint32_t b = 0; b < num_batches; ++b) {
+        // also protects the smem records of the previous batch
+        if (__syncthreads_count(done) >= (int)block_size) break;
+        const uint32_t batch_start = range_start + block_size * b;
+        const uint32_t idx = batch_start + tr;
+        if (idx < (uint32_t)range_end) {
+            const int32_t g = flatten_ids[idx];
+            const float2 xy = __ldg(means2d + g);
+            const float opac = __ldg(opacities + g);
+            const float ca = __ldg(conics + 3 * (size_t)g), cb = __ldg(conics + 3 * (size_t)g + 1),
+                        cc = __ldg(conics + 3 * (size_t)g + 2);
+            rec_a[tr] = make_float4(xy.x, xy.y, opac, ca);
+            rec_b[tr] = make_float4(cb, cc, __int_as_float(g), 0.f);
+            if (kStageColor) {
+                float c4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int k = 0; k < CDIM; ++k)
+                    if (k < (int)channels) c4[k] = __ldg(colors + (size_t)g * channels + k);
+                rec_c[tr] = make_float4(c4[0], c4[1], c4[2], c4[3]);
+            }
+        }
+        __syncthreads();
+        const uint32_t batch_size = min(block_size, (uint32_t)range_end - batch_start);
+        for (uint32_t t = 0; (t < batch_size) && !done; ++t) {
+            const float4 ra = rec_a[t];
+            const float4 rb = rec_b[t];
+            const float dx = ra.x - px, dy = ra.y - py;
+            const float sigma = 0.5f * (ra.w * dx * dx + rb.y * dy * dy) + rb.x * dx * dy;
+            const float alpha = fminf(kAlphaMax, ra.z * __expf(-sigma));
+            if (sigma < 0.f || alpha < kAlphaMin) continue;
+            const float next_T = T * (1.f - alpha);
+            if (next_T <= kTransmittanceEps) {  // exclusive: this Gaussian is not composited
+                done = true;
+                break;
+            }
+            const float vis = alpha * T;
+            if (kStageColor) {
+                const float4 rc = rec_c[t];
+                const float cv[4] = {rc.x, rc.y, rc.z, rc.w};
+#pragma unroll
+                for (int k = 0; k < CDIM; ++k) pix_out[k] += cv[k] * vis;
+            } else {
+                const float *c_ptr = colors + (size_t)__float_as_int(rb.z) * channels;
+#pragma unroll
+                for (int k = 0; k < CDIM; ++k)
+                    if (k < (int)channels) pix_out[k] += __ldg(c_ptr + k) * vis;
+            }
+            cur_idx = batch_start + t;
+            T = next_T;
+        }
+    }
+
+    if (inside) {
+        render_alphas[pix] = 1.f - T;
+#pragma unroll
+        for (int k = 0; k < CDIM; ++k)
+            if (k < (int)channels)
+                render_colors[pix * channels + k] =
+                    backgrounds == nullptr ? pix_out[k] : (pix_out[k] + T * backgrounds[k]);
+        last_ids[pix] = (int32_t)cur_idx;
+    }
+}
+
+template <int CDIM>
+static int launch_fwd(uint32_t C, uint64_t n_isects, uint32_t channels, const float *means2d, const float *conics,
+                      const float *colors, const float *opacities, const float *backgrounds, const uint8_t *masks,
+                      uint32_t W, uint32_t H, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+                      const int32_t *tile_offsets, const int32_t *flatten_ids, float *render_colors,
+                      float *render_alphas, int32_t *last_ids, cudaStream_t st) {
+    const uint32_t threads = ((tile_size * tile_size + 31) / 32) * 32;
+    const uint32_t grid = C * tile_width * tile_height;
+    const size_t smem = (size_t)threads * sizeof(float4) * (CDIM <= 4 ? 3 : 2);
+    if (threads <= 256) {
+        raster_fwd_kernel<CDIM, 256><<<grid, threads, smem, st>>>(
+            C, n_isects, channels, reinterpret_cast<const float2 *>(means2d), conics, colors, opacities, backgrounds,
+            masks, W, H, tile_size, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas,
+            last_ids);
+    } else {
+        raster_fwd_kernel<CDIM, 1024><<<grid, threads, smem, st>>>(
+            C, n_isects, channels, reinterpret_cast<const float2 *>(means2d), conics, colors, opacities, backgrounds,
+            masks, W, H, tile_size, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas,
+            last_ids);
+    }
+    return 0;
+}
+
+}  // namespace b2s
+
+using namespace b2s;
+
+extern "C" int b200splat_rasterize_fwd(uint32_t C, uint32_t n_gauss, uint64_t n_isects, uint32_t channels,
+                                       const float *means2d, const float *conics, const float *colors,
+                                       const float *opacities, const float *backgrounds, const uint8_t *masks,
+                                       uint32_t W, uint32_t H, uint32_t tile_size, uint32_t tile_width,
+                                       uint32_t tile_height, const int32_t *tile_offsets, const int32_t *flatten_ids,
+                                       float *render_colors, float *render_alphas, int32_t *last_ids, void *stream) {
+    const char *where = "b200splat_rasterize_fwd";
+    (void)n_gauss;
+    B2S_REQUIRE(tile_size >= 1 && tile_size <= 32, where, "tile_size must be in [1, 32]");
+    B2S_REQUIRE((uint64_t)tile_width * tile_size >= W && (uint64_t)tile_height * tile_size >= H, where,
+                "tile grid does not cover the image");
+    B2S_REQUIRE(n_isects <= 0x7fffffffull, where, "n_isects exceeds int32 offsets");
+    const int cdim = pick_cdim(channels);
+    B2S_REQUIRE(channels >= 1 && cdim > 0, where, "unsupported number of color channels (1..33)");
+    if ((uint64_t)C * tile_width * tile_height == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+#define B2S_FWD(D)                                                                                                   \
+    case D:                                                                                                          \
+        launch_fwd<D>(C, n_isects, channels, means2d, conics, colors, opacities, backgrounds, masks, W, H, tile_size, \
+                      tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids,    \
+                      st);                                                                                           \
+        break;
+    switch (cdim) {
+        B2S_FWD(1) B2S_FWD(2) B2S_FWD(3) B2S_FWD(4) B2S_FWD(5) B2S_FWD(8) B2S_FWD(9) B2S_FWD(16) B2S_FWD(17)
+        B2S_FWD(32) B2S_FWD(33)
+    }
+#undef B2S_FWD
+    B2S_CHECK_LAUNCH(where);
+    return 0;
+}

@@ -1,0 +1,231 @@
+// sh.cu — spherical-harmonics colour evaluation (a5), forward and backward.
+// Replaces CS/compute_sh_fwd.cu:12-71 and CS/compute_sh_bwd.cu:13-98; the closed forms
+// are Sloan's "Efficient Spherical Harmonic Evaluation" (JCGT 2013) as used by
+// CS/spherical_harmonics.cuh:17-366, up to degree 4 (25 bases).
+//
+// Design (B200): the stage is pure HBM streaming — 12·K bytes of coefficients per
+// visible element dominate.  One thread owns one element (all three channels, so the
+// basis is evaluated once instead of three times as in the reference's
+// thread-per-channel mapping), coefficients are fetched with 128-bit read-only loads
+// when the row is 16-byte aligned, and the backward writes every byte of v_coeffs
+// exactly once (zeros included) so no separate zero-fill pass is needed; v_dirs is
+// produced without atomics.
+#include "common.cuh"
+
+namespace b2s {
+
+// Calls f(k, B, dB/dx, dB/dy, dB/dz) for every basis k < (deg+1)^2 at unit direction
+// (x,y,z).  With WITH_GRAD=false the derivative arguments are 0 and dead-code eliminated.
+template <bool WITH_GRAD, typename F>
+__device__ __forceinline__ void sh_for_each_basis(const uint32_t deg, const float x, const float y, const float z,
+                                                  F &&f) {
+    f(0, 0.2820947917738781f, 0.f, 0.f, 0.f);
+    if (deg < 1) return;
+    constexpr float c1 = 0.48860251190292f;
+    f(1, -c1 * y, 0.f, -c1, 0.f);
+    f(2, c1 * z, 0.f, 0.f, c1);
+    f(3, -c1 * x, -c1, 0.f, 0.f);
+    if (deg < 2) return;
+    const float z2 = z * z;
+    const float fTmp0B = -1.092548430592079f * z;
+    const float fC1 = x * x - y * y;
+    const float fS1 = 2.f * x * y;
+    constexpr float c2 = 0.5462742152960395f;
+    const float fC1_x = 2.f * x, fC1_y = -2.f * y, fS1_x = 2.f * y, fS1_y = 2.f * x;
+    const float pSH6 = 0.9461746957575601f * z2 - 0.3153915652525201f;
+    const float pSH6_z = 2.f * 0.9461746957575601f * z;
+    f(4, c2 * fS1, c2 * fS1_x, c2 * fS1_y, 0.f);
+    f(5, fTmp0B * y, 0.f, fTmp0B, -1.092548430592079f * y);
+    f(6, pSH6, 0.f, 0.f, pSH6_z);
+    f(7, fTmp0B * x, fTmp0B, 0.f, -1.092548430592079f * x);
+    f(8, c2 * fC1, c2 * fC1_x, c2 * fC1_y, 0.f);
+    if (deg < 3) return;
+    const float fTmp0C = -2.285228997322329f * z2 + 0.4570457994644658f;
+    const float fTmp1B = 1.445305721320277f * z;
+    const float fC2 = x * fC1 - y * fS1;
+    const float fS2 = x * fS1 + y * fC1;
+    constexpr float c3 = -0.5900435899266435f;
+    const float fTmp0C_z = -2.285228997322329f * 2.f * z;
+    const float fC2_x = fC1 + x * fC1_x - y * fS1_x;
+    const float fC2_y = x * fC1_y - fS1 - y * fS1_y;
+    const float fS2_x = fS1 + x * fS1_x + y * fC1_x;
+    const float fS2_y = x * fS1_y + fC1 + y * fC1_y;
+    const float pSH12 = z * (1.865881662950577f * z2 - 1.119528997770346f);
+    const float pSH12_z = 3.f * 1.865881662950577f * z2 - 1.119528997770346f;
+    f(9, c3 * fS2, c3 * fS2_x, c3 * fS2_y, 0.f);
+    f(10, fTmp1B * fS1, fTmp1B * fS1_x, fTmp1B * fS1_y, 1.445305721320277f * fS1);
+    f(11, fTmp0C * y, 0.f, fTmp0C, fTmp0C_z * y);
+    f(12, pSH12, 0.f, 0.f, pSH12_z);
+    f(13, fTmp0C * x, fTmp0C, 0.f, fTmp0C_z * x);
+    f(14, fTmp1B * fC1, fTmp1B * fC1_x, fTmp1B * fC1_y, 1.445305721320277f * fC1);
+    f(15, c3 * fC2, c3 * fC2_x, c3 * fC2_y, 0.f);
+    if (deg < 4) return;
+    const float fTmp0D = z * (-4.683325804901025f * z2 + 2.007139630671868f);
+    const float fTmp1C = 3.31161143515146f * z2 - 0.47308734787878f;
+    const float fTmp2B = -1.770130769779931f * z;
+    const float fC3 = x * fC2 - y * fS2;
+    const float fS3 = x * fS2 + y * fC2;
+    constexpr float c4 = 0.6258357354491763f;
+    const float fTmp0D_z = 3.f * -4.683325804901025f * z2 + 2.007139630671868f;
+    const float fTmp1C_z = 2.f * 3.31161143515146f * z;
+    const float fC3_x = fC2 + x * fC2_x - y * fS2_x;
+    const float fC3_y = x * fC2_y - fS2 - y * fS2_y;
+    const float fS3_x = fS2 + y * fC2_x + x * fS2_x;
+    const float fS3_y = x * fS2_y + fC2 + y * fC2_y;
+    const float pSH20 = 1.984313483298443f * z * pSH12 - 1.006230589874905f * pSH6;
+    const float pSH20_z = 1.984313483298443f * (pSH12 + z * pSH12_z) - 1.006230589874905f * pSH6_z;
+    f(16, c4 * fS3, c4 * fS3_x, c4 * fS3_y, 0.f);
+    f(17, fTmp2B * fS2, fTmp2B * fS2_x, fTmp2B * fS2_y, -1.770130769779931f * fS2);
+    f(18, fTmp1C * fS1, fTmp1C * fS1_x, fTmp1C * fS1_y, fTmp1C_z * fS1);
+    f(19, fTmp0D * y, 0.f, fTmp0D, fTmp0D_z * y);
+    f(20, pSH20, 0.f, 0.f, pSH20_z);
+    f(21, fTmp0D * x, fTmp0D, 0.f, fTmp0D_z * x);
+    f(22, fTmp1C * fC1, fTmp1C * fC1_x, fTmp1C * fC1_y, fTmp1C_z * fC1);
+    f(23, fTmp2B * fC2, fTmp2B * fC2_x, fTmp2B * fC2_y, -1.770130769779931f * fC2);
+    f(24, c4 * fC3, c4 * fC3_x, c4 * fC3_y, 0.f);
+}
+
+// Row loader: 3*NB floats of one coefficient row into registers (128-bit loads when the
+// row start is 16-byte aligned and the length is a multiple of 4).
+template <int NB>
+__device__ __forceinline__ void load_row(const float *__restrict__ row, float (&c)[NB * 3], bool vec_ok) {
+    if ((NB * 3) % 4 == 0 && vec_ok) {
+        const float4 *p = reinterpret_cast<const float4 *>(row);
+#pragma unroll
+        for (int k = 0; k < NB * 3 / 4; k++) {
+            const float4 q = __ldg(p + k);
+            c[4 * k] = q.x; c[4 * k + 1] = q.y; c[4 * k + 2] = q.z; c[4 * k + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < NB * 3; k++) c[k] = __ldg(row + k);
+    }
+}
+
+// NB = number of active bases = (deg+1)^2 (compile time: 1,4,9,16,25).
+template <int NB>
+__global__ void __launch_bounds__(kThreads)
+sh_fwd_kernel(uint32_t n_elems, uint32_t n_rows, uint32_t K, uint32_t deg, const float *__restrict__ dirs,
+              const float *__restrict__ coeffs, const uint8_t *__restrict__ masks, float *__restrict__ colors) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_elems) return;
+    if (masks != nullptr && !masks[e]) return;
+    const uint32_t row_id = (n_rows == n_elems) ? e : (e % n_rows);
+    const float *row = coeffs + (size_t)row_id * K * 3;
+    float c[NB * 3];
+    load_row<NB>(row, c, ((K * 3) % 4 == 0) && ((reinterpret_cast<uintptr_t>(coeffs) & 15) == 0));
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (NB > 1) {
+        const float dx = dirs[3 * (size_t)e], dy = dirs[3 * (size_t)e + 1], dz = dirs[3 * (size_t)e + 2];
+        const float inorm = rsqrtf(dx * dx + dy * dy + dz * dz);
+        x = dx * inorm; y = dy * inorm; z = dz * inorm;
+    }
+    float r = 0.f, g = 0.f, b = 0.f;
+    sh_for_each_basis<false>(deg, x, y, z, [&](int k, float B, float, float, float) {
+        r += B * c[3 * k]; g += B * c[3 * k + 1]; b += B * c[3 * k + 2];
+    });
+    colors[3 * (size_t)e] = r; colors[3 * (size_t)e + 1] = g; colors[3 * (size_t)e + 2] = b;
+}
+
+template <int NB>
+__global__ void __launch_bounds__(kThreads)
+sh_bwd_kernel(uint32_t n_elems, uint32_t n_rows, uint32_t K, uint32_t deg, const float *__restrict__ dirs,
+              const float *__restrict__ coeffs, const uint8_t *__restrict__ masks,
+              const float *__restrict__ v_colors, float *__restrict__ v_coeffs, float *__restrict__ v_dirs) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_elems) return;
+    float *vrow = v_coeffs + (size_t)e * K * 3;
+    const bool vec_ok_out = ((K * 3) % 4 == 0) && ((reinterpret_cast<uintptr_t>(v_coeffs) & 15) == 0);
+    const bool active = (masks == nullptr) || masks[e];
+    float vc[NB * 3];
+    float vx = 0.f, vy = 0.f, vz = 0.f;
+    if (active) {
+        const float vr = v_colors[3 * (size_t)e], vg = v_colors[3 * (size_t)e + 1], vb = v_colors[3 * (size_t)e + 2];
+        float x = 0.f, y = 0.f, z = 0.f, inorm = 0.f;
+        if (NB > 1) {
+            const float dx = dirs[3 * (size_t)e], dy = dirs[3 * (size_t)e + 1], dz = dirs[3 * (size_t)e + 2];
+            inorm = rsqrtf(dx * dx + dy * dy + dz * dz);
+            x = dx * inorm; y = dy * inorm; z = dz * inorm;
+        }
+        if (v_dirs != nullptr && NB > 1) {
+            const uint32_t row_id = (n_rows == n_elems) ? e : (e % n_rows);
+            float c[NB * 3];
+            load_row<NB>(coeffs + (size_t)row_id * K * 3, c,
+                         ((K * 3) % 4 == 0) && ((reinterpret_cast<uintptr_t>(coeffs) & 15) == 0));
+            sh_for_each_basis<true>(deg, x, y, z, [&](int k, float B, float Bx, float By, float Bz) {
+                vc[3 * k] = B * vr; vc[3 * k + 1] = B * vg; vc[3 * k + 2] = B * vb;
+                const float w = c[3 * k] * vr + c[3 * k + 1] * vg + c[3 * k + 2] * vb;
+                vx += Bx * w; vy += By * w; vz += Bz * w;
+            });
+            // d(dir/|dir|)/d(dir): tangent-plane projection scaled by 1/|dir|
+            const float d = vx * x + vy * y + vz * z;
+            vx = (vx - d * x) * inorm; vy = (vy - d * y) * inorm; vz = (vz - d * z) * inorm;
+        } else {
+            sh_for_each_basis<false>(deg, x, y, z, [&](int k, float B, float, float, float) {
+                vc[3 * k] = B * vr; vc[3 * k + 1] = B * vg; vc[3 * k + 2] = B * vb;
+            });
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < NB * 3; k++) vc[k] = 0.f;
+    }
+    // write the whole row: active bases, then zeros up to K
+    if ((NB * 3) % 4 == 0 && vec_ok_out) {
+        float4 *o = reinterpret_cast<float4 *>(vrow);
+#pragma unroll
+        for (int k = 0; k < NB * 3 / 4; k++) __stcs(o + k, make_float4(vc[4 * k], vc[4 * k + 1], vc[4 * k + 2], vc[4 * k + 3]));
+        for (uint32_t k = NB * 3 / 4; k < K * 3 / 4; k++) __stcs(o + k, make_float4(0.f, 0.f, 0.f, 0.f));
+    } else {
+#pragma unroll
+        for (int k = 0; k < NB * 3; k++) vrow[k] = vc[k];
+        for (uint32_t k = NB * 3; k < K * 3; k++) vrow[k] = 0.f;
+    }
+    if (v_dirs != nullptr) {
+        v_dirs[3 * (size_t)e] = vx; v_dirs[3 * (size_t)e + 1] = vy; v_dirs[3 * (size_t)e + 2] = vz;
+    }
+}
+
+}  // namespace b2s
+
+using namespace b2s;
+
+extern "C" int b200splat_sh_fwd(uint32_t n_elems, uint32_t n_rows, uint32_t K, uint32_t deg, const float *dirs,
+                                const float *coeffs, const uint8_t *masks, float *colors, void *stream) {
+    const char *where = "b200splat_sh_fwd";
+    B2S_REQUIRE(deg <= 4, where, "degrees_to_use must be <= 4");
+    B2S_REQUIRE((deg + 1) * (deg + 1) <= K, where, "K too small for degrees_to_use");
+    if (n_elems == 0) return 0;
+    B2S_REQUIRE(n_rows > 0 && n_elems % n_rows == 0, where, "n_elems must be a multiple of n_coeff_rows");
+    const unsigned grid = div_up(n_elems, kThreads);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (deg) {
+        case 0: sh_fwd_kernel<1><<<grid, kThreads, 0, st>>>(n_elems, n_rows, K, deg, dirs, coeffs, masks, colors); break;
+        case 1: sh_fwd_kernel<4><<<grid, kThreads, 0, st>>>(n_elems, n_rows, K, deg, dirs, coeffs, masks, colors); break;
+        case 2: sh_fwd_kernel<9><<<grid, kThreads, 0, st>>>(n_elems, n_rows, K, deg, dirs, coeffs, masks, colors); break;
+        case 3: sh_fwd_kernel<16><<<grid, kThreads, 0, st>>>(n_elems, n_rows, K, deg, dirs, coeffs, masks, colors); break;
+        default: sh_fwd_kernel<25><<<grid, kThreads, 0, st>>>(n_elems, n_rows, K, deg, dirs, coeffs, masks, colors); break;
+    }
+    B2S_CHECK_LAUNCH(where);
+    return 0;
+}
+
+extern "C" int b200splat_sh_bwd(uint32_t n_elems, uint32_t n_rows, uint32_t K, uint32_t deg, const float *dirs,
+                                const float *coeffs, const uint8_t *masks, const float *v_colors, float *v_coeffs,
+                                float *v_dirs, void *stream) {
+    const char *where = "b200splat_sh_bwd";
+    B2S_REQUIRE(deg <= 4, where, "degrees_to_use must be <= 4");
+    B2S_REQUIRE((deg + 1) * (deg + 1) <= K, where, "K too small for degrees_to_use");
+    if (n_elems == 0) return 0;
+    B2S_REQUIRE(n_rows > 0 && n_elems % n_rows == 0, where, "n_elems must be a multiple of n_coeff_rows");
+    const unsigned grid = div_up(n_elems, kThreads);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (deg) {
+        case 0: sh_bwd_kernel<1><<<grid, kThreads, 0, st>>>(n_elems, n_rows, K, deg, dirs, coeffs, masks, v_colors, v_coeffs, v_dirs); break;
+        case 1: sh_bwd_kernel<4><<<grid, kThreads, 0, st>>>(n_elems, n_rows, K, deg, dirs, coeffs, masks, v_colors, v_coeffs, v_dirs); break;
+        case 2: sh_bwd_kernel<9><<<grid, kThreads, 0, st>>>(n_elems, n_rows, K, deg, dirs, coeffs, masks, v_colors, v_coeffs, v_dirs); break;
+        case 3: sh_bwd_kernel<16><<<grid, kThreads, 0, st>>>(n_elems, n_rows, K, deg, dirs, coeffs, masks, v_colors, v_coeffs, v_dirs); break;
+        default: sh_bwd_kernel<25><<<grid, kThreads, 0, st>>>(n_elems, n_rows, K, deg, dirs, coeffs, masks, v_colors, v_coeffs, v_dirs); break;
+    }
+    B2S_CHECK_LAUNCH(where);
+    return 0;
+}

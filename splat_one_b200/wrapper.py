@@ -1,0 +1,626 @@
+"""Python operator API of the hot path — the drop-in for `gsplat/cuda/_wrapper.py`.
+
+Same names, positional order, defaults, shape asserts, return arity and exception
+types as the reference (G = /root/reference/submodules/gsplat/gsplat):
+
+    spherical_harmonics      G/cuda/_wrapper.py:47-73     (+ _SphericalHarmonics :1226-1256)
+    fully_fused_projection   G/cuda/_wrapper.py:203-339   (+ _FullyFusedProjection :775-898,
+                                                            _FullyFusedProjectionPacked :1031-1223)
+    isect_tiles              G/cuda/_wrapper.py:342-413
+    isect_offset_encode      G/cuda/_wrapper.py:416-433
+    rasterize_to_pixels      G/cuda/_wrapper.py:436-568   (+ _RasterizeToPixels :901-1028)
+
+Every tensor (outputs, gradients, scan/sort workspaces) is allocated here with torch so
+memory stays under the caching allocator and the current stream; the native library
+owns nothing.  There is no CPU path: non-CUDA inputs raise RuntimeError like the
+reference's TORCH_CHECK (CS/bindings.h:10-16).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+from typing_extensions import Literal
+
+from ._lib import check, get_lib
+
+CAMERA_MODELS = {"pinhole": 0, "ortho": 1, "fisheye": 2, "spherical": 3}  # CS/bindings.h:34-40
+
+# compiled channel instances of the raster kernels (csrc/raster_common.cuh pick_cdim)
+_MAX_NATIVE_CHANNELS = 33
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device: torch.device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _check_cuda(*tensors: Optional[Tensor]) -> None:
+    """GSPLAT_CHECK_INPUT: CUDA + contiguous + fp32/int dtype (CS/bindings.h:10-16)."""
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("b200splat: tensor must be a CUDA tensor (no CPU fallback exists)")
+        if not t.is_contiguous():
+            raise RuntimeError("b200splat: tensor must be contiguous")
+
+
+def _f32(t: Optional[Tensor]) -> Optional[Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"b200splat: expected float32, got {t.dtype}")
+    return t
+
+
+def _aligned16(t: Optional[Tensor]) -> Optional[Tensor]:
+    """128-bit loads need 16-byte aligned bases; views into odd offsets are re-packed."""
+    if t is None or t.data_ptr() % 16 == 0:
+        return t
+    return t.clone(memory_format=torch.contiguous_format)
+
+
+# ----------------------------------------------------------------------------------------
+# spherical harmonics (a5)
+# ----------------------------------------------------------------------------------------
+def spherical_harmonics(
+    degrees_to_use: int,
+    dirs: Tensor,  # [..., 3]
+    coeffs: Tensor,  # [..., K, 3]
+    masks: Optional[Tensor] = None,
+) -> Tensor:
+    """Computes spherical harmonics (G/cuda/_wrapper.py:47-73).
+
+    Returns colours [..., 3].  Masked-out elements are zero (the reference leaves them
+    uninitialised, CS/compute_sh_fwd.cu:55).
+    """
+    assert (degrees_to_use + 1) ** 2 <= coeffs.shape[-2], coeffs.shape
+    assert dirs.shape[:-1] == coeffs.shape[:-2], (dirs.shape, coeffs.shape)
+    assert dirs.shape[-1] == 3, dirs.shape
+    assert coeffs.shape[-1] == 3, coeffs.shape
+    if masks is not None:
+        assert masks.shape == dirs.shape[:-1], masks.shape
+        masks = masks.contiguous()
+    # An `expand`ed [C,N,K,3] view of a [N,K,3] table (rendering.py:386) is passed through
+    # as the table itself: the kernel indexes it modulo N instead of materialising C copies.
+    table = _unexpanded_table(coeffs)
+    if table is not None:
+        return _SphericalHarmonics.apply(degrees_to_use, dirs.contiguous(), table.contiguous(), masks, True)
+    return _SphericalHarmonics.apply(degrees_to_use, dirs.contiguous(), coeffs.contiguous(), masks, False)
+
+
+def spherical_harmonics_table(degrees_to_use: int, dirs: Tensor, table: Tensor,
+                              masks: Optional[Tensor] = None) -> Tensor:
+    """SH colours of C view-direction sets [C,N,3] against ONE coefficient table [N,K,3].
+
+    Same result as `spherical_harmonics(deg, dirs, table.expand(C, -1, -1, -1), masks)` —
+    what rendering.py:386-390 computes — without the C-fold copy the reference's
+    `.contiguous()` makes (G/cuda/_wrapper.py:71-73) and with the coefficient gradient
+    reduced over cameras in the backward."""
+    assert dirs.dim() == 3 and table.dim() == 3, (dirs.shape, table.shape)
+    assert (degrees_to_use + 1) ** 2 <= table.shape[-2], table.shape
+    assert dirs.shape[1] == table.shape[0] and dirs.shape[-1] == 3 and table.shape[-1] == 3
+    if masks is not None:
+        assert masks.shape == dirs.shape[:-1], masks.shape
+        masks = masks.contiguous()
+    return _SphericalHarmonics.apply(degrees_to_use, dirs.contiguous(), table.contiguous(), masks, True)
+
+
+def _unexpanded_table(coeffs: Tensor) -> Optional[Tensor]:
+    """If `coeffs` [C,N,K,3] is a stride-0 broadcast of a [N,K,3] tensor, return that view."""
+    if coeffs.dim() == 4 and coeffs.shape[0] > 1 and coeffs.stride(0) == 0:
+        return coeffs[0]
+    return None
+
+
+class _SphericalHarmonics(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sh_degree: int, dirs: Tensor, coeffs: Tensor, masks: Optional[Tensor], broadcast: bool):
+        _check_cuda(dirs, coeffs, masks)
+        _f32(dirs), _f32(coeffs)
+        lib = get_lib()
+        K = coeffs.shape[-2]
+        n_elems = dirs.numel() // 3
+        n_rows = coeffs.numel() // (K * 3)
+        colors = torch.zeros_like(dirs)
+        if masks is not None and masks.dtype != torch.bool:
+            masks = masks != 0
+        if n_elems:
+            with torch.cuda.device(dirs.device):
+                check(lib.b200splat_sh_fwd(n_elems, n_rows, K, sh_degree, _ptr(dirs), _ptr(coeffs), _ptr(masks),
+                                           _ptr(colors), _stream(dirs.device)), lib)
+        ctx.save_for_backward(dirs, coeffs, masks)
+        ctx.sh_degree = sh_degree
+        ctx.num_bases = K
+        ctx.broadcast = broadcast
+        return colors
+
+    @staticmethod
+    def backward(ctx, v_colors: Tensor):
+        dirs, coeffs, masks = ctx.saved_tensors
+        lib = get_lib()
+        K = ctx.num_bases
+        n_elems = dirs.numel() // 3
+        n_rows = coeffs.numel() // (K * 3)
+        compute_v_dirs = ctx.needs_input_grad[1]
+        v_colors = v_colors.contiguous()
+        v_coeffs = torch.empty(dirs.shape[:-1] + (K, 3), device=dirs.device, dtype=dirs.dtype)
+        v_dirs = torch.empty_like(dirs) if compute_v_dirs else None
+        if n_elems:
+            with torch.cuda.device(dirs.device):
+                check(lib.b200splat_sh_bwd(n_elems, n_rows, K, ctx.sh_degree, _ptr(dirs), _ptr(coeffs), _ptr(masks),
+                                           _ptr(v_colors), _ptr(v_coeffs), _ptr(v_dirs), _stream(dirs.device)), lib)
+        if ctx.broadcast:
+            v_coeffs = v_coeffs[0] if v_coeffs.shape[0] == 1 else v_coeffs.sum(dim=0)
+        if not ctx.needs_input_grad[2]:
+            v_coeffs = None
+        return None, v_dirs, v_coeffs, None, None
+
+
+# ----------------------------------------------------------------------------------------
+# projection (a2, a3, a4)
+# ----------------------------------------------------------------------------------------
+def fully_fused_projection(
+    means: Tensor,  # [N, 3]
+    covars: Optional[Tensor],  # [N, 6] or None
+    quats: Optional[Tensor],  # [N, 4] or None
+    scales: Optional[Tensor],  # [N, 3] or None
+    viewmats: Tensor,  # [C, 4, 4]
+    Ks: Tensor,  # [C, 3, 3]
+    width: int,
+    height: int,
+    eps2d: float = 0.3,
+    near_plane: float = 0.01,
+    far_plane: float = 1e10,
+    radius_clip: float = 0.0,
+    packed: bool = False,
+    sparse_grad: bool = False,
+    calc_compensations: bool = False,
+    camera_model: Literal["pinhole", "ortho", "fisheye", "spherical"] = "pinhole",
+) -> Tuple[Tensor, ...]:
+    """Projects Gaussians to 2D (G/cuda/_wrapper.py:203-339).
+
+    packed=False: (radii [C,N] int32, means2d [C,N,2], depths [C,N], conics [C,N,3],
+    compensations [C,N] | None).  packed=True: (camera_ids, gaussian_ids [nnz] int64, radii,
+    means2d, depths, conics, compensations) in (camera, gaussian) row-major order.
+    """
+    C = viewmats.size(0)
+    N = means.size(0)
+    assert means.size() == (N, 3), means.size()
+    assert viewmats.size() == (C, 4, 4), viewmats.size()
+    assert Ks.size() == (C, 3, 3), Ks.size()
+    means = means.contiguous()
+    if covars is not None:
+        assert covars.size() == (N, 6), covars.size()
+        covars = covars.contiguous()
+    else:
+        assert quats is not None, "covars or quats is required"
+        assert scales is not None, "covars or scales is required"
+        assert quats.size() == (N, 4), quats.size()
+        assert scales.size() == (N, 3), scales.size()
+        quats = quats.contiguous()
+        scales = scales.contiguous()
+    if sparse_grad:
+        assert packed, "sparse_grad is only supported when packed is True"
+    if camera_model not in CAMERA_MODELS:
+        raise AttributeError(f"CameraModelType has no member {camera_model.upper()!r}")
+
+    viewmats = viewmats.contiguous()
+    Ks = Ks.contiguous()
+    if packed:
+        return _FullyFusedProjectionPacked.apply(
+            means, covars, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
+            radius_clip, sparse_grad, calc_compensations, camera_model)
+    return _FullyFusedProjection.apply(
+        means, covars, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
+        radius_clip, calc_compensations, camera_model)
+
+
+class _FullyFusedProjection(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means, covars, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
+                radius_clip, calc_compensations, camera_model="pinhole"):
+        _check_cuda(means, covars, quats, scales, viewmats, Ks)
+        for t in (means, covars, quats, scales, viewmats, Ks):
+            _f32(t)
+        lib = get_lib()
+        quats = _aligned16(quats)
+        C, N = viewmats.shape[0], means.shape[0]
+        dev = means.device
+        radii = torch.zeros((C, N), device=dev, dtype=torch.int32)
+        means2d = torch.zeros((C, N, 2), device=dev, dtype=torch.float32)
+        depths = torch.zeros((C, N), device=dev, dtype=torch.float32)
+        conics = torch.zeros((C, N, 3), device=dev, dtype=torch.float32)
+        compensations = torch.zeros((C, N), device=dev, dtype=torch.float32) if calc_compensations else None
+        if C and N:
+            with torch.cuda.device(dev):
+                check(lib.b200splat_projection_fwd(
+                    C, N, _ptr(means), _ptr(covars), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks),
+                    width, height, eps2d, near_plane, far_plane, radius_clip, CAMERA_MODELS[camera_model],
+                    _ptr(radii), _ptr(means2d), _ptr(depths), _ptr(conics), _ptr(compensations), _stream(dev)), lib)
+        ctx.save_for_backward(means, covars, quats, scales, viewmats, Ks, radii, conics, compensations)
+        ctx.width, ctx.height, ctx.eps2d = width, height, eps2d
+        ctx.camera_model = CAMERA_MODELS[camera_model]
+        ctx.mark_non_differentiable(radii)
+        return radii, means2d, depths, conics, compensations
+
+    @staticmethod
+    def backward(ctx, v_radii, v_means2d, v_depths, v_conics, v_compensations):
+        means, covars, quats, scales, viewmats, Ks, radii, conics, compensations = ctx.saved_tensors
+        lib = get_lib()
+        C, N = viewmats.shape[0], means.shape[0]
+        dev = means.device
+        if compensations is None:
+            v_compensations = None
+        elif v_compensations is not None:
+            v_compensations = v_compensations.contiguous()
+        v_means = torch.empty_like(means)
+        v_covars = torch.empty_like(covars) if covars is not None else None
+        v_quats = torch.empty_like(quats) if covars is None else None
+        v_scales = torch.empty_like(scales) if covars is None else None
+        v_viewmats = torch.zeros_like(viewmats) if ctx.needs_input_grad[4] else None
+        if N:
+            with torch.cuda.device(dev):
+                check(lib.b200splat_projection_bwd(
+                    C, N, _ptr(means), _ptr(covars), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks),
+                    ctx.width, ctx.height, ctx.eps2d, ctx.camera_model, _ptr(radii), _ptr(conics),
+                    _ptr(compensations), _ptr(v_means2d.contiguous()), _ptr(v_depths.contiguous()),
+                    _ptr(v_conics.contiguous()), _ptr(v_compensations), _ptr(v_means), _ptr(v_covars),
+                    _ptr(v_quats), _ptr(v_scales), _ptr(v_viewmats), _stream(dev)), lib)
+        need = ctx.needs_input_grad
+        return (v_means if need[0] else None, v_covars if need[1] else None, v_quats if need[2] else None,
+                v_scales if need[3] else None, v_viewmats if need[4] else None,
+                None, None, None, None, None, None, None, None, None, None)
+
+
+class _FullyFusedProjectionPacked(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means, covars, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
+                radius_clip, sparse_grad, calc_compensations, camera_model="pinhole"):
+        _check_cuda(means, covars, quats, scales, viewmats, Ks)
+        for t in (means, covars, quats, scales, viewmats, Ks):
+            _f32(t)
+        lib = get_lib()
+        quats = _aligned16(quats)
+        C, N = viewmats.shape[0], means.shape[0]
+        dev = means.device
+        cm = CAMERA_MODELS[camera_model]
+        nnz = 0
+        block_accum = None
+        if C and N:
+            block_accum = torch.empty((C * ((N + 255) // 256),), device=dev, dtype=torch.int32)
+            nnz_dev = torch.empty((1,), device=dev, dtype=torch.int32)
+            with torch.cuda.device(dev):
+                check(lib.b200splat_projection_packed_count(
+                    C, N, _ptr(means), _ptr(covars), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks),
+                    width, height, eps2d, near_plane, far_plane, radius_clip, cm, _ptr(block_accum),
+                    _ptr(nnz_dev), _stream(dev)), lib)
+            nnz = int(nnz_dev.item())  # the one host sync (CS/...packed_fwd.cu:352-353)
+        indptr = torch.zeros((C + 1,), device=dev, dtype=torch.int32)
+        camera_ids = torch.empty((nnz,), device=dev, dtype=torch.int64)
+        gaussian_ids = torch.empty((nnz,), device=dev, dtype=torch.int64)
+        radii = torch.empty((nnz,), device=dev, dtype=torch.int32)
+        means2d = torch.empty((nnz, 2), device=dev, dtype=torch.float32)
+        depths = torch.empty((nnz,), device=dev, dtype=torch.float32)
+        conics = torch.empty((nnz, 3), device=dev, dtype=torch.float32)
+        compensations = torch.zeros((nnz,), device=dev, dtype=torch.float32) if calc_compensations else None
+        if nnz:
+            with torch.cuda.device(dev):
+                check(lib.b200splat_projection_packed_fill(
+                    C, N, _ptr(means), _ptr(covars), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks),
+                    width, height, eps2d, near_plane, far_plane, radius_clip, cm, _ptr(block_accum),
+                    _ptr(indptr), _ptr(camera_ids), _ptr(gaussian_ids), _ptr(radii), _ptr(means2d), _ptr(depths),
+                    _ptr(conics), _ptr(compensations), _stream(dev)), lib)
+        ctx.save_for_backward(camera_ids, gaussian_ids, means, covars, quats, scales, viewmats, Ks, conics,
+                              compensations)
+        ctx.width, ctx.height, ctx.eps2d = width, height, eps2d
+        ctx.sparse_grad = sparse_grad
+        ctx.camera_model = cm
+        ctx.indptr = indptr
+        ctx.mark_non_differentiable(camera_ids, gaussian_ids, radii)
+        return camera_ids, gaussian_ids, radii, means2d, depths, conics, compensations
+
+    @staticmethod
+    def backward(ctx, v_camera_ids, v_gaussian_ids, v_radii, v_means2d, v_depths, v_conics, v_compensations):
+        (camera_ids, gaussian_ids, means, covars, quats, scales, viewmats, Ks, conics,
+         compensations) = ctx.saved_tensors
+        lib = get_lib()
+        C, N, nnz = viewmats.shape[0], means.shape[0], camera_ids.shape[0]
+        dev = means.device
+        sparse_grad = ctx.sparse_grad
+        if compensations is None:
+            v_compensations = None
+        elif v_compensations is not None:
+            v_compensations = v_compensations.contiguous()
+        rows = nnz if sparse_grad else N
+        v_means = torch.zeros((rows, 3), device=dev, dtype=torch.float32)
+        v_covars = torch.zeros((rows, 6), device=dev, dtype=torch.float32) if covars is not None else None
+        v_quats = torch.zeros((rows, 4), device=dev, dtype=torch.float32) if covars is None else None
+        v_scales = torch.zeros((rows, 3), device=dev, dtype=torch.float32) if covars is None else None
+        v_viewmats = torch.zeros_like(viewmats) if ctx.needs_input_grad[4] else None
+        if nnz:
+            with torch.cuda.device(dev):
+                check(lib.b200splat_projection_packed_bwd(
+                    C, N, nnz, _ptr(means), _ptr(covars), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks),
+                    ctx.width, ctx.height, ctx.eps2d, ctx.camera_model, _ptr(camera_ids), _ptr(gaussian_ids),
+                    _ptr(conics), _ptr(compensations), _ptr(v_means2d.contiguous()), _ptr(v_depths.contiguous()),
+                    _ptr(v_conics.contiguous()), _ptr(v_compensations), int(sparse_grad), _ptr(v_means),
+                    _ptr(v_covars), _ptr(v_quats), _ptr(v_scales), _ptr(v_viewmats), _stream(dev)), lib)
+        need = ctx.needs_input_grad
+
+        def _coo(values: Optional[Tensor], like: Optional[Tensor]):
+            # G/cuda/_wrapper.py:1163-1203
+            if values is None or not sparse_grad:
+                return values
+            return torch.sparse_coo_tensor(indices=gaussian_ids[None], values=values, size=like.size(),
+                                           is_coalesced=len(viewmats) == 1)
+
+        return (_coo(v_means, means) if need[0] else None,
+                _coo(v_covars, covars) if need[1] else None,
+                _coo(v_quats, quats) if need[2] else None,
+                _coo(v_scales, scales) if need[3] else None,
+                v_viewmats if need[4] else None,
+                None, None, None, None, None, None, None, None, None, None)
+
+
+# ----------------------------------------------------------------------------------------
+# tile intersection (a6) and offset encode (a7)
+# ----------------------------------------------------------------------------------------
+@torch.no_grad()
+def isect_tiles(
+    means2d: Tensor,  # [C, N, 2] or [nnz, 2]
+    radii: Tensor,  # [C, N] or [nnz]
+    depths: Tensor,  # [C, N] or [nnz]
+    tile_size: int,
+    tile_width: int,
+    tile_height: int,
+    sort: bool = True,
+    packed: bool = False,
+    n_cameras: Optional[int] = None,
+    camera_ids: Optional[Tensor] = None,
+    gaussian_ids: Optional[Tensor] = None,
+) -> Tuple[Tensor, Tensor, Tensor]:
+    """Maps projected Gaussians to intersecting tiles (G/cuda/_wrapper.py:342-413).
+
+    Returns (tiles_per_gauss int32 [C,N]|[nnz], isect_ids int64 [n_isects],
+    flatten_ids int32 [n_isects]); bit-exact with the reference given the same inputs.
+    """
+    if packed:
+        nnz = means2d.size(0)
+        assert means2d.shape == (nnz, 2), means2d.size()
+        assert radii.shape == (nnz,), radii.size()
+        assert depths.shape == (nnz,), depths.size()
+        assert camera_ids is not None, "camera_ids is required if packed is True"
+        assert gaussian_ids is not None, "gaussian_ids is required if packed is True"
+        assert n_cameras is not None, "n_cameras is required if packed is True"
+        camera_ids = camera_ids.contiguous()
+        gaussian_ids = gaussian_ids.contiguous()
+        C, N = n_cameras, 0
+    else:
+        C, N, _ = means2d.shape
+        assert means2d.shape == (C, N, 2), means2d.size()
+        assert radii.shape == (C, N), radii.size()
+        assert depths.shape == (C, N), depths.size()
+        nnz = 0
+
+    means2d = means2d.contiguous()
+    radii = radii.contiguous()
+    depths = depths.contiguous()
+    _check_cuda(means2d, radii, depths, camera_ids, gaussian_ids)
+    if means2d.dtype != torch.float32 or depths.dtype != torch.float32:
+        # the reference dispatches half/bf16/double and up-casts (CS/isect_tiles.cu:169-173)
+        means2d, depths = means2d.float(), depths.float()
+    if radii.dtype != torch.int32:
+        raise RuntimeError(f"b200splat: radii must be int32, got {radii.dtype}")
+    lib = get_lib()
+    dev = means2d.device
+    n_elems = nnz if packed else C * N
+    n_tiles = tile_width * tile_height
+    tile_n_bits = int(n_tiles).bit_length()  # == floor(log2(n_tiles)) + 1, CS/isect_tiles.cu:156
+    cam_n_bits = int(C).bit_length()
+    assert tile_n_bits + cam_n_bits <= 32, (tile_n_bits, cam_n_bits)
+
+    tiles_per_gauss = torch.empty(radii.shape, device=dev, dtype=torch.int32)
+    n_isects = 0
+    if n_elems:
+        cum_tiles = torch.empty((n_elems,), device=dev, dtype=torch.int64)
+        n_isects_dev = torch.empty((1,), device=dev, dtype=torch.int64)
+        ws_bytes = lib.b200splat_scan_workspace_bytes(n_elems)
+        ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
+        with torch.cuda.device(dev):
+            check(lib.b200splat_isect_count(
+                int(packed), C, N, nnz, _ptr(means2d), _ptr(radii), tile_size, tile_width, tile_height,
+                _ptr(tiles_per_gauss), _ptr(cum_tiles), _ptr(n_isects_dev), _ptr(ws), ws_bytes, _stream(dev)), lib)
+        n_isects = int(n_isects_dev.item())  # the one host sync (CS/isect_tiles.cu:201)
+
+    isect_ids = torch.empty((n_isects,), device=dev, dtype=torch.int64)
+    flatten_ids = torch.empty((n_isects,), device=dev, dtype=torch.int32)
+    if n_isects:
+        with torch.cuda.device(dev):
+            check(lib.b200splat_isect_fill(
+                int(packed), C, N, nnz, _ptr(camera_ids), _ptr(means2d), _ptr(radii), _ptr(depths),
+                _ptr(cum_tiles), tile_size, tile_width, tile_height, _ptr(isect_ids), _ptr(flatten_ids),
+                _stream(dev)), lib)
+        if sort:
+            isect_ids_alt = torch.empty_like(isect_ids)
+            flatten_ids_alt = torch.empty_like(flatten_ids)
+            ws_bytes = lib.b200splat_sort_workspace_bytes(n_isects)
+            ws = torch.empty((max(ws_bytes, 1),), device=dev, dtype=torch.uint8)
+            selector = ctypes.c_int(0)
+            with torch.cuda.device(dev):
+                check(lib.b200splat_isect_sort(
+                    n_isects, 32 + tile_n_bits + cam_n_bits, _ptr(isect_ids), _ptr(flatten_ids),
+                    _ptr(isect_ids_alt), _ptr(flatten_ids_alt), _ptr(ws), ws_bytes, ctypes.byref(selector),
+                    _stream(dev)), lib)
+            if selector.value == 1:
+                isect_ids, flatten_ids = isect_ids_alt, flatten_ids_alt
+    return tiles_per_gauss, isect_ids, flatten_ids
+
+
+@torch.no_grad()
+def isect_offset_encode(isect_ids: Tensor, n_cameras: int, tile_width: int, tile_height: int) -> Tensor:
+    """Encodes intersection ids to offsets [C, tile_height, tile_width] int32
+    (G/cuda/_wrapper.py:416-433)."""
+    isect_ids = isect_ids.contiguous()
+    _check_cuda(isect_ids)
+    if isect_ids.dtype != torch.int64:
+        raise RuntimeError(f"b200splat: isect_ids must be int64, got {isect_ids.dtype}")
+    lib = get_lib()
+    dev = isect_ids.device
+    offsets = torch.empty((n_cameras, tile_height, tile_width), device=dev, dtype=torch.int32)
+    if offsets.numel():
+        with torch.cuda.device(dev):
+            check(lib.b200splat_isect_offset_encode(isect_ids.numel(), _ptr(isect_ids), n_cameras, tile_width,
+                                                    tile_height, _ptr(offsets), _stream(dev)), lib)
+    return offsets
+
+
+# ----------------------------------------------------------------------------------------
+# rasterization (a8, a9)
+# ----------------------------------------------------------------------------------------
+def rasterize_to_pixels(
+    means2d: Tensor,  # [C, N, 2] or [nnz, 2]
+    conics: Tensor,  # [C, N, 3] or [nnz, 3]
+    colors: Tensor,  # [C, N, channels] or [nnz, channels]
+    opacities: Tensor,  # [C, N] or [nnz]
+    image_width: int,
+    image_height: int,
+    tile_size: int,
+    isect_offsets: Tensor,  # [C, tile_height, tile_width]
+    flatten_ids: Tensor,  # [n_isects]
+    backgrounds: Optional[Tensor] = None,  # [C, channels]
+    masks: Optional[Tensor] = None,  # [C, tile_height, tile_width]
+    packed: bool = False,
+    absgrad: bool = False,
+) -> Tuple[Tensor, Tensor]:
+    """Rasterizes Gaussians to pixels (G/cuda/_wrapper.py:436-568).
+
+    Returns (render_colors [C,H,W,channels], render_alphas [C,H,W,1]).
+    """
+    C = isect_offsets.size(0)
+    if packed:
+        nnz = means2d.size(0)
+        assert means2d.shape == (nnz, 2), means2d.shape
+        assert conics.shape == (nnz, 3), conics.shape
+        assert colors.shape[0] == nnz, colors.shape
+        assert opacities.shape == (nnz,), opacities.shape
+    else:
+        N = means2d.size(1)
+        assert means2d.shape == (C, N, 2), means2d.shape
+        assert conics.shape == (C, N, 3), conics.shape
+        assert colors.shape[:2] == (C, N), colors.shape
+        assert opacities.shape == (C, N), opacities.shape
+    if backgrounds is not None:
+        assert backgrounds.shape == (C, colors.shape[-1]), backgrounds.shape
+        backgrounds = backgrounds.contiguous()
+    if masks is not None:
+        assert masks.shape == isect_offsets.shape, masks.shape
+        masks = masks.contiguous()
+
+    channels = colors.shape[-1]
+    if channels > 513 or channels == 0:
+        raise ValueError(f"Unsupported number of color channels: {channels}")
+
+    tile_height, tile_width = isect_offsets.shape[1:3]
+    assert (
+        tile_height * tile_size >= image_height
+    ), f"Assert Failed: {tile_height} * {tile_size} >= {image_height}"
+    assert (
+        tile_width * tile_size >= image_width
+    ), f"Assert Failed: {tile_width} * {tile_size} >= {image_width}"
+
+    def _one(colors_, backgrounds_):
+        return _RasterizeToPixels.apply(
+            means2d.contiguous(), conics.contiguous(), colors_.contiguous(), opacities.contiguous(),
+            backgrounds_, masks, image_width, image_height, tile_size, isect_offsets.contiguous(),
+            flatten_ids.contiguous(), absgrad)
+
+    if channels <= _MAX_NATIVE_CHANNELS:
+        # the kernels take the real channel count: no zero-padding copy as in :497-541
+        return _one(colors, backgrounds)
+    # 34..513 channels: render in native-width chunks (the reference pads to 64..513-wide
+    # template instances instead); alphas are identical for every chunk.
+    outs, alphas = [], None
+    for s in range(0, channels, 32):
+        rc, ra = _one(colors[..., s:s + 32], None if backgrounds is None else backgrounds[..., s:s + 32].contiguous())
+        outs.append(rc)
+        alphas = ra if alphas is None else alphas
+    return torch.cat(outs, dim=-1), alphas
+
+
+class _RasterizeToPixels(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means2d, conics, colors, opacities, backgrounds, masks, width, height, tile_size,
+                isect_offsets, flatten_ids, absgrad):
+        _check_cuda(means2d, conics, colors, opacities, backgrounds, masks, isect_offsets, flatten_ids)
+        for t in (means2d, conics, colors, opacities, backgrounds):
+            _f32(t)
+        if isect_offsets.dtype != torch.int32 or flatten_ids.dtype != torch.int32:
+            raise RuntimeError("b200splat: isect_offsets and flatten_ids must be int32")
+        if masks is not None and masks.dtype != torch.bool:
+            raise RuntimeError("b200splat: masks must be a bool tensor")
+        lib = get_lib()
+        dev = means2d.device
+        C, tile_height, tile_width = isect_offsets.shape
+        channels = colors.shape[-1]
+        n_gauss = means2d.numel() // 2
+        n_isects = flatten_ids.numel()
+        means2d_a = _aligned16(means2d) if means2d.data_ptr() % 8 else means2d
+        render_colors = torch.empty((C, height, width, channels), device=dev, dtype=torch.float32)
+        render_alphas = torch.empty((C, height, width, 1), device=dev, dtype=torch.float32)
+        last_ids = torch.empty((C, height, width), device=dev, dtype=torch.int32)
+        if masks is not None:
+            # masked tiles never write alpha/last_ids (CS/...fwd.cu:71-77); give them defined values
+            render_alphas.zero_()
+            last_ids.zero_()
+        if render_colors.numel():
+            with torch.cuda.device(dev):
+                check(lib.b200splat_rasterize_fwd(
+                    C, n_gauss, n_isects, channels, _ptr(means2d_a), _ptr(conics), _ptr(colors), _ptr(opacities),
+                    _ptr(backgrounds), _ptr(masks), width, height, tile_size, tile_width, tile_height,
+                    _ptr(isect_offsets), _ptr(flatten_ids), _ptr(render_colors), _ptr(render_alphas),
+                    _ptr(last_ids), _stream(dev)), lib)
+        ctx.save_for_backward(means2d, conics, colors, opacities, backgrounds, masks, isect_offsets, flatten_ids,
+                              render_alphas, last_ids)
+        ctx.width, ctx.height, ctx.tile_size, ctx.absgrad = width, height, tile_size, absgrad
+        return render_colors, render_alphas
+
+    @staticmethod
+    def backward(ctx, v_render_colors: Tensor, v_render_alphas: Tensor):
+        (means2d, conics, colors, opacities, backgrounds, masks, isect_offsets, flatten_ids, render_alphas,
+         last_ids) = ctx.saved_tensors
+        lib = get_lib()
+        dev = means2d.device
+        C, tile_height, tile_width = isect_offsets.shape
+        channels = colors.shape[-1]
+        n_gauss = means2d.numel() // 2
+        n_isects = flatten_ids.numel()
+        v_render_colors = v_render_colors.contiguous()
+        v_render_alphas = v_render_alphas.contiguous()
+        v_means2d = torch.zeros_like(means2d)
+        v_conics = torch.zeros_like(conics)
+        v_colors = torch.zeros_like(colors)
+        v_opacities = torch.zeros_like(opacities)
+        v_means2d_abs = torch.zeros_like(means2d) if ctx.absgrad else None
+        means2d_a = _aligned16(means2d) if means2d.data_ptr() % 8 else means2d
+        if n_isects and render_alphas.numel():
+            with torch.cuda.device(dev):
+                check(lib.b200splat_rasterize_bwd(
+                    C, n_gauss, n_isects, channels, _ptr(means2d_a), _ptr(conics), _ptr(colors), _ptr(opacities),
+                    _ptr(backgrounds), _ptr(masks), ctx.width, ctx.height, ctx.tile_size, tile_width, tile_height,
+                    _ptr(isect_offsets), _ptr(flatten_ids), _ptr(render_alphas), _ptr(last_ids),
+                    _ptr(v_render_colors), _ptr(v_render_alphas), _ptr(v_means2d_abs), _ptr(v_means2d),
+                    _ptr(v_conics), _ptr(v_colors), _ptr(v_opacities), _stream(dev)), lib)
+        if ctx.absgrad:
+            means2d.absgrad = v_means2d_abs  # G/cuda/_wrapper.py:1005-1006
+        v_backgrounds = None
+        if ctx.needs_input_grad[4]:
+            v_backgrounds = (v_render_colors * (1.0 - render_alphas).float()).sum(dim=(1, 2))
+        return (v_means2d, v_conics, v_colors, v_opacities, v_backgrounds,
+                None, None, None, None, None, None, None)

@@ -1,0 +1,81 @@
+"""Host-side behaviour of the drop-in API that needs no GPU: shape asserts, error types
+and messages follow the reference wrappers (gsplat/cuda/_wrapper.py)."""
+import pytest
+import torch
+
+import splat_one_b200 as S
+
+
+def test_rasterization_shape_asserts():
+    N, C = 10, 1
+    ok = dict(means=torch.zeros(N, 3), quats=torch.zeros(N, 4), scales=torch.zeros(N, 3),
+              opacities=torch.zeros(N), colors=torch.zeros(N, 3), viewmats=torch.eye(4)[None],
+              Ks=torch.eye(3)[None], width=32, height=32)
+    for key, bad in [("means", torch.zeros(N, 2)), ("quats", torch.zeros(N, 3)), ("scales", torch.zeros(N, 4)),
+                     ("opacities", torch.zeros(N, 1)), ("viewmats", torch.eye(3)[None]), ("Ks", torch.eye(4)[None]),
+                     ("colors", torch.zeros(N + 1, 3))]:
+        kw = dict(ok)
+        kw[key] = bad
+        with pytest.raises(AssertionError):
+            S.rasterization(**kw)
+    with pytest.raises(AssertionError):
+        S.rasterization(**ok, render_mode="RGBD")
+    with pytest.raises(AssertionError):  # (sh_degree+1)^2 <= K
+        S.rasterization(**{**ok, "colors": torch.zeros(N, 4, 3)}, sh_degree=3)
+    with pytest.raises(NotImplementedError):
+        S.rasterization(**ok, distributed=True)
+
+
+def test_no_cpu_fallback():
+    N = 4
+    with pytest.raises(RuntimeError, match="CUDA"):
+        S.fully_fused_projection(torch.zeros(N, 3), None, torch.ones(N, 4), torch.ones(N, 3), torch.eye(4)[None],
+                                 torch.eye(3)[None], 8, 8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        S.isect_tiles(torch.zeros(1, N, 2), torch.ones(1, N, dtype=torch.int32), torch.ones(1, N), 16, 1, 1)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        S.isect_offset_encode(torch.zeros(3, dtype=torch.int64), 1, 1, 1)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        S.spherical_harmonics(0, torch.zeros(N, 3), torch.zeros(N, 1, 3))
+
+
+def test_projection_argument_checks():
+    N = 4
+    a = (torch.zeros(N, 3), None, torch.ones(N, 4), torch.ones(N, 3), torch.eye(4)[None], torch.eye(3)[None], 8, 8)
+    with pytest.raises(AssertionError, match="sparse_grad"):
+        S.fully_fused_projection(*a, sparse_grad=True, packed=False)
+    with pytest.raises(AssertionError):
+        S.fully_fused_projection(torch.zeros(N, 3), None, None, None, torch.eye(4)[None], torch.eye(3)[None], 8, 8)
+    with pytest.raises(AttributeError):  # CameraModelType has no such member (_wrapper.py:796-798)
+        S.fully_fused_projection(*a, camera_model="cylindrical")
+
+
+def test_rasterize_to_pixels_argument_checks():
+    C, N = 1, 5
+    offs = torch.zeros(C, 2, 2, dtype=torch.int32)
+    base = (torch.zeros(C, N, 2), torch.zeros(C, N, 3))
+    with pytest.raises(ValueError, match="Unsupported number of color channels"):
+        S.rasterize_to_pixels(*base, torch.zeros(C, N, 0), torch.zeros(C, N), 32, 32, 16, offs,
+                              torch.zeros(0, dtype=torch.int32))
+    with pytest.raises(ValueError, match="Unsupported number of color channels"):
+        S.rasterize_to_pixels(*base, torch.zeros(C, N, 514), torch.zeros(C, N), 32, 32, 16, offs,
+                              torch.zeros(0, dtype=torch.int32))
+    with pytest.raises(AssertionError, match="Assert Failed"):
+        S.rasterize_to_pixels(*base, torch.zeros(C, N, 3), torch.zeros(C, N), 64, 32, 16, offs,
+                              torch.zeros(0, dtype=torch.int32))
+    with pytest.raises(AssertionError):
+        S.rasterize_to_pixels(*base, torch.zeros(C, N, 3), torch.zeros(C, N), 32, 32, 16, offs,
+                              torch.zeros(0, dtype=torch.int32), backgrounds=torch.zeros(C, 4))
+
+
+def test_isect_tiles_packed_requires_ids():
+    with pytest.raises(AssertionError, match="camera_ids"):
+        S.isect_tiles(torch.zeros(3, 2), torch.ones(3, dtype=torch.int32), torch.ones(3), 16, 1, 1, packed=True,
+                      n_cameras=1)
+
+
+def test_sh_argument_checks():
+    with pytest.raises(AssertionError):
+        S.spherical_harmonics(3, torch.zeros(4, 3), torch.zeros(4, 9, 3))
+    with pytest.raises(AssertionError):
+        S.spherical_harmonics(1, torch.zeros(4, 3), torch.zeros(5, 4, 3))
