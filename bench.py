@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""Benchmark of the rasterization hot path (BASELINE.json metric):
+rendered Mpix/s, forward + backward, 1 M Gaussians / SH degree 3 / one 1920x1080 pinhole
+camera per GPU ("config B"), on 1/2/4/8 B200 with camera-sharded data parallelism.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A step = one `rasterization()` forward + `backward()` with fixed random cotangents on
+one synthetic scene, plus — for N > 1 — the all-reduce of the parameter
+gradients.  Prints ONE JSON line (see the keys below).  `--impl reference` times the CPU
+restatement of the reference (oracle/, the reference's native code being CUDA-only and
+its PyTorch `_torch_impl` having no runnable rasterizer) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+N_GAUSS = 1_000_000
+WIDTH, HEIGHT = 1920, 1080
+SH_DEGREE = 3
+WORKLOAD = "configB: 1M Gaussians, SH3, 1920x1080 pinhole, packed=False, fwd+bwd"
+# bounded CPU sample: same scene generator at 1/16 of the pixels and Gaussians (same
+# depth complexity per pixel), so a CPU step takes seconds instead of minutes
+CPU_SAMPLE = dict(n=N_GAUSS // 16, width=WIDTH // 4, height=HEIGHT // 4)
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+# ----------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference, bounded sample
+# ----------------------------------------------------------------------------------------
+def cpu_reference_step(scene, params, cot):
+    from oracle import raster_ref as RC
+    from oracle import torch_ref as O
+
+    for p in params:
+        p.grad = None
+    rc, ra, meta = O.rasterization(*params, scene["viewmats"], scene["Ks"], scene["width"], scene["height"],
+                                   sh_degree=SH_DEGREE, packed=False, raster_fn=RC.rasterize_to_pixels)
+    if cot is None:
+        g = torch.Generator().manual_seed(123)
+        cot = (torch.randn(rc.shape, generator=g), torch.randn(ra.shape, generator=g))
+    ((rc * cot[0]).sum() + (ra * cot[1]).sum()).backward()
+    return cot, meta
+
+
+def cpu_baseline(steps: int, warmup: int):
+    """Time the oracle port on the host cores. Returns (Mpix/s, ms/step, cores, sample str)."""
+    from oracle import raster_ref as RC
+    from splat_one_b200 import synthetic
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    RC.build()
+    scene = synthetic.pinhole_scene(CPU_SAMPLE["n"], CPU_SAMPLE["width"], CPU_SAMPLE["height"], seed=42,
+                                    sh_degree=SH_DEGREE)
+    params = [scene[k].clone().requires_grad_() for k in ("means", "quats", "scales", "opacities", "sh")]
+    cot = None
+    for _ in range(warmup):
+        cot, _ = cpu_reference_step(scene, params, cot)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cot, meta = cpu_reference_step(scene, params, cot)
+    dt = (time.perf_counter() - t0) / steps
+    mpix = CPU_SAMPLE["width"] * CPU_SAMPLE["height"] / dt / 1e6
+    sample = (f"{CPU_SAMPLE['n']} Gaussians @ {CPU_SAMPLE['width']}x{CPU_SAMPLE['height']} (1/16 of config B, same "
+              f"density; n_isects={meta['flatten_ids'].numel()}), oracle port: torch-CPU projection/SH/autograd + "
+              f"numpy isect + C raster fwd/bwd, {steps} steps")
+    return mpix, dt * 1e3, cores, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    mpix, ms, cores, sample = cpu_baseline(steps, max(1, min(args.warmup, 1)))
+    line = {
+        "impl": "reference", "metric": "rendered Mpix/s fwd+bwd", "value": mpix, "unit": "Mpix/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": mpix, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": mpix, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch.distributed as dist
+
+    import splat_one_b200 as S
+    from splat_one_b200 import synthetic, wrapper
+    from splat_one_b200.distributed import GradArena
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # replicated Gaussians (same seed on every rank), one camera per rank (distinct poses)
+    scene = synthetic.pinhole_scene(N_GAUSS, WIDTH, HEIGHT, seed=42, sh_degree=SH_DEGREE, n_cameras=world)
+    names = ("means", "quats", "scales", "opacities", "sh")
+    params = [scene[k].to(dev).requires_grad_() for k in names]
+    vm_host = scene["viewmats"][rank::world].contiguous().pin_memory()
+    K_host = scene["Ks"][rank::world].contiguous().pin_memory()
+    vm, Ks = vm_host.to(dev), K_host.to(dev)
+    C_local = vm.shape[0]
+    g = torch.Generator().manual_seed(1000 + rank)
+    vc_host = torch.randn(C_local, HEIGHT, WIDTH, 3, generator=g).pin_memory()
+    va_host = torch.randn(C_local, HEIGHT, WIDTH, 1, generator=g).pin_memory()
+    vc, va = vc_host.to(dev), va_host.to(dev)
+    arena = GradArena(params) if world > 1 else None
+
+    def step():
+        for p in params:
+            p.grad = None
+        rc, ra, meta = S.rasterization(*params, vm, Ks, WIDTH, HEIGHT, sh_degree=SH_DEGREE, packed=False)
+        torch.autograd.backward([rc, ra], [vc, va])
+        if arena is not None:
+            arena.gather_from_params()
+            arena.all_reduce()
+        return rc, ra, meta
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        rc, ra, meta = step()
+    barrier()
+
+    # ---- timed region: device-resident inputs --------------------------------------------
+    wrapper.profiler.reset()
+    wrapper.profiler.enabled = True
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        rc, ra, meta = step()
+    e1.record()
+    barrier()
+    wrapper.profiler.enabled = False
+    clocks = sampler.stop() if sampler else None
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    launches = wrapper.profiler.launches()
+    stages = wrapper.profiler.summary_ms()
+
+    # realised sizes for the roofline denominators
+    V = int((meta["radii"] > 0).sum())
+    I = int(meta["flatten_ids"].numel())
+    P = C_local * HEIGHT * WIDTH
+    n_pairs = None
+
+    # ---- e2e: host buffers in, image out, copies inside the timed region -----------------
+    out_c_host = torch.empty(C_local, HEIGHT, WIDTH, 3).pin_memory()
+    out_a_host = torch.empty(C_local, HEIGHT, WIDTH, 1).pin_memory()
+    gnorm_host = torch.empty(1).pin_memory()
+
+    def e2e_step():
+        vm_d = vm_host.to(dev, non_blocking=True)
+        K_d = K_host.to(dev, non_blocking=True)
+        vc_d = vc_host.to(dev, non_blocking=True)
+        va_d = va_host.to(dev, non_blocking=True)
+        for p in params:
+            p.grad = None
+        rc_, ra_, _ = S.rasterization(*params, vm_d, K_d, WIDTH, HEIGHT, sh_degree=SH_DEGREE, packed=False)
+        torch.autograd.backward([rc_, ra_], [vc_d, va_d])
+        if arena is not None:
+            arena.gather_from_params()
+            arena.all_reduce()
+        out_c_host.copy_(rc_.detach(), non_blocking=True)
+        out_a_host.copy_(ra_.detach(), non_blocking=True)
+        gnorm_host.copy_(params[0].grad.norm().reshape(1), non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = t.item() / args.steps
+    h2d = vm_host.numel() * 4 + K_host.numel() * 4 + vc_host.numel() * 4 + va_host.numel() * 4
+    d2h = out_c_host.numel() * 4 + out_a_host.numel() * 4 + 4
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        # dominant kernel = the longest native call per step
+        dom = max(stages.items(), key=lambda kv: kv[1]["total_ms"])[0] if stages else None
+        N, C = N_GAUSS, C_local
+        alg_bytes = {  # SURVEY.md §8(d), per launch
+            "projection_fwd": 40 * N + 4 * C * N + 24 * V,
+            "sh_fwd": 216 * V,
+            "isect_count": 4 * C * N + 8 * V + 4 * C * N + 8 * C * N,
+            "isect_fill": 16 * V + 8 * C * N + 12 * I,
+            "isect_sort": 24 * I,
+            "isect_offset_encode": 8 * I + 4 * (meta["isect_offsets"].numel()),
+            "rasterize_fwd": 40 * I + 20 * P,
+            "rasterize_bwd": 40 * I + 24 * P + 72 * V,
+            "sh_bwd": 228 * V + 192 * N,
+            "projection_bwd": 40 * N + 4 * C * N + 36 * V + 40 * N,
+        }
+        roof = None
+        if dom is not None:
+            dur = stages[dom]["avg_ms"] * 1e-3
+            ach = alg_bytes.get(dom, 0) / dur / 1e9
+            roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes": alg_bytes.get(dom, 0), "avg_launch_ms": stages[dom]["avg_ms"]}
+        stage_report = {k: {"avg_ms": round(v["avg_ms"], 4),
+                            "GBps": round(alg_bytes.get(k, 0) / (v["avg_ms"] * 1e-3) / 1e9, 1) if v["avg_ms"] > 0 else None}
+                        for k, v in stages.items()}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            mpix, ms, cores, sample = cpu_baseline(2, 1)
+            cpu = {"value": mpix, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample}
+        line = {
+            "metric": "rendered Mpix/s fwd+bwd", "value": world * C_local * HEIGHT * WIDTH / (ms_step * 1e-3) / 1e6,
+            "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "n_gaussians": N_GAUSS, "cameras_per_gpu": C_local,
+                       "visible_pairs": V, "n_isects": I, "l2_policy": "per-step working set ~1 GB > 126 MB L2",
+                       "parallelism": f"camera-sharded dp{world}" + (" + NCCL allreduce of 236 MB grads" if world > 1 else "")},
+            "clocks": clocks,
+            "e2e": {"value": world * C_local * HEIGHT * WIDTH / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s",
+                    "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "what": "camera + cotangent images H2D from pinned memory, rasterization()+backward, "
+                            "rendered image + alpha + grad norm D2H; Gaussians stay resident (model state)"},
+            "gpu_launches": launches,
+            "roofline": roof,
+            "stages": stage_report,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

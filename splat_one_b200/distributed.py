@@ -1,0 +1,100 @@
+"""Camera-sharded data parallelism for the rasterization path.
+
+One process per GPU (torch.distributed, NCCL over NVLink/NVSwitch).  Gaussians are
+replicated, rank r renders cameras r, r+W, r+2W, ... of the global batch with the
+single-GPU path unchanged, and the parameter gradients are summed with ONE all-reduce
+over a flat fp32 arena [means | quats | scales | opacities | sh] (59·N floats at K=16).
+This replaces — by design — the reference's Gaussian-sharded all-to-all mode
+(`distributed=True`, G/rendering.py:279-294, 394-478; helpers in G/distributed.py).
+
+The helpers work on any backend (gloo on CPU for the tests, nccl on the GPUs).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+
+def shard_cameras(viewmats: Tensor, Ks: Tensor, rank: Optional[int] = None,
+                  world_size: Optional[int] = None) -> Tuple[Tensor, Tensor, Tensor]:
+    """Cameras owned by `rank`: indices rank, rank+W, ...  Returns (viewmats, Ks, global ids)."""
+    rank = dist.get_rank() if rank is None else rank
+    world_size = dist.get_world_size() if world_size is None else world_size
+    ids = torch.arange(rank, viewmats.shape[0], world_size, device=viewmats.device)
+    return viewmats[ids].contiguous(), Ks[ids].contiguous(), ids
+
+
+class GradArena:
+    """Flat, 16-byte-segment-aligned fp32 buffer holding the gradients of a fixed list of
+    parameters, so a step needs exactly one all-reduce launch."""
+
+    def __init__(self, params: Sequence[Tensor]):
+        self.params = list(params)
+        offs, n = [], 0
+        for p in self.params:
+            assert p.dtype == torch.float32, "arena holds fp32 gradients"
+            offs.append(n)
+            n += (p.numel() + 3) // 4 * 4  # keep every segment 16-byte aligned
+        self.offsets = offs
+        self.flat = torch.zeros(n, dtype=torch.float32, device=self.params[0].device)
+        self.views = [self.flat[o:o + p.numel()].view_as(p) for o, p in zip(offs, self.params)]
+
+    @property
+    def nbytes(self) -> int:
+        return self.flat.numel() * 4
+
+    def gather_from_params(self, zero_missing: bool = True) -> None:
+        """Copy p.grad (dense or sparse COO) of every parameter into the arena."""
+        for p, v in zip(self.params, self.views):
+            g = p.grad
+            if g is None:
+                if zero_missing:
+                    v.zero_()
+                continue
+            if g.is_sparse:
+                v.zero_()
+                g = g.coalesce()
+                v.index_add_(0, g.indices()[0], g.values())
+            else:
+                v.copy_(g)
+
+    def all_reduce(self, group=None, average: bool = False, async_op: bool = False):
+        """SUM over ranks (optionally / world_size); a no-op outside a process group."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return None
+        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        if average and not async_op:
+            self.flat.div_(dist.get_world_size(group))
+        return work
+
+    def scatter_to_params(self) -> None:
+        """Point every p.grad at its arena view (no copy)."""
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+
+def allreduce_gradients(params: Sequence[Tensor], arena: Optional[GradArena] = None, group=None,
+                        average: bool = False) -> GradArena:
+    """Pack p.grad of `params` into one arena, all-reduce it, and re-attach the views."""
+    arena = arena or GradArena(params)
+    arena.gather_from_params()
+    arena.all_reduce(group=group, average=average)
+    arena.scatter_to_params()
+    return arena
+
+
+def rasterization_dp(render_fn, params: Dict[str, Tensor], viewmats: Tensor, Ks: Tensor, width: int, height: int,
+                     rank: Optional[int] = None, world_size: Optional[int] = None, **kwargs):
+    """Render this rank's share of a global camera batch.
+
+    `render_fn` is `splat_one_b200.rasterization` (or the oracle's, in CPU tests);
+    `params` holds means/quats/scales/opacities/colors.  Returns (colors, alphas, meta,
+    global camera ids of the local batch).  Intersection ids use LOCAL camera indices, as in
+    the reference's own distributed mode (G/rendering.py:417-425)."""
+    vm, k, ids = shard_cameras(viewmats, Ks, rank, world_size)
+    rc, ra, meta = render_fn(params["means"], params["quats"], params["scales"], params["opacities"],
+                             params["colors"], vm, k, width, height, **kwargs)
+    return rc, ra, meta, ids

@@ -32,6 +32,57 @@ CAMERA_MODELS = {"pinhole": 0, "ortho": 1, "fisheye": 2, "spherical": 3}  # CS/b
 _MAX_NATIVE_CHANNELS = 33
 
 
+class _Profiler:
+    """Optional per-native-call CUDA-event timing + kernel-launch counting (bench.py).
+    Disabled by default: `native()` is then a plain call."""
+
+    # kernels launched by this library per native call (csrc/*.cu); the radix sort's
+    # launches are CUB's and counted separately as "library"
+    KERNELS = {
+        "projection_fwd": 1, "projection_bwd": 1, "projection_packed_count": 3, "projection_packed_fill": 1,
+        "projection_packed_bwd": 1, "sh_fwd": 1, "sh_bwd": 1, "isect_count": 2, "isect_fill": 1,
+        "isect_sort": 0, "isect_offset_encode": 1, "rasterize_fwd": 1, "rasterize_bwd": 1,
+    }
+
+    def __init__(self):
+        self.enabled = False
+        self.reset()
+
+    def reset(self):
+        self.events = {}
+        self.calls = {}
+
+    def launches(self) -> int:
+        return sum(self.KERNELS.get(k, 0) * n for k, n in self.calls.items())
+
+    def summary_ms(self):
+        out = {}
+        for name, evs in self.events.items():
+            ts = [a.elapsed_time(b) for a, b in evs]
+            out[name] = {"calls": len(ts), "avg_ms": sum(ts) / max(len(ts), 1), "total_ms": sum(ts)}
+        return out
+
+
+profiler = _Profiler()
+
+
+def native(name: str, lib, device, *args):
+    """Call `lib.b200splat_<name>(*args, stream)` on the current stream of `device`."""
+    fn = getattr(lib, "b200splat_" + name)
+    with torch.cuda.device(device):
+        st = _stream(device)
+        if profiler.enabled:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            rc = fn(*args, st)
+            b.record()
+            profiler.events.setdefault(name, []).append((a, b))
+            profiler.calls[name] = profiler.calls.get(name, 0) + 1
+        else:
+            rc = fn(*args, st)
+    check(rc, lib)
+
+
 def _ptr(t: Optional[Tensor]):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -132,9 +183,8 @@ class _SphericalHarmonics(torch.autograd.Function):
         if masks is not None and masks.dtype != torch.bool:
             masks = masks != 0
         if n_elems:
-            with torch.cuda.device(dirs.device):
-                check(lib.b200splat_sh_fwd(n_elems, n_rows, K, sh_degree, _ptr(dirs), _ptr(coeffs), _ptr(masks),
-                                           _ptr(colors), _stream(dirs.device)), lib)
+            native("sh_fwd", lib, dirs.device, n_elems, n_rows, K, sh_degree, _ptr(dirs), _ptr(coeffs), _ptr(masks),
+                                           _ptr(colors))
         ctx.save_for_backward(dirs, coeffs, masks)
         ctx.sh_degree = sh_degree
         ctx.num_bases = K
@@ -153,9 +203,8 @@ class _SphericalHarmonics(torch.autograd.Function):
         v_coeffs = torch.empty(dirs.shape[:-1] + (K, 3), device=dirs.device, dtype=dirs.dtype)
         v_dirs = torch.empty_like(dirs) if compute_v_dirs else None
         if n_elems:
-            with torch.cuda.device(dirs.device):
-                check(lib.b200splat_sh_bwd(n_elems, n_rows, K, ctx.sh_degree, _ptr(dirs), _ptr(coeffs), _ptr(masks),
-                                           _ptr(v_colors), _ptr(v_coeffs), _ptr(v_dirs), _stream(dirs.device)), lib)
+            native("sh_bwd", lib, dirs.device, n_elems, n_rows, K, ctx.sh_degree, _ptr(dirs), _ptr(coeffs), _ptr(masks),
+                                           _ptr(v_colors), _ptr(v_coeffs), _ptr(v_dirs))
         if ctx.broadcast:
             v_coeffs = v_coeffs[0] if v_coeffs.shape[0] == 1 else v_coeffs.sum(dim=0)
         if not ctx.needs_input_grad[2]:
@@ -239,11 +288,9 @@ class _FullyFusedProjection(torch.autograd.Function):
         conics = torch.zeros((C, N, 3), device=dev, dtype=torch.float32)
         compensations = torch.zeros((C, N), device=dev, dtype=torch.float32) if calc_compensations else None
         if C and N:
-            with torch.cuda.device(dev):
-                check(lib.b200splat_projection_fwd(
-                    C, N, _ptr(means), _ptr(covars), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks),
+            native("projection_fwd", lib, dev, C, N, _ptr(means), _ptr(covars), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks),
                     width, height, eps2d, near_plane, far_plane, radius_clip, CAMERA_MODELS[camera_model],
-                    _ptr(radii), _ptr(means2d), _ptr(depths), _ptr(conics), _ptr(compensations), _stream(dev)), lib)
+                    _ptr(radii), _ptr(means2d), _ptr(depths), _ptr(conics), _ptr(compensations))
         ctx.save_for_backward(means, covars, quats, scales, viewmats, Ks, radii, conics, compensations)
         ctx.width, ctx.height, ctx.eps2d = width, height, eps2d
         ctx.camera_model = CAMERA_MODELS[camera_model]
@@ -266,13 +313,11 @@ class _FullyFusedProjection(torch.autograd.Function):
         v_scales = torch.empty_like(scales) if covars is None else None
         v_viewmats = torch.zeros_like(viewmats) if ctx.needs_input_grad[4] else None
         if N:
-            with torch.cuda.device(dev):
-                check(lib.b200splat_projection_bwd(
-                    C, N, _ptr(means), _ptr(covars), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks),
+            native("projection_bwd", lib, dev, C, N, _ptr(means), _ptr(covars), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks),
                     ctx.width, ctx.height, ctx.eps2d, ctx.camera_model, _ptr(radii), _ptr(conics),
                     _ptr(compensations), _ptr(v_means2d.contiguous()), _ptr(v_depths.contiguous()),
                     _ptr(v_conics.contiguous()), _ptr(v_compensations), _ptr(v_means), _ptr(v_covars),
-                    _ptr(v_quats), _ptr(v_scales), _ptr(v_viewmats), _stream(dev)), lib)
+                    _ptr(v_quats), _ptr(v_scales), _ptr(v_viewmats))
         need = ctx.needs_input_grad
         return (v_means if need[0] else None, v_covars if need[1] else None, v_quats if need[2] else None,
                 v_scales if need[3] else None, v_viewmats if need[4] else None,
@@ -296,11 +341,9 @@ class _FullyFusedProjectionPacked(torch.autograd.Function):
         if C and N:
             block_accum = torch.empty((C * ((N + 255) // 256),), device=dev, dtype=torch.int32)
             nnz_dev = torch.empty((1,), device=dev, dtype=torch.int32)
-            with torch.cuda.device(dev):
-                check(lib.b200splat_projection_packed_count(
-                    C, N, _ptr(means), _ptr(covars), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks),
+            native("projection_packed_count", lib, dev, C, N, _ptr(means), _ptr(covars), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks),
                     width, height, eps2d, near_plane, far_plane, radius_clip, cm, _ptr(block_accum),
-                    _ptr(nnz_dev), _stream(dev)), lib)
+                    _ptr(nnz_dev))
             nnz = int(nnz_dev.item())  # the one host sync (CS/...packed_fwd.cu:352-353)
         indptr = torch.zeros((C + 1,), device=dev, dtype=torch.int32)
         camera_ids = torch.empty((nnz,), device=dev, dtype=torch.int64)
@@ -311,12 +354,10 @@ class _FullyFusedProjectionPacked(torch.autograd.Function):
         conics = torch.empty((nnz, 3), device=dev, dtype=torch.float32)
         compensations = torch.zeros((nnz,), device=dev, dtype=torch.float32) if calc_compensations else None
         if nnz:
-            with torch.cuda.device(dev):
-                check(lib.b200splat_projection_packed_fill(
-                    C, N, _ptr(means), _ptr(covars), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks),
+            native("projection_packed_fill", lib, dev, C, N, _ptr(means), _ptr(covars), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks),
                     width, height, eps2d, near_plane, far_plane, radius_clip, cm, _ptr(block_accum),
                     _ptr(indptr), _ptr(camera_ids), _ptr(gaussian_ids), _ptr(radii), _ptr(means2d), _ptr(depths),
-                    _ptr(conics), _ptr(compensations), _stream(dev)), lib)
+                    _ptr(conics), _ptr(compensations))
         ctx.save_for_backward(camera_ids, gaussian_ids, means, covars, quats, scales, viewmats, Ks, conics,
                               compensations)
         ctx.width, ctx.height, ctx.eps2d = width, height, eps2d
@@ -345,13 +386,11 @@ class _FullyFusedProjectionPacked(torch.autograd.Function):
         v_scales = torch.zeros((rows, 3), device=dev, dtype=torch.float32) if covars is None else None
         v_viewmats = torch.zeros_like(viewmats) if ctx.needs_input_grad[4] else None
         if nnz:
-            with torch.cuda.device(dev):
-                check(lib.b200splat_projection_packed_bwd(
-                    C, N, nnz, _ptr(means), _ptr(covars), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks),
+            native("projection_packed_bwd", lib, dev, C, N, nnz, _ptr(means), _ptr(covars), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks),
                     ctx.width, ctx.height, ctx.eps2d, ctx.camera_model, _ptr(camera_ids), _ptr(gaussian_ids),
                     _ptr(conics), _ptr(compensations), _ptr(v_means2d.contiguous()), _ptr(v_depths.contiguous()),
                     _ptr(v_conics.contiguous()), _ptr(v_compensations), int(sparse_grad), _ptr(v_means),
-                    _ptr(v_covars), _ptr(v_quats), _ptr(v_scales), _ptr(v_viewmats), _stream(dev)), lib)
+                    _ptr(v_covars), _ptr(v_quats), _ptr(v_scales), _ptr(v_viewmats))
         need = ctx.needs_input_grad
 
         def _coo(values: Optional[Tensor], like: Optional[Tensor]):
@@ -433,31 +472,23 @@ def isect_tiles(
         n_isects_dev = torch.empty((1,), device=dev, dtype=torch.int64)
         ws_bytes = lib.b200splat_scan_workspace_bytes(n_elems)
         ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
-        with torch.cuda.device(dev):
-            check(lib.b200splat_isect_count(
-                int(packed), C, N, nnz, _ptr(means2d), _ptr(radii), tile_size, tile_width, tile_height,
-                _ptr(tiles_per_gauss), _ptr(cum_tiles), _ptr(n_isects_dev), _ptr(ws), ws_bytes, _stream(dev)), lib)
+        native("isect_count", lib, dev, int(packed), C, N, nnz, _ptr(means2d), _ptr(radii), tile_size, tile_width, tile_height,
+                _ptr(tiles_per_gauss), _ptr(cum_tiles), _ptr(n_isects_dev), _ptr(ws), ws_bytes)
         n_isects = int(n_isects_dev.item())  # the one host sync (CS/isect_tiles.cu:201)
 
     isect_ids = torch.empty((n_isects,), device=dev, dtype=torch.int64)
     flatten_ids = torch.empty((n_isects,), device=dev, dtype=torch.int32)
     if n_isects:
-        with torch.cuda.device(dev):
-            check(lib.b200splat_isect_fill(
-                int(packed), C, N, nnz, _ptr(camera_ids), _ptr(means2d), _ptr(radii), _ptr(depths),
-                _ptr(cum_tiles), tile_size, tile_width, tile_height, _ptr(isect_ids), _ptr(flatten_ids),
-                _stream(dev)), lib)
+        native("isect_fill", lib, dev, int(packed), C, N, nnz, _ptr(camera_ids), _ptr(means2d), _ptr(radii), _ptr(depths),
+                _ptr(cum_tiles), tile_size, tile_width, tile_height, _ptr(isect_ids), _ptr(flatten_ids))
         if sort:
             isect_ids_alt = torch.empty_like(isect_ids)
             flatten_ids_alt = torch.empty_like(flatten_ids)
             ws_bytes = lib.b200splat_sort_workspace_bytes(n_isects)
             ws = torch.empty((max(ws_bytes, 1),), device=dev, dtype=torch.uint8)
             selector = ctypes.c_int(0)
-            with torch.cuda.device(dev):
-                check(lib.b200splat_isect_sort(
-                    n_isects, 32 + tile_n_bits + cam_n_bits, _ptr(isect_ids), _ptr(flatten_ids),
-                    _ptr(isect_ids_alt), _ptr(flatten_ids_alt), _ptr(ws), ws_bytes, ctypes.byref(selector),
-                    _stream(dev)), lib)
+            native("isect_sort", lib, dev, n_isects, 32 + tile_n_bits + cam_n_bits, _ptr(isect_ids), _ptr(flatten_ids),
+                    _ptr(isect_ids_alt), _ptr(flatten_ids_alt), _ptr(ws), ws_bytes, ctypes.byref(selector))
             if selector.value == 1:
                 isect_ids, flatten_ids = isect_ids_alt, flatten_ids_alt
     return tiles_per_gauss, isect_ids, flatten_ids
@@ -475,9 +506,8 @@ def isect_offset_encode(isect_ids: Tensor, n_cameras: int, tile_width: int, tile
     dev = isect_ids.device
     offsets = torch.empty((n_cameras, tile_height, tile_width), device=dev, dtype=torch.int32)
     if offsets.numel():
-        with torch.cuda.device(dev):
-            check(lib.b200splat_isect_offset_encode(isect_ids.numel(), _ptr(isect_ids), n_cameras, tile_width,
-                                                    tile_height, _ptr(offsets), _stream(dev)), lib)
+        native("isect_offset_encode", lib, dev, isect_ids.numel(), _ptr(isect_ids), n_cameras, tile_width,
+                                                    tile_height, _ptr(offsets))
     return offsets
 
 
@@ -580,12 +610,10 @@ class _RasterizeToPixels(torch.autograd.Function):
             render_alphas.zero_()
             last_ids.zero_()
         if render_colors.numel():
-            with torch.cuda.device(dev):
-                check(lib.b200splat_rasterize_fwd(
-                    C, n_gauss, n_isects, channels, _ptr(means2d_a), _ptr(conics), _ptr(colors), _ptr(opacities),
+            native("rasterize_fwd", lib, dev, C, n_gauss, n_isects, channels, _ptr(means2d_a), _ptr(conics), _ptr(colors), _ptr(opacities),
                     _ptr(backgrounds), _ptr(masks), width, height, tile_size, tile_width, tile_height,
                     _ptr(isect_offsets), _ptr(flatten_ids), _ptr(render_colors), _ptr(render_alphas),
-                    _ptr(last_ids), _stream(dev)), lib)
+                    _ptr(last_ids))
         ctx.save_for_backward(means2d, conics, colors, opacities, backgrounds, masks, isect_offsets, flatten_ids,
                               render_alphas, last_ids)
         ctx.width, ctx.height, ctx.tile_size, ctx.absgrad = width, height, tile_size, absgrad
@@ -610,13 +638,11 @@ class _RasterizeToPixels(torch.autograd.Function):
         v_means2d_abs = torch.zeros_like(means2d) if ctx.absgrad else None
         means2d_a = _aligned16(means2d) if means2d.data_ptr() % 8 else means2d
         if n_isects and render_alphas.numel():
-            with torch.cuda.device(dev):
-                check(lib.b200splat_rasterize_bwd(
-                    C, n_gauss, n_isects, channels, _ptr(means2d_a), _ptr(conics), _ptr(colors), _ptr(opacities),
+            native("rasterize_bwd", lib, dev, C, n_gauss, n_isects, channels, _ptr(means2d_a), _ptr(conics), _ptr(colors), _ptr(opacities),
                     _ptr(backgrounds), _ptr(masks), ctx.width, ctx.height, ctx.tile_size, tile_width, tile_height,
                     _ptr(isect_offsets), _ptr(flatten_ids), _ptr(render_alphas), _ptr(last_ids),
                     _ptr(v_render_colors), _ptr(v_render_alphas), _ptr(v_means2d_abs), _ptr(v_means2d),
-                    _ptr(v_conics), _ptr(v_colors), _ptr(v_opacities), _stream(dev)), lib)
+                    _ptr(v_conics), _ptr(v_colors), _ptr(v_opacities))
         if ctx.absgrad:
             means2d.absgrad = v_means2d_abs  # G/cuda/_wrapper.py:1005-1006
         v_backgrounds = None
