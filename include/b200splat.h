@@ -208,9 +208,22 @@ B200SPLAT_API int b200splat_isect_offset_encode(
  * a8  rasterize_to_pixels_fwd            CS/bindings.h:169-185, kernel
  *     CS/rasterize_to_pixels_fwd.cu:16-186.
  * n_gauss = C*N (unpacked) or nnz (packed): number of rows of means2d/conics/colors/
- * opacities.  channels: any 1..64 (the Python wrapper chunks above that).
+ * opacities.  channels: any 1..33 (the Python wrapper chunks above that).
  * backgrounds [C,channels] / masks [C,tile_h,tile_w] (uint8/bool) may be NULL.
+ *
+ * `records` (optional, may be NULL): a packed 48-byte-per-Gaussian table built by
+ * `b200splat_rasterize_pack` (size from `b200splat_rasterize_records_bytes`, which is 0
+ * when the fast path does not apply: it needs tile_size == 16 and channels <= 4).  With
+ * records the warp-per-tile kernels run (same results); without, the generic kernels.
+ * The same table serves the forward and the backward call.
  * ---------------------------------------------------------------------------------- */
+B200SPLAT_API size_t b200splat_rasterize_records_bytes(uint32_t n_gauss, uint32_t channels, uint32_t tile_size);
+
+B200SPLAT_API int b200splat_rasterize_pack(
+    uint32_t n_gauss, uint32_t channels,
+    const float *means2d, const float *conics, const float *colors, const float *opacities,
+    void *records, void *stream);
+
 B200SPLAT_API int b200splat_rasterize_fwd(
     uint32_t C, uint32_t n_gauss, uint64_t n_isects, uint32_t channels,
     const float *means2d, const float *conics, const float *colors, const float *opacities,
@@ -218,6 +231,7 @@ B200SPLAT_API int b200splat_rasterize_fwd(
     uint32_t image_width, uint32_t image_height,
     uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
     const int32_t *tile_offsets, const int32_t *flatten_ids,
+    const void *records,
     float *render_colors, float *render_alphas, int32_t *last_ids,
     void *stream);
 
@@ -232,6 +246,7 @@ B200SPLAT_API int b200splat_rasterize_bwd(
     uint32_t image_width, uint32_t image_height,
     uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
     const int32_t *tile_offsets, const int32_t *flatten_ids,
+    const void *records,
     const float *render_alphas, const int32_t *last_ids,
     const float *v_render_colors, const float *v_render_alphas,
     float *v_means2d_abs, float *v_means2d, float *v_conics, float *v_colors,

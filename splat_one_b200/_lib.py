@@ -17,7 +17,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("B200SPLAT_LIB", _PKG / "libb200splat.so"))
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _P = c_void_p
 _U32 = c_uint32
@@ -48,10 +48,13 @@ SIGNATURES = {
     "b200splat_sort_workspace_bytes": (c_size_t, [_U64]),
     "b200splat_isect_sort": (_I, [_U64, _U32, _P, _P, _P, _P, _P, c_size_t, ctypes.POINTER(c_int), _P]),
     "b200splat_isect_offset_encode": (_I, [_U64, _P, _U32, _U32, _U32, _P, _P]),
+    "b200splat_rasterize_records_bytes": (c_size_t, [_U32, _U32, _U32]),
+    "b200splat_rasterize_pack": (_I, [_U32, _U32, _P, _P, _P, _P, _P, _P]),
     "b200splat_rasterize_fwd": (
-        _I, [_U32, _U32, _U64, _U32, _P, _P, _P, _P, _P, _P, _U32, _U32, _U32, _U32, _U32, _P, _P, _P, _P, _P, _P]),
+        _I, [_U32, _U32, _U64, _U32, _P, _P, _P, _P, _P, _P, _U32, _U32, _U32, _U32, _U32, _P, _P, _P,
+             _P, _P, _P, _P]),
     "b200splat_rasterize_bwd": (
-        _I, [_U32, _U32, _U64, _U32, _P, _P, _P, _P, _P, _P, _U32, _U32, _U32, _U32, _U32, _P, _P,
+        _I, [_U32, _U32, _U64, _U32, _P, _P, _P, _P, _P, _P, _U32, _U32, _U32, _U32, _U32, _P, _P, _P,
              _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 

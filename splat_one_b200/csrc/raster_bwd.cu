@@ -10,6 +10,7 @@
 // (reduce-scatter) butterfly — 16 SHFL for up to 16 values — which leaves value k in
 // lane 2k, so a single RED instruction with <= 16 active lanes commits all of them.
 #include "raster_common.cuh"
+#include "raster_v2.cuh"
 
 namespace b2s {
 
@@ -216,6 +217,186 @@ static void launch_bwd(uint32_t C, uint64_t n_isects, uint32_t channels, const f
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// v2: warp-per-tile, 8 pixels per lane, culled staging (see raster_v2.cuh).
+// Per (tile, Gaussian): each lane folds its 8 pixels into 3 colour sums and the moments
+//   W0 = sum v_sigma,  W1 = sum v_sigma·dy,  W2 = sum v_sigma·dy²
+// (dx is shared by the lane's pixels), converts them to the 9 gradient values, and ONE
+// reduce-scatter butterfly + one RED per value commits them.
+// ---------------------------------------------------------------------------------------
+template <int CDIM, bool ABS>
+__global__ void __launch_bounds__(kV2Warps * 32)
+raster_bwd_v2_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channels, const float4 *__restrict__ rec,
+                     const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks, uint32_t W, uint32_t H,
+                     uint32_t tile_width, uint32_t tile_height, const int32_t *__restrict__ tile_offsets,
+                     const int32_t *__restrict__ flatten_ids, const float *__restrict__ render_alphas,
+                     const int32_t *__restrict__ last_ids, const float *__restrict__ v_render_colors,
+                     const float *__restrict__ v_render_alphas, float *__restrict__ v_means2d_abs,
+                     float *__restrict__ v_means2d, float *__restrict__ v_conics, float *__restrict__ v_colors,
+                     float *__restrict__ v_opacities) {
+    constexpr int NV = CDIM + 6 + (ABS ? 2 : 0);
+    __shared__ float4 s_rec[kV2Warps][32 * 3];
+    __shared__ int32_t s_idx[kV2Warps][32];
+    __shared__ int32_t s_gid[kV2Warps][32];
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t tile_lin = blockIdx.x * kV2Warps + wid;
+    if (tile_lin >= n_tiles_total) return;
+    if (masks != nullptr && !masks[tile_lin]) return;
+    const V2Tile tc = v2_tile(tile_lin, tile_width, tile_height, W, H, lane);
+    const size_t pix0 = ((size_t)tc.cam * H + tc.y0) * W + tc.x;
+
+    const int32_t range_start = tile_offsets[tile_lin];
+    const int32_t range_end = (tile_lin == n_tiles_total - 1) ? (int32_t)n_isects : tile_offsets[tile_lin + 1];
+    if (range_end <= range_start) return;
+
+    // per-pixel state
+    float T[kV2Rows], tfa[kV2Rows];          // running T; T_final * (v_alpha_out - sum_k bg_k v_c_k)
+    float v_c[kV2Rows][CDIM], buf[kV2Rows][CDIM];
+    int32_t binf[kV2Rows];
+    int32_t max_bin = -1;
+#pragma unroll
+    for (int j = 0; j < kV2Rows; ++j) {
+        T[j] = 1.f; tfa[j] = 0.f; binf[j] = -1;
+#pragma unroll
+        for (int k = 0; k < CDIM; ++k) { v_c[j][k] = 0.f; buf[j][k] = 0.f; }
+        if (tc.row_mask >> j & 1) {
+            const size_t p = pix0 + (size_t)j * W;
+            const float T_final = 1.f - render_alphas[p];
+            T[j] = T_final;
+            binf[j] = last_ids[p];
+            float bg_dot = 0.f;
+#pragma unroll
+            for (int k = 0; k < CDIM; ++k) {
+                if (k < (int)channels) {
+                    v_c[j][k] = v_render_colors[p * channels + k];
+                    if (backgrounds != nullptr) bg_dot += backgrounds[(size_t)tc.cam * channels + k] * v_c[j][k];
+                }
+            }
+            tfa[j] = T_final * (v_render_alphas[p] - bg_dot);
+            max_bin = max(max_bin, binf[j]);
+        }
+    }
+    max_bin = warp_max(max_bin);
+    // nothing behind the last contributor of any pixel of this tile matters
+    const int32_t hi0 = min(range_end - 1, max_bin);
+    if (hi0 < range_start) return;
+
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
+    int32_t my_idx = hi0 - (int32_t)lane, my_g = 0;
+    if (my_idx >= range_start) {
+        my_g = flatten_ids[my_idx];
+        r0 = __ldg(rec + 3 * (size_t)my_g); r1 = __ldg(rec + 3 * (size_t)my_g + 1); r2 = __ldg(rec + 3 * (size_t)my_g + 2);
+    }
+    for (int32_t hi = hi0; hi >= range_start; hi -= 32) {
+        const bool keep = (my_idx >= range_start) &&
+                          tile_may_contribute(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tc.rx0, tc.ry0, tc.rx1, tc.ry1);
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        const int n = __popc(bal);
+        __syncwarp();
+        if (keep) {
+            const int pos = __popc(bal & ((1u << lane) - 1u));
+            s_rec[wid][3 * pos] = r0; s_rec[wid][3 * pos + 1] = r1; s_rec[wid][3 * pos + 2] = r2;
+            s_idx[wid][pos] = my_idx;
+            s_gid[wid][pos] = my_g;
+        }
+        __syncwarp();
+        my_idx = hi - 32 - (int32_t)lane;
+        if (my_idx >= range_start) {
+            my_g = flatten_ids[my_idx];
+            r0 = __ldg(rec + 3 * (size_t)my_g); r1 = __ldg(rec + 3 * (size_t)my_g + 1); r2 = __ldg(rec + 3 * (size_t)my_g + 2);
+        }
+        for (int t = 0; t < n; ++t) {
+            const float4 a = s_rec[wid][3 * t], b4 = s_rec[wid][3 * t + 1];
+            const int32_t idx = s_idx[wid][t];
+            const float dx = a.x - tc.px, dy0 = a.y - tc.py0;
+            const float hA = a.z, cb = a.w, hC = b4.x, opac = b4.y;
+            const float A = hA * dx * dx, B = cb * dx;
+            uint32_t acc = 0;
+            float vis[kV2Rows];
+#pragma unroll
+            for (int j = 0; j < kV2Rows; ++j) {
+                const float dy = dy0 - (float)j;
+                const float sigma = A + dy * (B + hC * dy);
+                vis[j] = __expf(-sigma);
+                const float alpha = fminf(kAlphaMax, opac * vis[j]);
+                if (sigma >= 0.f && alpha >= kAlphaMin && idx <= binf[j]) acc |= 1u << j;
+            }
+            if (!__any_sync(0xffffffffu, acc != 0)) continue;
+            float v[NV];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) v[k] = 0.f;
+            if (acc != 0) {
+                const float4 c4 = s_rec[wid][3 * t + 2];
+                const float col[4] = {b4.z, b4.w, c4.x, c4.y};
+                float W0 = 0.f, W1 = 0.f, W2 = 0.f, ax = 0.f, ay = 0.f;
+#pragma unroll
+                for (int j = 0; j < kV2Rows; ++j) {
+                    if (acc >> j & 1) {
+                        const float ov = opac * vis[j];
+                        const float alpha = fminf(kAlphaMax, ov);
+                        const float ra = 1.f / (1.f - alpha);
+                        T[j] *= ra;
+                        const float fac = alpha * T[j];
+                        float v_alpha = 0.f;
+#pragma unroll
+                        for (int k = 0; k < CDIM; ++k) {
+                            v[k] += fac * v_c[j][k];
+                            v_alpha += (col[k] * T[j] - buf[j][k] * ra) * v_c[j][k];
+                            buf[j][k] += col[k] * fac;
+                        }
+                        v_alpha += tfa[j] * ra;
+                        if (ov <= kAlphaMax) {
+                            const float v_sigma = -ov * v_alpha;
+                            const float dy = dy0 - (float)j;
+                            const float wy = v_sigma * dy;
+                            W0 += v_sigma; W1 += wy; W2 += wy * dy;
+                            if (ABS) {
+                                ax += fabsf(v_sigma * (2.f * hA * dx + cb * dy));
+                                ay += fabsf(v_sigma * (cb * dx + 2.f * hC * dy));
+                            }
+                        }
+                    }
+                }
+                const float S1x = dx * W0;
+                v[CDIM + 0] = 0.5f * dx * S1x;                 // 1/2 sum v_sigma dx²
+                v[CDIM + 1] = dx * W1;                         // sum v_sigma dx dy
+                v[CDIM + 2] = 0.5f * W2;                       // 1/2 sum v_sigma dy²
+                v[CDIM + 3] = 2.f * hA * S1x + cb * W1;        // sum v_sigma (a dx + b dy)
+                v[CDIM + 4] = cb * S1x + 2.f * hC * W1;        // sum v_sigma (b dx + c dy)
+                v[CDIM + 5] = -W0 / opac;                      // sum vis·v_alpha
+                if (ABS) { v[CDIM + 6] = ax; v[CDIM + 7] = ay; }
+            }
+            const int32_t g = s_gid[wid][t];
+            warp_reduce_commit<NV>(v, lane, [&](int k, float val) {
+                float *dst;
+                if (k < CDIM) {
+                    if (k >= (int)channels) return;
+                    dst = v_colors + (size_t)g * channels + k;
+                } else if (k < CDIM + 3) dst = v_conics + 3 * (size_t)g + (k - CDIM);
+                else if (k < CDIM + 5) dst = v_means2d + 2 * (size_t)g + (k - CDIM - 3);
+                else if (k == CDIM + 5) dst = v_opacities + g;
+                else dst = v_means2d_abs + 2 * (size_t)g + (k - CDIM - 6);
+                atomicAdd(dst, val);
+            });
+        }
+    }
+}
+
+template <int CDIM, bool ABS>
+static void launch_bwd_v2(uint32_t C, uint64_t n_isects, uint32_t channels, const float4 *rec,
+                          const float *backgrounds, const uint8_t *masks, uint32_t W, uint32_t H, uint32_t tile_width,
+                          uint32_t tile_height, const int32_t *tile_offsets, const int32_t *flatten_ids,
+                          const float *render_alphas, const int32_t *last_ids, const float *v_render_colors,
+                          const float *v_render_alphas, float *v_means2d_abs, float *v_means2d, float *v_conics,
+                          float *v_colors, float *v_opacities, cudaStream_t st) {
+    const uint32_t total = C * tile_width * tile_height;
+    raster_bwd_v2_kernel<CDIM, ABS><<<div_up(total, kV2Warps), kV2Warps * 32, 0, st>>>(
+        total, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids,
+        render_alphas, last_ids, v_render_colors, v_render_alphas, v_means2d_abs, v_means2d, v_conics, v_colors,
+        v_opacities);
+}
+
 }  // namespace b2s
 
 using namespace b2s;
@@ -225,12 +406,37 @@ extern "C" int b200splat_rasterize_bwd(uint32_t C, uint32_t n_gauss, uint64_t n_
                                        const float *opacities, const float *backgrounds, const uint8_t *masks,
                                        uint32_t W, uint32_t H, uint32_t tile_size, uint32_t tile_width,
                                        uint32_t tile_height, const int32_t *tile_offsets, const int32_t *flatten_ids,
+                                       const void *records,
                                        const float *render_alphas, const int32_t *last_ids,
                                        const float *v_render_colors, const float *v_render_alphas,
                                        float *v_means2d_abs, float *v_means2d, float *v_conics, float *v_colors,
                                        float *v_opacities, void *stream) {
     const char *where = "b200splat_rasterize_bwd";
     (void)n_gauss;
+    if (records != nullptr) {
+        B2S_REQUIRE(tile_size == kV2Tile && channels >= 1 && channels <= 4, where,
+                    "packed records are only valid for tile_size 16 and <= 4 channels");
+        B2S_REQUIRE(n_isects <= 0x7fffffffull, where, "n_isects exceeds int32 offsets");
+        if ((uint64_t)C * tile_width * tile_height == 0 || n_isects == 0) return 0;
+        const float4 *rec = reinterpret_cast<const float4 *>(records);
+        cudaStream_t st2 = (cudaStream_t)stream;
+        const bool ab = v_means2d_abs != nullptr;
+#define B2S_BWD2(D)                                                                                                    \
+    case D:                                                                                                            \
+        if (ab)                                                                                                        \
+            launch_bwd_v2<D, true>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height,      \
+                                   tile_offsets, flatten_ids, render_alphas, last_ids, v_render_colors,                \
+                                   v_render_alphas, v_means2d_abs, v_means2d, v_conics, v_colors, v_opacities, st2);   \
+        else                                                                                                           \
+            launch_bwd_v2<D, false>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height,     \
+                                    tile_offsets, flatten_ids, render_alphas, last_ids, v_render_colors,               \
+                                    v_render_alphas, v_means2d_abs, v_means2d, v_conics, v_colors, v_opacities, st2);  \
+        break;
+        switch (channels) { B2S_BWD2(1) B2S_BWD2(2) B2S_BWD2(3) B2S_BWD2(4) }
+#undef B2S_BWD2
+        B2S_CHECK_LAUNCH(where);
+        return 0;
+    }
     B2S_REQUIRE(tile_size >= 1 && tile_size <= 32, where, "tile_size must be in [1, 32]");
     B2S_REQUIRE(n_isects <= 0x7fffffffull, where, "n_isects exceeds int32 offsets");
     const int cdim = pick_cdim(channels);

@@ -12,6 +12,7 @@
 // consumed with coalesced loads.  The loop body is the fp32/MUFU critical path; see
 // DESIGN.md for the measured limits.
 #include "raster_common.cuh"
+#include "raster_v2.cuh"
 
 namespace b2s {
 
@@ -146,18 +147,187 @@ static int launch_fwd(uint32_t C, uint64_t n_isects, uint32_t channels, const fl
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// v2: warp-per-tile, 8 pixels per lane, culled staging (see raster_v2.cuh)
+// ---------------------------------------------------------------------------------------
+template <int CDIM>
+__global__ void __launch_bounds__(kV2Warps * 32)
+raster_fwd_v2_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channels, const float4 *__restrict__ rec,
+                     const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks, uint32_t W, uint32_t H,
+                     uint32_t tile_width, uint32_t tile_height, const int32_t *__restrict__ tile_offsets,
+                     const int32_t *__restrict__ flatten_ids, float *__restrict__ render_colors,
+                     float *__restrict__ render_alphas, int32_t *__restrict__ last_ids) {
+    __shared__ float4 s_rec[kV2Warps][32 * 3];
+    __shared__ int32_t s_idx[kV2Warps][32];
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t tile_lin = blockIdx.x * kV2Warps + wid;
+    if (tile_lin >= n_tiles_total) return;  // warp-uniform; no block-level sync is used below
+    const V2Tile tc = v2_tile(tile_lin, tile_width, tile_height, W, H, lane);
+    if (backgrounds != nullptr) backgrounds += (size_t)tc.cam * channels;
+    const size_t pix0 = ((size_t)tc.cam * H + tc.y0) * W + tc.x;
+
+    if (masks != nullptr && !masks[tile_lin]) {
+#pragma unroll
+        for (int j = 0; j < kV2Rows; ++j)
+            if (tc.row_mask >> j & 1)
+                for (uint32_t k = 0; k < channels; ++k)
+                    render_colors[(pix0 + (size_t)j * W) * channels + k] = backgrounds == nullptr ? 0.f : backgrounds[k];
+        return;
+    }
+
+    const int32_t range_start = tile_offsets[tile_lin];
+    const int32_t range_end = (tile_lin == n_tiles_total - 1) ? (int32_t)n_isects : tile_offsets[tile_lin + 1];
+
+    float T[kV2Rows], pix[kV2Rows][CDIM];
+    int32_t cur[kV2Rows];
+#pragma unroll
+    for (int j = 0; j < kV2Rows; ++j) {
+        T[j] = 1.f;
+        cur[j] = 0;
+#pragma unroll
+        for (int k = 0; k < CDIM; ++k) pix[j][k] = 0.f;
+    }
+    uint32_t live = tc.row_mask;  // bit j: pixel j still accumulating
+
+    // software prefetch of this lane's record for the first batch
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
+    int32_t my_idx = range_start + (int32_t)lane;
+    if (my_idx < range_end) {
+        const int32_t g = flatten_ids[my_idx];
+        r0 = __ldg(rec + 3 * (size_t)g); r1 = __ldg(rec + 3 * (size_t)g + 1); r2 = __ldg(rec + 3 * (size_t)g + 2);
+    }
+    for (int32_t base = range_start; base < range_end; base += 32) {
+        const bool keep = (my_idx < range_end) &&
+                          tile_may_contribute(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tc.rx0, tc.ry0, tc.rx1, tc.ry1);
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        const int n = __popc(bal);
+        __syncwarp();  // readers of the previous batch are done
+        if (keep) {
+            const int pos = __popc(bal & ((1u << lane) - 1u));
+            s_rec[wid][3 * pos] = r0; s_rec[wid][3 * pos + 1] = r1; s_rec[wid][3 * pos + 2] = r2;
+            s_idx[wid][pos] = my_idx;
+        }
+        __syncwarp();
+        // prefetch the next batch while this one is composited
+        my_idx = base + 32 + (int32_t)lane;
+        if (my_idx < range_end) {
+            const int32_t g = flatten_ids[my_idx];
+            r0 = __ldg(rec + 3 * (size_t)g); r1 = __ldg(rec + 3 * (size_t)g + 1); r2 = __ldg(rec + 3 * (size_t)g + 2);
+        }
+        for (int t = 0; t < n; ++t) {
+            const float4 a = s_rec[wid][3 * t], b4 = s_rec[wid][3 * t + 1];
+            const float dx = a.x - tc.px;
+            const float dy0 = a.y - tc.py0;
+            const float A = a.z * dx * dx, B = a.w * dx, hC = b4.x, opac = b4.y;
+            uint32_t acc = 0;  // pixels that composite this Gaussian
+            float alpha[kV2Rows];
+#pragma unroll
+            for (int j = 0; j < kV2Rows; ++j) {
+                const float dy = dy0 - (float)j;
+                const float sigma = A + dy * (B + hC * dy);
+                alpha[j] = fminf(kAlphaMax, opac * __expf(-sigma));
+                if (sigma >= 0.f && alpha[j] >= kAlphaMin) acc |= 1u << j;
+            }
+            acc &= live;
+            if (acc == 0) continue;
+            const float4 c4 = s_rec[wid][3 * t + 2];
+            const float col[4] = {b4.z, b4.w, c4.x, c4.y};
+            const int32_t idx = s_idx[wid][t];
+#pragma unroll
+            for (int j = 0; j < kV2Rows; ++j) {
+                if (acc >> j & 1) {
+                    const float next_T = T[j] * (1.f - alpha[j]);
+                    if (next_T <= kTransmittanceEps) {
+                        live &= ~(1u << j);  // exclusive stop
+                    } else {
+                        const float vis = alpha[j] * T[j];
+#pragma unroll
+                        for (int k = 0; k < CDIM; ++k) pix[j][k] += col[k] * vis;
+                        cur[j] = idx;
+                        T[j] = next_T;
+                    }
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, live == 0)) break;
+    }
+
+#pragma unroll
+    for (int j = 0; j < kV2Rows; ++j) {
+        if (tc.row_mask >> j & 1) {
+            const size_t p = pix0 + (size_t)j * W;
+            render_alphas[p] = 1.f - T[j];
+#pragma unroll
+            for (int k = 0; k < CDIM; ++k)
+                if (k < (int)channels)
+                    render_colors[p * channels + k] = backgrounds == nullptr ? pix[j][k] : (pix[j][k] + T[j] * backgrounds[k]);
+            last_ids[p] = cur[j];
+        }
+    }
+}
+
+template <int CDIM>
+static void launch_fwd_v2(uint32_t C, uint64_t n_isects, uint32_t channels, const float4 *rec,
+                          const float *backgrounds, const uint8_t *masks, uint32_t W, uint32_t H, uint32_t tile_width,
+                          uint32_t tile_height, const int32_t *tile_offsets, const int32_t *flatten_ids,
+                          float *render_colors, float *render_alphas, int32_t *last_ids, cudaStream_t st) {
+    const uint32_t total = C * tile_width * tile_height;
+    raster_fwd_v2_kernel<CDIM><<<div_up(total, kV2Warps), kV2Warps * 32, 0, st>>>(
+        total, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids,
+        render_colors, render_alphas, last_ids);
+}
+
 }  // namespace b2s
 
 using namespace b2s;
+
+extern "C" size_t b200splat_rasterize_records_bytes(uint32_t n_gauss, uint32_t channels, uint32_t tile_size) {
+    if (tile_size != kV2Tile || channels < 1 || channels > 4) return 0;  // generic path: no records
+    return (size_t)n_gauss * 3 * sizeof(float4);
+}
+
+extern "C" int b200splat_rasterize_pack(uint32_t n_gauss, uint32_t channels, const float *means2d,
+                                        const float *conics, const float *colors, const float *opacities,
+                                        void *records, void *stream) {
+    const char *where = "b200splat_rasterize_pack";
+    B2S_REQUIRE(channels >= 1 && channels <= 4, where, "records hold at most 4 channels");
+    B2S_REQUIRE((reinterpret_cast<uintptr_t>(records) & 15) == 0, where, "records must be 16-byte aligned");
+    if (n_gauss == 0) return 0;
+    pack_records_kernel<<<div_up(n_gauss, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        n_gauss, channels, reinterpret_cast<const float2 *>(means2d), conics, colors, opacities,
+        reinterpret_cast<float4 *>(records));
+    B2S_CHECK_LAUNCH(where);
+    return 0;
+}
 
 extern "C" int b200splat_rasterize_fwd(uint32_t C, uint32_t n_gauss, uint64_t n_isects, uint32_t channels,
                                        const float *means2d, const float *conics, const float *colors,
                                        const float *opacities, const float *backgrounds, const uint8_t *masks,
                                        uint32_t W, uint32_t H, uint32_t tile_size, uint32_t tile_width,
                                        uint32_t tile_height, const int32_t *tile_offsets, const int32_t *flatten_ids,
+                                       const void *records,
                                        float *render_colors, float *render_alphas, int32_t *last_ids, void *stream) {
     const char *where = "b200splat_rasterize_fwd";
     (void)n_gauss;
+    if (records != nullptr) {
+        B2S_REQUIRE(tile_size == kV2Tile && channels >= 1 && channels <= 4, where,
+                    "packed records are only valid for tile_size 16 and <= 4 channels");
+        B2S_REQUIRE((uint64_t)tile_width * tile_size >= W && (uint64_t)tile_height * tile_size >= H, where,
+                    "tile grid does not cover the image");
+        B2S_REQUIRE(n_isects <= 0x7fffffffull, where, "n_isects exceeds int32 offsets");
+        if ((uint64_t)C * tile_width * tile_height == 0) return 0;
+        const float4 *rec = reinterpret_cast<const float4 *>(records);
+        cudaStream_t st2 = (cudaStream_t)stream;
+        switch (channels) {
+            case 1: launch_fwd_v2<1>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids, st2); break;
+            case 2: launch_fwd_v2<2>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids, st2); break;
+            case 3: launch_fwd_v2<3>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids, st2); break;
+            default: launch_fwd_v2<4>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids, st2); break;
+        }
+        B2S_CHECK_LAUNCH(where);
+        return 0;
+    }
     B2S_REQUIRE(tile_size >= 1 && tile_size <= 32, where, "tile_size must be in [1, 32]");
     B2S_REQUIRE((uint64_t)tile_width * tile_size >= W && (uint64_t)tile_height * tile_size >= H, where,
                 "tile grid does not cover the image");

@@ -18,6 +18,7 @@ reference's TORCH_CHECK (CS/bindings.h:10-16).
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -30,6 +31,8 @@ CAMERA_MODELS = {"pinhole": 0, "ortho": 1, "fisheye": 2, "spherical": 3}  # CS/b
 
 # compiled channel instances of the raster kernels (csrc/raster_common.cuh pick_cdim)
 _MAX_NATIVE_CHANNELS = 33
+# debugging / A-B switch: B200SPLAT_GENERIC_RASTER=1 disables the warp-per-tile raster kernels
+_FORCE_GENERIC_RASTER = os.environ.get("B200SPLAT_GENERIC_RASTER", "0") == "1"
 
 
 class _Profiler:
@@ -41,7 +44,7 @@ class _Profiler:
     KERNELS = {
         "projection_fwd": 1, "projection_bwd": 1, "projection_packed_count": 3, "projection_packed_fill": 1,
         "projection_packed_bwd": 1, "sh_fwd": 1, "sh_bwd": 1, "isect_count": 2, "isect_fill": 1,
-        "isect_sort": 0, "isect_offset_encode": 1, "rasterize_fwd": 1, "rasterize_bwd": 1,
+        "isect_sort": 0, "isect_offset_encode": 1, "rasterize_pack": 1, "rasterize_fwd": 1, "rasterize_bwd": 1,
     }
 
     def __init__(self):
@@ -609,20 +612,28 @@ class _RasterizeToPixels(torch.autograd.Function):
             # masked tiles never write alpha/last_ids (CS/...fwd.cu:71-77); give them defined values
             render_alphas.zero_()
             last_ids.zero_()
+        # warp-per-tile fast path (tile_size 16, <= 4 channels): one packed 48-byte record per
+        # Gaussian, shared by the forward and the backward kernel
+        records = None
+        rec_bytes = 0 if _FORCE_GENERIC_RASTER else lib.b200splat_rasterize_records_bytes(n_gauss, channels, tile_size)
+        if rec_bytes and n_isects:
+            records = torch.empty((rec_bytes // 4,), device=dev, dtype=torch.float32)
+            native("rasterize_pack", lib, dev, n_gauss, channels, _ptr(means2d_a), _ptr(conics), _ptr(colors),
+                   _ptr(opacities), _ptr(records))
         if render_colors.numel():
             native("rasterize_fwd", lib, dev, C, n_gauss, n_isects, channels, _ptr(means2d_a), _ptr(conics), _ptr(colors), _ptr(opacities),
                     _ptr(backgrounds), _ptr(masks), width, height, tile_size, tile_width, tile_height,
-                    _ptr(isect_offsets), _ptr(flatten_ids), _ptr(render_colors), _ptr(render_alphas),
+                    _ptr(isect_offsets), _ptr(flatten_ids), _ptr(records), _ptr(render_colors), _ptr(render_alphas),
                     _ptr(last_ids))
         ctx.save_for_backward(means2d, conics, colors, opacities, backgrounds, masks, isect_offsets, flatten_ids,
-                              render_alphas, last_ids)
+                              render_alphas, last_ids, records)
         ctx.width, ctx.height, ctx.tile_size, ctx.absgrad = width, height, tile_size, absgrad
         return render_colors, render_alphas
 
     @staticmethod
     def backward(ctx, v_render_colors: Tensor, v_render_alphas: Tensor):
         (means2d, conics, colors, opacities, backgrounds, masks, isect_offsets, flatten_ids, render_alphas,
-         last_ids) = ctx.saved_tensors
+         last_ids, records) = ctx.saved_tensors
         lib = get_lib()
         dev = means2d.device
         C, tile_height, tile_width = isect_offsets.shape
@@ -640,7 +651,7 @@ class _RasterizeToPixels(torch.autograd.Function):
         if n_isects and render_alphas.numel():
             native("rasterize_bwd", lib, dev, C, n_gauss, n_isects, channels, _ptr(means2d_a), _ptr(conics), _ptr(colors), _ptr(opacities),
                     _ptr(backgrounds), _ptr(masks), ctx.width, ctx.height, ctx.tile_size, tile_width, tile_height,
-                    _ptr(isect_offsets), _ptr(flatten_ids), _ptr(render_alphas), _ptr(last_ids),
+                    _ptr(isect_offsets), _ptr(flatten_ids), _ptr(records), _ptr(render_alphas), _ptr(last_ids),
                     _ptr(v_render_colors), _ptr(v_render_alphas), _ptr(v_means2d_abs), _ptr(v_means2d),
                     _ptr(v_conics), _ptr(v_colors), _ptr(v_opacities))
         if ctx.absgrad:

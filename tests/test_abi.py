@@ -18,7 +18,7 @@ def _header_symbols():
 def test_library_loads_and_exports_every_header_symbol():
     lib = _lib.get_lib()
     syms = _header_symbols()
-    assert len(syms) == 18
+    assert len(syms) == 20
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/b200splat.h but not exported"
     assert lib.b200splat_abi_version() == _lib.ABI_VERSION
@@ -45,7 +45,7 @@ def test_validation_errors_are_reported_without_a_gpu():
     with pytest.raises(_lib.B200SplatError):
         _lib.check(rc, lib)
     rc = lib.b200splat_rasterize_fwd(1, 1, 1, 700, None, None, None, None, None, None, 16, 16, 16, 1, 1, None, None,
-                                     None, None, None, None)
+                                     None, None, None, None, None)
     assert rc != 0 and b"channels" in lib.b200splat_last_error()
     rc = lib.b200splat_projection_fwd(1, 1, None, None, None, None, None, None, 8, 8, 0.3, 0.01, 1e10, 0.0, 9,
                                       None, None, None, None, None, None)
