@@ -158,7 +158,9 @@ B200SPLAT_API int b200splat_sh_bwd(
  * a6  isect_tiles                         CS/bindings.h:148-160, kernel
  *     CS/isect_tiles.cu:17-105, host :107-307.
  * Phase 1 (`_count`): tiles_per_gauss [n_elems] int32, cum_tiles [n_elems] int64
- *   (inclusive scan) and *n_isects_out (device int64).
+ *   (inclusive scan) and n_isects_out (device int64[2]: [0] = n_isects, [1] = 1 if some
+ *   visible depth has its sign bit set, which sign-extends into the tile/camera fields of
+ *   the reference key and is routed to the generic sort; depths may be NULL).
  * Phase 2 (`_fill`): unsorted keys `cam | tile | depth bits` + flat indices.
  * Phase 3 (`_sort`): stable LSD radix sort of (key,value) on bits [0, end_bit) over a
  *   pair of ping-pong buffers (the reference's cub::DoubleBuffer, CS/isect_tiles.cu:262-299);
@@ -169,7 +171,7 @@ B200SPLAT_API int b200splat_sh_bwd(
  * ---------------------------------------------------------------------------------- */
 B200SPLAT_API int b200splat_isect_count(
     int packed, uint32_t C, uint32_t N, uint32_t nnz,
-    const float *means2d, const int32_t *radii,
+    const float *means2d, const int32_t *radii, const float *depths,
     uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
     int32_t *tiles_per_gauss, int64_t *cum_tiles, int64_t *n_isects_out,
     void *scan_workspace, size_t scan_workspace_bytes,
@@ -194,6 +196,22 @@ B200SPLAT_API int b200splat_isect_sort(
     int64_t *keys_b, int32_t *vals_b,   /* alternate buffers */
     void *workspace, size_t workspace_bytes,
     int *selector_out,                  /* HOST int: 0 => result in *_a, 1 => in *_b */
+    void *stream);
+
+/* Phases 2+3 in one call for non-negative depths — the B200 path used by
+ * rasterization(): Gaussians are ordered by depth first (n_elems 32-bit keys), expanded
+ * into their tiles in that order, and only the cam|tile bits are sorted at intersection
+ * scale; the output is bit-identical to `_fill` + `_sort` (see csrc/sort.cu). */
+B200SPLAT_API size_t b200splat_isect_sorted_workspace_bytes(uint64_t n_elems, uint64_t n_isects);
+
+B200SPLAT_API int b200splat_isect_sorted(
+    int packed, uint32_t C, uint32_t N, uint32_t nnz,
+    const int64_t *camera_ids,
+    const float *means2d, const int32_t *radii, const float *depths,
+    const int32_t *tiles_per_gauss, uint64_t n_isects,
+    uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+    int64_t *isect_ids, int32_t *flatten_ids,
+    void *workspace, size_t workspace_bytes,
     void *stream);
 
 /* a7  isect_offset_encode                 CS/bindings.h:162-167, kernel

@@ -31,7 +31,8 @@ __device__ __forceinline__ TileRect tile_rect(float mx, float my, float radius, 
 
 __global__ void __launch_bounds__(kThreads)
 isect_count_kernel(uint64_t n_elems, const float *__restrict__ means2d, const int32_t *__restrict__ radii,
-                   float ts, uint32_t tw, uint32_t th, int32_t *__restrict__ tiles_per_gauss) {
+                   const float *__restrict__ depths, float ts, uint32_t tw, uint32_t th,
+                   int32_t *__restrict__ tiles_per_gauss, int64_t *__restrict__ neg_depth_flag) {
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_elems) return;
     const float radius = (float)radii[idx];
@@ -40,6 +41,9 @@ isect_count_kernel(uint64_t n_elems, const float *__restrict__ means2d, const in
         const float2 m = reinterpret_cast<const float2 *>(means2d)[idx];
         const TileRect r = tile_rect(m.x, m.y, radius, ts, tw, th);
         cnt = (int32_t)((r.y1 - r.y0) * (r.x1 - r.x0));
+        // a set sign bit sign-extends into the tile/camera fields of the reference key
+        // (CS/isect_tiles.cu:92): outside the contract, routed to the generic sort
+        if (cnt > 0 && depths != nullptr && __float_as_int(depths[idx]) < 0) *neg_depth_flag = 1;
     }
     tiles_per_gauss[idx] = cnt;
 }
@@ -107,7 +111,7 @@ using namespace b2s;
 extern "C" size_t b200splat_scan_workspace_bytes(uint64_t n_elems) { return scan_workspace_bytes(n_elems); }
 
 extern "C" int b200splat_isect_count(int packed, uint32_t C, uint32_t N, uint32_t nnz, const float *means2d,
-                                     const int32_t *radii, uint32_t tile_size, uint32_t tile_width,
+                                     const int32_t *radii, const float *depths, uint32_t tile_size, uint32_t tile_width,
                                      uint32_t tile_height, int32_t *tiles_per_gauss, int64_t *cum_tiles,
                                      int64_t *n_isects_out, void *scan_workspace, size_t scan_workspace_bytes_,
                                      void *stream) {
@@ -115,12 +119,11 @@ extern "C" int b200splat_isect_count(int packed, uint32_t C, uint32_t N, uint32_
     cudaStream_t st = (cudaStream_t)stream;
     B2S_REQUIRE(tile_size > 0, where, "tile_size must be positive");
     const uint64_t n_elems = packed ? (uint64_t)nnz : (uint64_t)C * N;
-    if (n_elems == 0) {
-        cudaMemsetAsync(n_isects_out, 0, sizeof(int64_t), st);
-        return 0;
-    }
-    isect_count_kernel<<<div_up(n_elems, kThreads), kThreads, 0, st>>>(n_elems, means2d, radii, (float)tile_size,
-                                                                        tile_width, tile_height, tiles_per_gauss);
+    cudaMemsetAsync(n_isects_out, 0, 2 * sizeof(int64_t), st);
+    if (n_elems == 0) return 0;
+    isect_count_kernel<<<div_up(n_elems, kThreads), kThreads, 0, st>>>(n_elems, means2d, radii, depths, (float)tile_size,
+                                                                        tile_width, tile_height, tiles_per_gauss,
+                                                                        n_isects_out + 1);
     B2S_CHECK_LAUNCH(where);
     const int rc = lookback_scan_i32_to_i64(tiles_per_gauss, cum_tiles, n_elems, n_isects_out, scan_workspace,
                                             scan_workspace_bytes_, st);

@@ -42,7 +42,9 @@ constexpr int next_pow2(int n) { return n <= 1 ? 1 : n <= 2 ? 2 : n <= 4 ? 4 : n
 // on exactly one lane.  Values are processed in chunks of <= 32.
 template <int NV, int OFF = 0, typename Commit>
 __device__ __forceinline__ void warp_reduce_commit(const float *v, const unsigned lane, Commit &&commit) {
-    constexpr int CH = (NV - OFF) > 32 ? 32 : (NV - OFF);
+    // chunk sizes are powers of two where that saves shuffles: 9..11 values go as 8 + rest
+    constexpr int REM = NV - OFF;
+    constexpr int CH = REM > 32 ? 32 : (REM > 8 && REM < 12) ? 8 : REM;
     constexpr int P = next_pow2(CH);
     float w[P];
 #pragma unroll
@@ -250,16 +252,17 @@ raster_bwd_v2_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channel
     const int32_t range_end = (tile_lin == n_tiles_total - 1) ? (int32_t)n_isects : tile_offsets[tile_lin + 1];
     if (range_end <= range_start) return;
 
-    // per-pixel state
-    float T[kV2Rows], tfa[kV2Rows];          // running T; T_final * (v_alpha_out - sum_k bg_k v_c_k)
-    float v_c[kV2Rows][CDIM], buf[kV2Rows][CDIM];
+    // per-pixel state.  bv = sum_k buffer_k * v_c_k replaces the reference's per-channel
+    // `buffer` (CS/rasterize_to_pixels_bwd.cu:203-241): v_alpha only ever needs that dot product.
+    float T[kV2Rows], tfa[kV2Rows], bv[kV2Rows];  // tfa = T_final * (v_alpha_out - sum_k bg_k v_c_k)
+    float v_c[kV2Rows][CDIM];
     int32_t binf[kV2Rows];
     int32_t max_bin = -1;
 #pragma unroll
     for (int j = 0; j < kV2Rows; ++j) {
-        T[j] = 1.f; tfa[j] = 0.f; binf[j] = -1;
+        T[j] = 1.f; tfa[j] = 0.f; bv[j] = 0.f; binf[j] = -1;
 #pragma unroll
-        for (int k = 0; k < CDIM; ++k) { v_c[j][k] = 0.f; buf[j][k] = 0.f; }
+        for (int k = 0; k < CDIM; ++k) v_c[j][k] = 0.f;
         if (tc.row_mask >> j & 1) {
             const size_t p = pix0 + (size_t)j * W;
             const float T_final = 1.f - render_alphas[p];
@@ -307,66 +310,66 @@ raster_bwd_v2_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channel
             r0 = __ldg(rec + 3 * (size_t)my_g); r1 = __ldg(rec + 3 * (size_t)my_g + 1); r2 = __ldg(rec + 3 * (size_t)my_g + 2);
         }
         for (int t = 0; t < n; ++t) {
-            const float4 a = s_rec[wid][3 * t], b4 = s_rec[wid][3 * t + 1];
+            const float4 a = s_rec[wid][3 * t], b4 = s_rec[wid][3 * t + 1], c4 = s_rec[wid][3 * t + 2];
             const int32_t idx = s_idx[wid][t];
             const float dx = a.x - tc.px, dy0 = a.y - tc.py0;
             const float hA = a.z, cb = a.w, hC = b4.x, opac = b4.y;
             const float A = hA * dx * dx, B = cb * dx;
+            const float col[4] = {b4.z, b4.w, c4.x, c4.y};
+            // phase 1 (branch-free, 8 independent chains): which of the lane's pixels accept
+            float ovs[kV2Rows];
             uint32_t acc = 0;
-            float vis[kV2Rows];
 #pragma unroll
             for (int j = 0; j < kV2Rows; ++j) {
                 const float dy = dy0 - (float)j;
                 const float sigma = A + dy * (B + hC * dy);
-                vis[j] = __expf(-sigma);
-                const float alpha = fminf(kAlphaMax, opac * vis[j]);
-                if (sigma >= 0.f && alpha >= kAlphaMin && idx <= binf[j]) acc |= 1u << j;
+                ovs[j] = opac * __expf(-sigma);
+                if (sigma >= 0.f && fminf(kAlphaMax, ovs[j]) >= kAlphaMin && idx <= binf[j]) acc |= 1u << j;
             }
-            if (!__any_sync(0xffffffffu, acc != 0)) continue;
+            const uint32_t rows = __reduce_or_sync(0xffffffffu, acc);
+            if (rows == 0) continue;
+            // phase 2: a pixel row is skipped with a WARP-UNIFORM branch when no lane needs it
+            // and runs predicated otherwise (a rejected pixel has alpha = 0: ra = 1, fac = 0,
+            // v_sigma = 0), so there is no divergence and the chains interleave
             float v[NV];
 #pragma unroll
             for (int k = 0; k < NV; ++k) v[k] = 0.f;
-            if (acc != 0) {
-                const float4 c4 = s_rec[wid][3 * t + 2];
-                const float col[4] = {b4.z, b4.w, c4.x, c4.y};
-                float W0 = 0.f, W1 = 0.f, W2 = 0.f, ax = 0.f, ay = 0.f;
+            float W0 = 0.f, W1 = 0.f, W2 = 0.f;
 #pragma unroll
-                for (int j = 0; j < kV2Rows; ++j) {
-                    if (acc >> j & 1) {
-                        const float ov = opac * vis[j];
-                        const float alpha = fminf(kAlphaMax, ov);
-                        const float ra = 1.f / (1.f - alpha);
-                        T[j] *= ra;
-                        const float fac = alpha * T[j];
-                        float v_alpha = 0.f;
+            for (int j = 0; j < kV2Rows; ++j) {
+                if (rows >> j & 1) {
+                    const bool ok = acc >> j & 1;
+                    const float dy = dy0 - (float)j;
+                    const float ov = ovs[j];
+                    const float alpha = ok ? fminf(kAlphaMax, ov) : 0.f;
+                    const float ra = __fdividef(1.f, 1.f - alpha);
+                    const float Tn = T[j] * ra;
+                    T[j] = Tn;
+                    const float fac = alpha * Tn;
+                    float cv = 0.f;
 #pragma unroll
-                        for (int k = 0; k < CDIM; ++k) {
-                            v[k] += fac * v_c[j][k];
-                            v_alpha += (col[k] * T[j] - buf[j][k] * ra) * v_c[j][k];
-                            buf[j][k] += col[k] * fac;
-                        }
-                        v_alpha += tfa[j] * ra;
-                        if (ov <= kAlphaMax) {
-                            const float v_sigma = -ov * v_alpha;
-                            const float dy = dy0 - (float)j;
-                            const float wy = v_sigma * dy;
-                            W0 += v_sigma; W1 += wy; W2 += wy * dy;
-                            if (ABS) {
-                                ax += fabsf(v_sigma * (2.f * hA * dx + cb * dy));
-                                ay += fabsf(v_sigma * (cb * dx + 2.f * hC * dy));
-                            }
-                        }
+                    for (int k = 0; k < CDIM; ++k) {
+                        v[k] += fac * v_c[j][k];
+                        cv += col[k] * v_c[j][k];
+                    }
+                    const float v_alpha = Tn * cv + ra * (tfa[j] - bv[j]);
+                    bv[j] += fac * cv;
+                    const float v_sigma = (ok && ov <= kAlphaMax) ? -ov * v_alpha : 0.f;
+                    const float wy = v_sigma * dy;
+                    W0 += v_sigma; W1 += wy; W2 += wy * dy;
+                    if (ABS) {
+                        v[CDIM + 6] += fabsf(v_sigma * (2.f * hA * dx + cb * dy));
+                        v[CDIM + 7] += fabsf(v_sigma * (cb * dx + 2.f * hC * dy));
                     }
                 }
-                const float S1x = dx * W0;
-                v[CDIM + 0] = 0.5f * dx * S1x;                 // 1/2 sum v_sigma dx²
-                v[CDIM + 1] = dx * W1;                         // sum v_sigma dx dy
-                v[CDIM + 2] = 0.5f * W2;                       // 1/2 sum v_sigma dy²
-                v[CDIM + 3] = 2.f * hA * S1x + cb * W1;        // sum v_sigma (a dx + b dy)
-                v[CDIM + 4] = cb * S1x + 2.f * hC * W1;        // sum v_sigma (b dx + c dy)
-                v[CDIM + 5] = -W0 / opac;                      // sum vis·v_alpha
-                if (ABS) { v[CDIM + 6] = ax; v[CDIM + 7] = ay; }
             }
+            const float S1x = dx * W0;
+            v[CDIM + 0] = 0.5f * dx * S1x;                 // 1/2 sum v_sigma dx²
+            v[CDIM + 1] = dx * W1;                         // sum v_sigma dx dy
+            v[CDIM + 2] = 0.5f * W2;                       // 1/2 sum v_sigma dy²
+            v[CDIM + 3] = 2.f * hA * S1x + cb * W1;        // sum v_sigma (a dx + b dy)
+            v[CDIM + 4] = cb * S1x + 2.f * hC * W1;        // sum v_sigma (b dx + c dy)
+            v[CDIM + 5] = -W0 / opac;                      // sum vis·v_alpha
             const int32_t g = s_gid[wid][t];
             warp_reduce_commit<NV>(v, lane, [&](int k, float val) {
                 float *dst;

@@ -216,12 +216,15 @@ raster_fwd_v2_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channel
             r0 = __ldg(rec + 3 * (size_t)g); r1 = __ldg(rec + 3 * (size_t)g + 1); r2 = __ldg(rec + 3 * (size_t)g + 2);
         }
         for (int t = 0; t < n; ++t) {
-            const float4 a = s_rec[wid][3 * t], b4 = s_rec[wid][3 * t + 1];
+            const float4 a = s_rec[wid][3 * t], b4 = s_rec[wid][3 * t + 1], c4 = s_rec[wid][3 * t + 2];
+            const int32_t idx = s_idx[wid][t];
             const float dx = a.x - tc.px;
             const float dy0 = a.y - tc.py0;
             const float A = a.z * dx * dx, B = a.w * dx, hC = b4.x, opac = b4.y;
-            uint32_t acc = 0;  // pixels that composite this Gaussian
+            const float col[4] = {b4.z, b4.w, c4.x, c4.y};
+            // phase 1 (branch-free, 8 independent chains): alpha of the lane's 8 pixels
             float alpha[kV2Rows];
+            uint32_t acc = 0;
 #pragma unroll
             for (int j = 0; j < kV2Rows; ++j) {
                 const float dy = dy0 - (float)j;
@@ -230,23 +233,22 @@ raster_fwd_v2_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channel
                 if (sigma >= 0.f && alpha[j] >= kAlphaMin) acc |= 1u << j;
             }
             acc &= live;
-            if (acc == 0) continue;
-            const float4 c4 = s_rec[wid][3 * t + 2];
-            const float col[4] = {b4.z, b4.w, c4.x, c4.y};
-            const int32_t idx = s_idx[wid][t];
+            // phase 2: composite; a pixel row is skipped with a WARP-UNIFORM branch when no
+            // lane needs it, and runs predicated (weight 0) otherwise — no divergence
+            const uint32_t rows = __reduce_or_sync(0xffffffffu, acc);
 #pragma unroll
             for (int j = 0; j < kV2Rows; ++j) {
-                if (acc >> j & 1) {
+                if (rows >> j & 1) {
+                    const bool ok = acc >> j & 1;
                     const float next_T = T[j] * (1.f - alpha[j]);
-                    if (next_T <= kTransmittanceEps) {
-                        live &= ~(1u << j);  // exclusive stop
-                    } else {
-                        const float vis = alpha[j] * T[j];
+                    const bool stop = ok && (next_T <= kTransmittanceEps);  // exclusive stop
+                    const bool comp = ok && !stop;
+                    if (stop) live &= ~(1u << j);
+                    const float vis = comp ? alpha[j] * T[j] : 0.f;
 #pragma unroll
-                        for (int k = 0; k < CDIM; ++k) pix[j][k] += col[k] * vis;
-                        cur[j] = idx;
-                        T[j] = next_T;
-                    }
+                    for (int k = 0; k < CDIM; ++k) pix[j][k] += col[k] * vis;
+                    cur[j] = comp ? idx : cur[j];
+                    T[j] = comp ? next_T : T[j];
                 }
             }
         }

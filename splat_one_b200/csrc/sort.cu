@@ -1,13 +1,152 @@
-// sort.cu — stable LSD radix sort of (int64 key, int32 value) pairs for isect_tiles (a6).
-// Replaces the cub::DeviceRadixSort::SortPairs call at CS/isect_tiles.cu:252-300.
+// sort.cu — ordering stage of isect_tiles (a6): produce the (isect_ids, flatten_ids) arrays
+// sorted exactly like the reference's stable LSD radix sort of the 64-bit keys
+// `cam | tile | depth bits` (CS/isect_tiles.cu:252-300).
 //
-// Round-1 implementation: CUB 2.8 (CUDA 12.9 toolkit) onesweep with its SM100 tuning
-// policy behind the C ABI — the same library kernel the reference would instantiate for
-// sm_100a, used here as the correctness anchor and the bar to beat.
-// The hand-written depth-first sort (sort Gaussians by depth, expand, then two
-// tile-digit passes) plugs in behind the same entry point; see DESIGN.md.
+// Two implementations behind the C ABI:
+//
+//  * b200splat_isect_sort       — generic: sort already-built (key,value) pairs on bits
+//    [0,end_bit).  One library call (CUB onesweep, the kernel the reference itself would
+//    instantiate for sm_100a); kept for `sort=True` on caller-provided keys and as the
+//    fallback for inputs outside the contract (negative depths).
+//
+//  * b200splat_isect_sorted     — the B200 path used by rasterization().  An LSD radix
+//    sort of `cam|tile|depth` first orders by the 32 depth bits, and those bits are a
+//    property of the GAUSSIAN, not of the intersection.  So:
+//      1. sort the C·N (or nnz) Gaussians by depth bits       (32-bit keys,  n elements)
+//      2. scan tiles_per_gauss in that order                  (                n elements)
+//      3. expand every Gaussian into its tiles, in that order (8 B out per intersection)
+//      4. stable-sort the intersections by the cam|tile bits  (<= 2 digit passes over I)
+//      5. assemble the 64-bit ids (depth bits gathered back)  (12 B out per intersection)
+//    The result is bit-identical to sorting the full keys (a stable sort by the high bits
+//    of a sequence already ordered by the low bits, and the expansion order equals the
+//    reference's tie order), but the intersection-sized traffic drops from
+//    ~150 B (6 onesweep passes of 12-byte pairs + histogram) to ~56 B per intersection.
 #include "common.cuh"
+#include "scan.cuh"
 #include <cub/device/device_radix_sort.cuh>
+
+namespace b2s {
+
+struct TileRect2 { uint32_t x0, y0, x1, y1; };
+
+// identical to isect.cu's tile_rect (CS/isect_tiles.cu:60-70)
+__device__ __forceinline__ TileRect2 tile_rect2(float mx, float my, float radius, float ts, uint32_t tw,
+                                                uint32_t th) {
+    const float tr = __fdividef(radius, ts), tx = __fdividef(mx, ts), ty = __fdividef(my, ts);
+    TileRect2 r;
+    r.x0 = min(__float2uint_rz(floorf(tx - tr)), tw);
+    r.y0 = min(__float2uint_rz(floorf(ty - tr)), th);
+    r.x1 = min(__float2uint_rz(ceilf(tx + tr)), tw);
+    r.y1 = min(__float2uint_rz(ceilf(ty + tr)), th);
+    return r;
+}
+
+// step 1 input: key = depth bits of visible elements, 0xFFFFFFFF for invisible ones
+// (a visible depth can never be 0xFFFFFFFF: the sign bit is excluded by the caller).
+__global__ void __launch_bounds__(kThreads)
+depth_keys_kernel(uint64_t n_elems, const int32_t *__restrict__ tiles_per_gauss, const float *__restrict__ depths,
+                  uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_elems) return;
+    keys[i] = tiles_per_gauss[i] > 0 ? (uint32_t)__float_as_int(depths[i]) : 0xFFFFFFFFu;
+    vals[i] = (uint32_t)i;
+}
+
+// step 2 input: counts in depth order
+__global__ void __launch_bounds__(kThreads)
+gather_counts_kernel(uint64_t n_elems, const uint32_t *__restrict__ order, const int32_t *__restrict__ tiles_per_gauss,
+                     int32_t *__restrict__ counts) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_elems) return;
+    counts[i] = tiles_per_gauss[order[i]];
+}
+
+// step 3: one warp expands 32 consecutive Gaussians (in depth order); for each, the 32
+// lanes write its tiles side by side, so a warp's stores cover one contiguous range.
+__global__ void __launch_bounds__(kThreads)
+expand_kernel(int packed, uint32_t N, uint64_t n_elems, const uint32_t *__restrict__ order,
+              const int64_t *__restrict__ cum_sorted, const int64_t *__restrict__ camera_ids,
+              const float *__restrict__ means2d, const int32_t *__restrict__ radii, float ts, uint32_t tw, uint32_t th,
+              uint32_t tile_n_bits, uint32_t *__restrict__ tile_keys, uint32_t *__restrict__ vals) {
+    const unsigned lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t i = warp * 32 + lane;
+    uint32_t idx = 0, x0 = 0, y0 = 0, w = 0, cnt = 0, cam_enc = 0;
+    int64_t start = 0;
+    if (i < n_elems) {
+        idx = order[i];
+        const float radius = (float)radii[idx];
+        if (radius > 0.f) {
+            const float2 m = reinterpret_cast<const float2 *>(means2d)[idx];
+            const TileRect2 r = tile_rect2(m.x, m.y, radius, ts, tw, th);
+            x0 = r.x0; y0 = r.y0; w = r.x1 - r.x0;
+            cnt = (r.y1 - r.y0) * w;
+            const uint32_t cid = packed ? (uint32_t)camera_ids[idx] : (uint32_t)(idx / N);
+            cam_enc = cid << tile_n_bits;
+            start = (i == 0) ? 0 : cum_sorted[i - 1];
+        }
+    }
+    const unsigned active = __ballot_sync(0xffffffffu, cnt > 0);
+    for (unsigned m = active; m; m &= m - 1) {
+        const int src = __ffs(m) - 1;
+        const uint32_t g_idx = __shfl_sync(0xffffffffu, idx, src);
+        const uint32_t g_x0 = __shfl_sync(0xffffffffu, x0, src), g_y0 = __shfl_sync(0xffffffffu, y0, src);
+        const uint32_t g_w = __shfl_sync(0xffffffffu, w, src), g_cnt = __shfl_sync(0xffffffffu, cnt, src);
+        const uint32_t g_cam = __shfl_sync(0xffffffffu, cam_enc, src);
+        const int64_t g_start = __shfl_sync(0xffffffffu, start, src);
+        for (uint32_t k = lane; k < g_cnt; k += 32) {
+            const uint32_t ry = k / g_w, rx = k - ry * g_w;
+            tile_keys[g_start + k] = g_cam | ((g_y0 + ry) * tw + (g_x0 + rx));
+            vals[g_start + k] = g_idx;
+        }
+    }
+}
+
+// step 5: 64-bit ids from the sorted (cam|tile, flat index) pairs
+__global__ void __launch_bounds__(kThreads)
+assemble_kernel(uint64_t n_isects, const uint32_t *__restrict__ tile_keys, const uint32_t *__restrict__ vals,
+                const float *__restrict__ depths, int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_isects) return;
+    const uint32_t v = vals[i];
+    const uint32_t d = (uint32_t)__float_as_int(__ldg(depths + v));
+    isect_ids[i] = (int64_t)(((uint64_t)tile_keys[i] << 32) | (uint64_t)d);
+    flatten_ids[i] = (int32_t)v;
+}
+
+static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct SortedLayout {
+    size_t gkeys_a, gkeys_b, gvals_a, gvals_b, counts, cum, total, scan_ws, scan_ws_bytes;
+    size_t tkeys_a, tkeys_b, tvals_a, tvals_b, cub, cub_bytes, end;
+};
+
+static SortedLayout sorted_layout(uint64_t n_elems, uint64_t n_isects) {
+    SortedLayout L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes); return r; };
+    L.gkeys_a = take(4 * n_elems); L.gkeys_b = take(4 * n_elems);
+    L.gvals_a = take(4 * n_elems); L.gvals_b = take(4 * n_elems);
+    L.counts = take(4 * n_elems);
+    L.cum = take(8 * n_elems);
+    L.total = take(8);
+    L.scan_ws_bytes = scan_workspace_bytes(n_elems);
+    L.scan_ws = take(L.scan_ws_bytes);
+    L.tkeys_a = take(4 * n_isects); L.tkeys_b = take(4 * n_isects);
+    L.tvals_a = take(4 * n_isects); L.tvals_b = take(4 * n_isects);
+    size_t b1 = 0, b2 = 0;
+    {
+        cub::DoubleBuffer<uint32_t> k(nullptr, nullptr), v(nullptr, nullptr);
+        cub::DeviceRadixSort::SortPairs(nullptr, b1, k, v, (int64_t)(n_elems ? n_elems : 1), 0, 32, (cudaStream_t)0);
+        cub::DeviceRadixSort::SortPairs(nullptr, b2, k, v, (int64_t)(n_isects ? n_isects : 1), 0, 32, (cudaStream_t)0);
+    }
+    L.cub_bytes = (b1 > b2 ? b1 : b2) + 256;
+    L.cub = take(L.cub_bytes);
+    L.end = o;
+    return L;
+}
+
+}  // namespace b2s
 
 using namespace b2s;
 
@@ -37,5 +176,65 @@ extern "C" int b200splat_isect_sort(uint64_t n_isects, uint32_t end_bit, int64_t
                                                     (cudaStream_t)stream);
     if (e != cudaSuccess) return fail_cuda(where, e);
     *selector_out = keys.selector;
+    return 0;
+}
+
+extern "C" size_t b200splat_isect_sorted_workspace_bytes(uint64_t n_elems, uint64_t n_isects) {
+    return sorted_layout(n_elems, n_isects).end;
+}
+
+extern "C" int b200splat_isect_sorted(int packed, uint32_t C, uint32_t N, uint32_t nnz, const int64_t *camera_ids,
+                                      const float *means2d, const int32_t *radii, const float *depths,
+                                      const int32_t *tiles_per_gauss, uint64_t n_isects, uint32_t tile_size,
+                                      uint32_t tile_width, uint32_t tile_height, int64_t *isect_ids,
+                                      int32_t *flatten_ids, void *workspace, size_t workspace_bytes, void *stream) {
+    const char *where = "b200splat_isect_sorted";
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint64_t n_elems = packed ? (uint64_t)nnz : (uint64_t)C * N;
+    B2S_REQUIRE(!packed || camera_ids != nullptr, where, "camera_ids required when packed");
+    B2S_REQUIRE(n_elems <= 0xffffffffull, where, "more than 2^32 (camera, Gaussian) pairs");
+    const uint32_t n_tiles = tile_width * tile_height;
+    uint32_t tile_n_bits = 0, cam_n_bits = 0;
+    for (uint32_t v = n_tiles; v; v >>= 1) ++tile_n_bits;
+    for (uint32_t v = C; v; v >>= 1) ++cam_n_bits;
+    B2S_REQUIRE(tile_n_bits + cam_n_bits <= 32, where, "camera and tile ids do not fit in 32 bits");
+    if (n_isects == 0 || n_elems == 0) return 0;
+    const SortedLayout L = sorted_layout(n_elems, n_isects);
+    B2S_REQUIRE(workspace != nullptr && workspace_bytes >= L.end, where,
+                "workspace too small (see b200splat_isect_sorted_workspace_bytes)");
+    char *ws = reinterpret_cast<char *>(workspace);
+    auto u32 = [&](size_t off) { return reinterpret_cast<uint32_t *>(ws + off); };
+
+    // 1. Gaussians by depth
+    depth_keys_kernel<<<div_up(n_elems, kThreads), kThreads, 0, st>>>(n_elems, tiles_per_gauss, depths, u32(L.gkeys_a),
+                                                                      u32(L.gvals_a));
+    B2S_CHECK_LAUNCH(where);
+    cub::DoubleBuffer<uint32_t> gk(u32(L.gkeys_a), u32(L.gkeys_b)), gv(u32(L.gvals_a), u32(L.gvals_b));
+    size_t cb = L.cub_bytes;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(ws + L.cub, cb, gk, gv, (int64_t)n_elems, 0, 32, st);
+    if (e != cudaSuccess) return fail_cuda(where, e);
+    const uint32_t *order = gv.Current();
+    // 2. offsets in depth order
+    int32_t *counts = reinterpret_cast<int32_t *>(ws + L.counts);
+    int64_t *cum = reinterpret_cast<int64_t *>(ws + L.cum);
+    gather_counts_kernel<<<div_up(n_elems, kThreads), kThreads, 0, st>>>(n_elems, order, tiles_per_gauss, counts);
+    B2S_CHECK_LAUNCH(where);
+    if (lookback_scan_i32_to_i64(counts, cum, n_elems, reinterpret_cast<int64_t *>(ws + L.total), ws + L.scan_ws,
+                                 L.scan_ws_bytes, st))
+        return fail(where, "scan failed");
+    // 3. expand
+    expand_kernel<<<div_up(n_elems, kThreads), kThreads, 0, st>>>(packed, N, n_elems, order, cum, camera_ids, means2d,
+                                                                  radii, (float)tile_size, tile_width, tile_height,
+                                                                  tile_n_bits, u32(L.tkeys_a), u32(L.tvals_a));
+    B2S_CHECK_LAUNCH(where);
+    // 4. stable sort by cam|tile
+    cub::DoubleBuffer<uint32_t> tk(u32(L.tkeys_a), u32(L.tkeys_b)), tv(u32(L.tvals_a), u32(L.tvals_b));
+    cb = L.cub_bytes;
+    e = cub::DeviceRadixSort::SortPairs(ws + L.cub, cb, tk, tv, (int64_t)n_isects, 0, (int)(tile_n_bits + cam_n_bits), st);
+    if (e != cudaSuccess) return fail_cuda(where, e);
+    // 5. assemble
+    assemble_kernel<<<div_up(n_isects, kThreads), kThreads, 0, st>>>(n_isects, tk.Current(), tv.Current(), depths,
+                                                                     isect_ids, flatten_ids);
+    B2S_CHECK_LAUNCH(where);
     return 0;
 }

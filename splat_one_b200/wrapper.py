@@ -33,6 +33,8 @@ CAMERA_MODELS = {"pinhole": 0, "ortho": 1, "fisheye": 2, "spherical": 3}  # CS/b
 _MAX_NATIVE_CHANNELS = 33
 # debugging / A-B switch: B200SPLAT_GENERIC_RASTER=1 disables the warp-per-tile raster kernels
 _FORCE_GENERIC_RASTER = os.environ.get("B200SPLAT_GENERIC_RASTER", "0") == "1"
+# same for the depth-first intersection ordering (falls back to fill + full 64-bit key sort)
+_FORCE_GENERIC_SORT = os.environ.get("B200SPLAT_GENERIC_SORT", "0") == "1"
 
 
 class _Profiler:
@@ -44,7 +46,7 @@ class _Profiler:
     KERNELS = {
         "projection_fwd": 1, "projection_bwd": 1, "projection_packed_count": 3, "projection_packed_fill": 1,
         "projection_packed_bwd": 1, "sh_fwd": 1, "sh_bwd": 1, "isect_count": 2, "isect_fill": 1,
-        "isect_sort": 0, "isect_offset_encode": 1, "rasterize_pack": 1, "rasterize_fwd": 1, "rasterize_bwd": 1,
+        "isect_sort": 0, "isect_sorted": 5, "isect_offset_encode": 1, "rasterize_pack": 1, "rasterize_fwd": 1, "rasterize_bwd": 1,
     }
 
     def __init__(self):
@@ -469,21 +471,30 @@ def isect_tiles(
     assert tile_n_bits + cam_n_bits <= 32, (tile_n_bits, cam_n_bits)
 
     tiles_per_gauss = torch.empty(radii.shape, device=dev, dtype=torch.int32)
-    n_isects = 0
+    n_isects, neg_depth = 0, False
     if n_elems:
         cum_tiles = torch.empty((n_elems,), device=dev, dtype=torch.int64)
-        n_isects_dev = torch.empty((1,), device=dev, dtype=torch.int64)
+        n_isects_dev = torch.empty((2,), device=dev, dtype=torch.int64)
         ws_bytes = lib.b200splat_scan_workspace_bytes(n_elems)
         ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
-        native("isect_count", lib, dev, int(packed), C, N, nnz, _ptr(means2d), _ptr(radii), tile_size, tile_width, tile_height,
-                _ptr(tiles_per_gauss), _ptr(cum_tiles), _ptr(n_isects_dev), _ptr(ws), ws_bytes)
-        n_isects = int(n_isects_dev.item())  # the one host sync (CS/isect_tiles.cu:201)
+        native("isect_count", lib, dev, int(packed), C, N, nnz, _ptr(means2d), _ptr(radii), _ptr(depths), tile_size,
+               tile_width, tile_height, _ptr(tiles_per_gauss), _ptr(cum_tiles), _ptr(n_isects_dev), _ptr(ws), ws_bytes)
+        n_isects, neg = n_isects_dev.tolist()  # the one host sync (CS/isect_tiles.cu:201)
+        neg_depth = bool(neg)
 
     isect_ids = torch.empty((n_isects,), device=dev, dtype=torch.int64)
     flatten_ids = torch.empty((n_isects,), device=dev, dtype=torch.int32)
     if n_isects:
-        native("isect_fill", lib, dev, int(packed), C, N, nnz, _ptr(camera_ids), _ptr(means2d), _ptr(radii), _ptr(depths),
-                _ptr(cum_tiles), tile_size, tile_width, tile_height, _ptr(isect_ids), _ptr(flatten_ids))
+        if sort and not neg_depth and not _FORCE_GENERIC_SORT:
+            # depth-first ordering (csrc/sort.cu): bit-identical to fill + full-key sort
+            ws_bytes = lib.b200splat_isect_sorted_workspace_bytes(n_elems, n_isects)
+            ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
+            native("isect_sorted", lib, dev, int(packed), C, N, nnz, _ptr(camera_ids), _ptr(means2d), _ptr(radii),
+                   _ptr(depths), _ptr(tiles_per_gauss), n_isects, tile_size, tile_width, tile_height,
+                   _ptr(isect_ids), _ptr(flatten_ids), _ptr(ws), ws_bytes)
+            return tiles_per_gauss, isect_ids, flatten_ids
+        native("isect_fill", lib, dev, int(packed), C, N, nnz, _ptr(camera_ids), _ptr(means2d), _ptr(radii),
+               _ptr(depths), _ptr(cum_tiles), tile_size, tile_width, tile_height, _ptr(isect_ids), _ptr(flatten_ids))
         if sort:
             isect_ids_alt = torch.empty_like(isect_ids)
             flatten_ids_alt = torch.empty_like(flatten_ids)
@@ -491,7 +502,7 @@ def isect_tiles(
             ws = torch.empty((max(ws_bytes, 1),), device=dev, dtype=torch.uint8)
             selector = ctypes.c_int(0)
             native("isect_sort", lib, dev, n_isects, 32 + tile_n_bits + cam_n_bits, _ptr(isect_ids), _ptr(flatten_ids),
-                    _ptr(isect_ids_alt), _ptr(flatten_ids_alt), _ptr(ws), ws_bytes, ctypes.byref(selector))
+                   _ptr(isect_ids_alt), _ptr(flatten_ids_alt), _ptr(ws), ws_bytes, ctypes.byref(selector))
             if selector.value == 1:
                 isect_ids, flatten_ids = isect_ids_alt, flatten_ids_alt
     return tiles_per_gauss, isect_ids, flatten_ids
