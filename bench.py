@@ -241,21 +241,39 @@ def run_gpu(args):
     out_a_host = torch.empty(C_local, HEIGHT, WIDTH, 1).pin_memory()
     gnorm_host = torch.empty(1).pin_memory()
 
+    copy_stream = torch.cuda.Stream(device=dev)
+
     def e2e_step():
+        """camera H2D -> forward -> (image D2H || cotangent H2D) -> backward -> grad-norm D2H.
+        The big copies run on a side stream so they overlap the kernels of the same step."""
+        main = torch.cuda.current_stream(dev)
         vm_d = vm_host.to(dev, non_blocking=True)
         K_d = K_host.to(dev, non_blocking=True)
-        vc_d = vc_host.to(dev, non_blocking=True)
-        va_d = va_host.to(dev, non_blocking=True)
+        with torch.cuda.stream(copy_stream):  # cotangents are only needed by the backward
+            vc_d = vc_host.to(dev, non_blocking=True)
+            va_d = va_host.to(dev, non_blocking=True)
+            cot_ready = torch.cuda.Event()
+            cot_ready.record(copy_stream)
         for p in params:
             p.grad = None
         rc_, ra_, _ = S.rasterization(*params, vm_d, K_d, WIDTH, HEIGHT, sh_degree=SH_DEGREE, packed=False)
+        fwd_done = torch.cuda.Event()
+        fwd_done.record(main)
+        with torch.cuda.stream(copy_stream):  # the rendered image leaves while the backward runs
+            copy_stream.wait_event(fwd_done)
+            out_c_host.copy_(rc_.detach(), non_blocking=True)
+            out_a_host.copy_(ra_.detach(), non_blocking=True)
+            rc_.record_stream(copy_stream)
+            ra_.record_stream(copy_stream)
+        main.wait_event(cot_ready)
+        vc_d.record_stream(main)
+        va_d.record_stream(main)
         torch.autograd.backward([rc_, ra_], [vc_d, va_d])
         if arena is not None:
             arena.gather_from_params()
             arena.all_reduce()
-        out_c_host.copy_(rc_.detach(), non_blocking=True)
-        out_a_host.copy_(ra_.detach(), non_blocking=True)
         gnorm_host.copy_(params[0].grad.norm().reshape(1), non_blocking=True)
+        main.wait_stream(copy_stream)
 
     for _ in range(2):
         e2e_step()
@@ -280,6 +298,10 @@ def run_gpu(args):
         alg_bytes = {  # SURVEY.md §8(d), per launch
             "projection_fwd": 40 * N + 4 * C * N + 24 * V,
             "sh_fwd": 216 * V,
+            "sh_colors_fwd": 216 * V + 4 * C * N,
+            "sh_colors_bwd": 228 * V + 192 * N + 4 * C * N,
+            "isect_sorted": 16 * V + 8 * C * N + 12 * I + 24 * I,
+            "rasterize_pack": 36 * C * N + 48 * C * N,
             "isect_count": 4 * C * N + 8 * V + 4 * C * N + 8 * C * N,
             "isect_fill": 16 * V + 8 * C * N + 12 * I,
             "isect_sort": 24 * I,

@@ -154,6 +154,27 @@ B200SPLAT_API int b200splat_sh_bwd(
     const float *v_colors,
     float *v_coeffs, float *v_dirs, void *stream);
 
+/* Fused colour stage of rasterization() for the unpacked layout (G/rendering.py:368-392:
+ * torch.inverse(viewmats)[:, :3, 3]; dirs = means - campos; spherical_harmonics(...,
+ * masks = radii > 0); clamp_min(colors + 0.5, 0)) as one kernel per direction.
+ *  camera_centers: campos [C,3] = inverse(viewmats)[:, :3, 3] (general 4x4).
+ *  sh_colors_fwd : colors [C,N,3] (zeros where radii <= 0).  per_view != 0: coeffs is
+ *                  [C,N,K,3], else one [N,K,3] table shared by the cameras.
+ *  sh_colors_bwd : v_coeffs ([N,K,3] or [C,N,K,3]) and v_means [N,3] (may be NULL), both
+ *                  fully overwritten; sums over cameras are done in registers. */
+B200SPLAT_API int b200splat_camera_centers(uint32_t C, const float *viewmats, float *campos, void *stream);
+
+B200SPLAT_API int b200splat_sh_colors_fwd(
+    uint32_t C, uint32_t N, uint32_t K, uint32_t degrees_to_use, int per_view,
+    const float *means, const float *campos, const float *coeffs, const int32_t *radii,
+    float *colors, void *stream);
+
+B200SPLAT_API int b200splat_sh_colors_bwd(
+    uint32_t C, uint32_t N, uint32_t K, uint32_t degrees_to_use, int per_view,
+    const float *means, const float *campos, const float *coeffs, const int32_t *radii,
+    const float *colors, const float *v_colors,
+    float *v_coeffs, float *v_means, void *stream);
+
 /* ------------------------------------------------------------------------------------
  * a6  isect_tiles                         CS/bindings.h:148-160, kernel
  *     CS/isect_tiles.cu:17-105, host :107-307.

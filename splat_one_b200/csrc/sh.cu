@@ -185,6 +185,132 @@ sh_bwd_kernel(uint32_t n_elems, uint32_t n_rows, uint32_t K, uint32_t deg, const
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Fused view-dependent colours for rasterization() (G/rendering.py:368-392):
+//   dirs = means - campos[c];  colors = clamp_min(SH(dirs, coeffs) + 0.5, 0);  masked by
+//   radii > 0.  One kernel instead of sub / compare / SH / add / clamp (and, backward,
+//   where / SH-bwd / sum over cameras / sub-bwd), and no [C,N,3] `dirs` tensor.
+// ---------------------------------------------------------------------------------------
+// camera centre = inverse(viewmat)[:3, 3], general 4x4 (adjugate, evaluated in double)
+__global__ void camera_centers_kernel(uint32_t C, const float *__restrict__ viewmats, float *__restrict__ out) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double m[4][4];
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) m[i][j] = (double)viewmats[16 * c + 4 * i + j];
+    // minor of (row r, col q): determinant of the 3x3 left after deleting them
+    auto minor3 = [&](int r, int q) {
+        int rr[3], cc[3], a = 0, b = 0;
+        for (int i = 0; i < 4; i++) if (i != r) rr[a++] = i;
+        for (int j = 0; j < 4; j++) if (j != q) cc[b++] = j;
+        return m[rr[0]][cc[0]] * (m[rr[1]][cc[1]] * m[rr[2]][cc[2]] - m[rr[1]][cc[2]] * m[rr[2]][cc[1]]) -
+               m[rr[0]][cc[1]] * (m[rr[1]][cc[0]] * m[rr[2]][cc[2]] - m[rr[1]][cc[2]] * m[rr[2]][cc[0]]) +
+               m[rr[0]][cc[2]] * (m[rr[1]][cc[0]] * m[rr[2]][cc[1]] - m[rr[1]][cc[1]] * m[rr[2]][cc[0]]);
+    };
+    double det = 0.0;
+    for (int j = 0; j < 4; j++) det += ((j & 1) ? -1.0 : 1.0) * m[0][j] * minor3(0, j);
+    // inv[i][3] = cofactor(3, i) / det
+    for (int i = 0; i < 3; i++) out[3 * c + i] = (float)((((3 + i) & 1) ? -1.0 : 1.0) * minor3(3, i) / det);
+}
+
+template <int NB>
+__global__ void __launch_bounds__(kThreads)
+sh_colors_fwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, int per_view, const float *__restrict__ means,
+                     const float *__restrict__ campos, const float *__restrict__ coeffs,
+                     const int32_t *__restrict__ radii, float *__restrict__ colors) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (uint64_t)C * N) return;
+    const uint32_t c = e / N, n = e % N;
+    float r = 0.f, g = 0.f, b = 0.f;
+    if (radii[e] > 0) {
+        const float *row = coeffs + (per_view ? e : (uint64_t)n) * K * 3;
+        float cf[NB * 3];
+        load_row<NB>(row, cf, ((K * 3) % 4 == 0) && ((reinterpret_cast<uintptr_t>(coeffs) & 15) == 0));
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (NB > 1) {
+            const float dx = __ldg(means + 3 * n) - campos[3 * c], dy = __ldg(means + 3 * n + 1) - campos[3 * c + 1],
+                        dz = __ldg(means + 3 * n + 2) - campos[3 * c + 2];
+            const float inorm = rsqrtf(dx * dx + dy * dy + dz * dz);
+            x = dx * inorm; y = dy * inorm; z = dz * inorm;
+        }
+        sh_for_each_basis<false>(deg, x, y, z, [&](int k, float B, float, float, float) {
+            r += B * cf[3 * k]; g += B * cf[3 * k + 1]; b += B * cf[3 * k + 2];
+        });
+        r = fmaxf(r + 0.5f, 0.f); g = fmaxf(g + 0.5f, 0.f); b = fmaxf(b + 0.5f, 0.f);
+    }
+    colors[3 * e] = r; colors[3 * e + 1] = g; colors[3 * e + 2] = b;
+}
+
+// One thread per Gaussian, loop over cameras: v_coeffs (shared table) and v_means are
+// written once, without atomics.  The clamp passes gradient where the clamped colour > 0.
+template <int NB>
+__global__ void __launch_bounds__(kThreads)
+sh_colors_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, int per_view, const float *__restrict__ means,
+                     const float *__restrict__ campos, const float *__restrict__ coeffs,
+                     const int32_t *__restrict__ radii, const float *__restrict__ colors,
+                     const float *__restrict__ v_colors, float *__restrict__ v_coeffs, float *__restrict__ v_means) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const bool vec_ok = ((K * 3) % 4 == 0) && ((reinterpret_cast<uintptr_t>(v_coeffs) & 15) == 0);
+    // vc accumulates over the cameras for a shared table; per-view tables flush it per camera
+    float vc[NB * 3];
+#pragma unroll
+    for (int k = 0; k < NB * 3; k++) vc[k] = 0.f;
+    float vmx = 0.f, vmy = 0.f, vmz = 0.f;
+    const float mx = __ldg(means + 3 * n), my = __ldg(means + 3 * n + 1), mz = __ldg(means + 3 * n + 2);
+    auto flush = [&](float *vrow) {
+        if ((NB * 3) % 4 == 0 && vec_ok) {
+            float4 *o = reinterpret_cast<float4 *>(vrow);
+#pragma unroll
+            for (int k = 0; k < NB * 3 / 4; k++) __stcs(o + k, make_float4(vc[4 * k], vc[4 * k + 1], vc[4 * k + 2], vc[4 * k + 3]));
+            for (uint32_t k = NB * 3 / 4; k < K * 3 / 4; k++) __stcs(o + k, make_float4(0.f, 0.f, 0.f, 0.f));
+        } else {
+#pragma unroll
+            for (int k = 0; k < NB * 3; k++) vrow[k] = vc[k];
+            for (uint32_t k = NB * 3; k < K * 3; k++) vrow[k] = 0.f;
+        }
+    };
+    for (uint32_t c = 0; c < C; ++c) {
+        const uint64_t e = (uint64_t)c * N + n;
+        if (radii[e] > 0) {
+            const float vr = colors[3 * e] > 0.f ? v_colors[3 * e] : 0.f;
+            const float vg = colors[3 * e + 1] > 0.f ? v_colors[3 * e + 1] : 0.f;
+            const float vb = colors[3 * e + 2] > 0.f ? v_colors[3 * e + 2] : 0.f;
+            float x = 0.f, y = 0.f, z = 0.f, inorm = 0.f;
+            if (NB > 1) {
+                const float dx = mx - campos[3 * c], dy = my - campos[3 * c + 1], dz = mz - campos[3 * c + 2];
+                inorm = rsqrtf(dx * dx + dy * dy + dz * dz);
+                x = dx * inorm; y = dy * inorm; z = dz * inorm;
+            }
+            if (v_means != nullptr && NB > 1) {
+                const float4 *row4 = reinterpret_cast<const float4 *>(coeffs + (per_view ? e : (uint64_t)n) * K * 3);
+                const float *row = coeffs + (per_view ? e : (uint64_t)n) * K * 3;
+                float vx = 0.f, vy = 0.f, vz = 0.f;
+                (void)row4;
+                sh_for_each_basis<true>(deg, x, y, z, [&](int k, float B, float Bx, float By, float Bz) {
+                    vc[3 * k] += B * vr; vc[3 * k + 1] += B * vg; vc[3 * k + 2] += B * vb;
+                    const float w = __ldg(row + 3 * k) * vr + __ldg(row + 3 * k + 1) * vg + __ldg(row + 3 * k + 2) * vb;
+                    vx += Bx * w; vy += By * w; vz += Bz * w;
+                });
+                const float d = vx * x + vy * y + vz * z;
+                vmx += (vx - d * x) * inorm; vmy += (vy - d * y) * inorm; vmz += (vz - d * z) * inorm;
+            } else {
+                sh_for_each_basis<false>(deg, x, y, z, [&](int k, float B, float, float, float) {
+                    vc[3 * k] += B * vr; vc[3 * k + 1] += B * vg; vc[3 * k + 2] += B * vb;
+                });
+            }
+        }
+        if (per_view) {
+            flush(v_coeffs + e * K * 3);
+#pragma unroll
+            for (int k = 0; k < NB * 3; k++) vc[k] = 0.f;
+        }
+    }
+    if (!per_view) flush(v_coeffs + (uint64_t)n * K * 3);
+    if (v_means != nullptr) { v_means[3 * n] = vmx; v_means[3 * n + 1] = vmy; v_means[3 * n + 2] = vmz; }
+}
+
 }  // namespace b2s
 
 using namespace b2s;
@@ -226,6 +352,58 @@ extern "C" int b200splat_sh_bwd(uint32_t n_elems, uint32_t n_rows, uint32_t K, u
         case 3: sh_bwd_kernel<16><<<grid, kThreads, 0, st>>>(n_elems, n_rows, K, deg, dirs, coeffs, masks, v_colors, v_coeffs, v_dirs); break;
         default: sh_bwd_kernel<25><<<grid, kThreads, 0, st>>>(n_elems, n_rows, K, deg, dirs, coeffs, masks, v_colors, v_coeffs, v_dirs); break;
     }
+    B2S_CHECK_LAUNCH(where);
+    return 0;
+}
+
+extern "C" int b200splat_camera_centers(uint32_t C, const float *viewmats, float *campos, void *stream) {
+    if (C == 0) return 0;
+    camera_centers_kernel<<<div_up(C, 64), 64, 0, (cudaStream_t)stream>>>(C, viewmats, campos);
+    B2S_CHECK_LAUNCH("b200splat_camera_centers");
+    return 0;
+}
+
+extern "C" int b200splat_sh_colors_fwd(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, int per_view,
+                                       const float *means, const float *campos, const float *coeffs,
+                                       const int32_t *radii, float *colors, void *stream) {
+    const char *where = "b200splat_sh_colors_fwd";
+    B2S_REQUIRE(deg <= 4, where, "degrees_to_use must be <= 4");
+    B2S_REQUIRE((deg + 1) * (deg + 1) <= K, where, "K too small for degrees_to_use");
+    if ((uint64_t)C * N == 0) return 0;
+    const unsigned grid = div_up((uint64_t)C * N, kThreads);
+    cudaStream_t st = (cudaStream_t)stream;
+#define B2S_SHC(NBV) sh_colors_fwd_kernel<NBV><<<grid, kThreads, 0, st>>>(C, N, K, deg, per_view, means, campos, coeffs, radii, colors)
+    switch (deg) {
+        case 0: B2S_SHC(1); break;
+        case 1: B2S_SHC(4); break;
+        case 2: B2S_SHC(9); break;
+        case 3: B2S_SHC(16); break;
+        default: B2S_SHC(25); break;
+    }
+#undef B2S_SHC
+    B2S_CHECK_LAUNCH(where);
+    return 0;
+}
+
+extern "C" int b200splat_sh_colors_bwd(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, int per_view,
+                                       const float *means, const float *campos, const float *coeffs,
+                                       const int32_t *radii, const float *colors, const float *v_colors,
+                                       float *v_coeffs, float *v_means, void *stream) {
+    const char *where = "b200splat_sh_colors_bwd";
+    B2S_REQUIRE(deg <= 4, where, "degrees_to_use must be <= 4");
+    B2S_REQUIRE((deg + 1) * (deg + 1) <= K, where, "K too small for degrees_to_use");
+    if (N == 0) return 0;
+    const unsigned grid = div_up(N, kThreads);
+    cudaStream_t st = (cudaStream_t)stream;
+#define B2S_SHC(NBV) sh_colors_bwd_kernel<NBV><<<grid, kThreads, 0, st>>>(C, N, K, deg, per_view, means, campos, coeffs, radii, colors, v_colors, v_coeffs, v_means)
+    switch (deg) {
+        case 0: B2S_SHC(1); break;
+        case 1: B2S_SHC(4); break;
+        case 2: B2S_SHC(9); break;
+        case 3: B2S_SHC(16); break;
+        default: B2S_SHC(25); break;
+    }
+#undef B2S_SHC
     B2S_CHECK_LAUNCH(where);
     return 0;
 }

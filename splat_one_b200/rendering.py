@@ -25,8 +25,8 @@ from .wrapper import (
     isect_offset_encode,
     isect_tiles,
     rasterize_to_pixels,
+    sh_view_colors,
     spherical_harmonics,
-    spherical_harmonics_table,
 )
 
 
@@ -115,7 +115,7 @@ def rasterization(
         opacities = opacities[gaussian_ids]  # [nnz]
     else:
         radii, means2d, depths, conics, compensations = proj_results
-        opacities = opacities.repeat(C, 1)  # [C, N]
+        opacities = opacities[None].expand(C, -1)  # [C, N]; no copy when C == 1 (reference: .repeat)
         camera_ids, gaussian_ids = None, None
 
     if compensations is not None:
@@ -138,20 +138,19 @@ def rasterization(
         else:
             colors = colors.expand(C, -1, -1) if colors.dim() == 2 else colors
     else:
-        camtoworlds = torch.inverse(viewmats)  # [C, 4, 4]
-        if packed:
-            dirs = means[gaussian_ids, :] - camtoworlds[camera_ids, :3, 3]  # [nnz, 3]
-            masks = radii > 0
-            shs = colors[gaussian_ids, :, :] if colors.dim() == 3 else colors[camera_ids, gaussian_ids, :, :]
-            colors = spherical_harmonics(sh_degree, dirs, shs, masks=masks)  # [nnz, 3]
-        else:
-            dirs = means[None, :, :] - camtoworlds[:, None, :3, 3]  # [C, N, 3]
-            masks = radii > 0
-            if colors.dim() == 3:
-                colors = spherical_harmonics_table(sh_degree, dirs, colors, masks=masks)  # [C, N, 3]
+        if packed or viewmats.requires_grad:
+            camtoworlds = torch.inverse(viewmats)  # [C, 4, 4]
+            if packed:
+                dirs = means[gaussian_ids, :] - camtoworlds[camera_ids, :3, 3]  # [nnz, 3]
+                shs = colors[gaussian_ids, :, :] if colors.dim() == 3 else colors[camera_ids, gaussian_ids, :, :]
             else:
-                colors = spherical_harmonics(sh_degree, dirs, colors, masks=masks)  # [C, N, 3]
-        colors = torch.clamp_min(colors + 0.5, 0.0)  # rendering.py:392
+                dirs = means[None, :, :] - camtoworlds[:, None, :3, 3]  # [C, N, 3]
+                shs = colors.expand(C, -1, -1, -1) if colors.dim() == 3 else colors
+            colors = spherical_harmonics(sh_degree, dirs, shs, masks=radii > 0)
+            colors = torch.clamp_min(colors + 0.5, 0.0)  # rendering.py:392
+        else:
+            # same maths, one fused kernel per direction (no dirs / mask / +0.5 / clamp passes)
+            colors = sh_view_colors(sh_degree, means, viewmats, colors, radii)  # [C, N, 3]
 
     # ---- depth channel (rendering.py:481-492) ---------------------------------------
     if render_mode in ["RGB+D", "RGB+ED"]:

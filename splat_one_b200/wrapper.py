@@ -45,7 +45,8 @@ class _Profiler:
     # launches are CUB's and counted separately as "library"
     KERNELS = {
         "projection_fwd": 1, "projection_bwd": 1, "projection_packed_count": 3, "projection_packed_fill": 1,
-        "projection_packed_bwd": 1, "sh_fwd": 1, "sh_bwd": 1, "isect_count": 2, "isect_fill": 1,
+        "projection_packed_bwd": 1, "sh_fwd": 1, "sh_bwd": 1, "camera_centers": 1, "sh_colors_fwd": 1,
+        "sh_colors_bwd": 1, "isect_count": 2, "isect_fill": 1,
         "isect_sort": 0, "isect_sorted": 5, "isect_offset_encode": 1, "rasterize_pack": 1, "rasterize_fwd": 1, "rasterize_bwd": 1,
     }
 
@@ -217,6 +218,69 @@ class _SphericalHarmonics(torch.autograd.Function):
         return None, v_dirs, v_coeffs, None, None
 
 
+def camera_centers(viewmats: Tensor) -> Tensor:
+    """`torch.inverse(viewmats)[:, :3, 3]` (G/rendering.py:370, 382) as one tiny kernel
+    (general 4x4 inverse, evaluated in double); no gradient."""
+    viewmats = viewmats.detach().contiguous()
+    _check_cuda(viewmats)
+    _f32(viewmats)
+    lib = get_lib()
+    out = torch.empty((viewmats.shape[0], 3), device=viewmats.device, dtype=torch.float32)
+    if viewmats.shape[0]:
+        native("camera_centers", lib, viewmats.device, viewmats.shape[0], _ptr(viewmats), _ptr(out))
+    return out
+
+
+def sh_view_colors(sh_degree: int, means: Tensor, viewmats: Tensor, coeffs: Tensor, radii: Tensor) -> Tensor:
+    """The colour stage of `rasterization()` for the unpacked layout, fused:
+
+        dirs = means[None] - inverse(viewmats)[:, None, :3, 3]
+        colors = clamp_min(spherical_harmonics(deg, dirs, coeffs, masks=radii > 0) + 0.5, 0)
+
+    (G/rendering.py:368-392).  means [N,3], coeffs [N,K,3] or [C,N,K,3], radii [C,N] int32 ->
+    colors [C,N,3].  Differentiable w.r.t. means and coeffs (not viewmats: callers that
+    optimise poses use the unfused operators)."""
+    C, N = radii.shape
+    assert means.shape == (N, 3), means.shape
+    assert coeffs.shape[-1] == 3 and (coeffs.shape[:-2] == (N,) or coeffs.shape[:-2] == (C, N)), coeffs.shape
+    assert (sh_degree + 1) ** 2 <= coeffs.shape[-2], coeffs.shape
+    campos = camera_centers(viewmats)
+    return _ShViewColors.apply(sh_degree, means.contiguous(), campos, coeffs.contiguous(), radii.contiguous())
+
+
+class _ShViewColors(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sh_degree, means, campos, coeffs, radii):
+        _check_cuda(means, campos, coeffs, radii)
+        _f32(means), _f32(coeffs)
+        lib = get_lib()
+        C, N = radii.shape
+        K = coeffs.shape[-2]
+        per_view = int(coeffs.dim() == 4)
+        colors = torch.empty((C, N, 3), device=means.device, dtype=torch.float32)
+        if C * N:
+            native("sh_colors_fwd", lib, means.device, C, N, K, sh_degree, per_view, _ptr(means), _ptr(campos),
+                   _ptr(coeffs), _ptr(radii), _ptr(colors))
+        ctx.save_for_backward(means, campos, coeffs, radii, colors)
+        ctx.sh_degree = sh_degree
+        return colors
+
+    @staticmethod
+    def backward(ctx, v_colors):
+        means, campos, coeffs, radii, colors = ctx.saved_tensors
+        lib = get_lib()
+        C, N = radii.shape
+        K = coeffs.shape[-2]
+        per_view = int(coeffs.dim() == 4)
+        v_coeffs = torch.empty_like(coeffs)
+        v_means = torch.empty_like(means) if ctx.needs_input_grad[1] else None
+        if N:
+            native("sh_colors_bwd", lib, means.device, C, N, K, ctx.sh_degree, per_view, _ptr(means), _ptr(campos),
+                   _ptr(coeffs), _ptr(radii), _ptr(colors), _ptr(v_colors.contiguous()), _ptr(v_coeffs),
+                   _ptr(v_means))
+        return None, v_means, None, (v_coeffs if ctx.needs_input_grad[3] else None), None
+
+
 # ----------------------------------------------------------------------------------------
 # projection (a2, a3, a4)
 # ----------------------------------------------------------------------------------------
@@ -287,11 +351,16 @@ class _FullyFusedProjection(torch.autograd.Function):
         quats = _aligned16(quats)
         C, N = viewmats.shape[0], means.shape[0]
         dev = means.device
-        radii = torch.zeros((C, N), device=dev, dtype=torch.int32)
-        means2d = torch.zeros((C, N, 2), device=dev, dtype=torch.float32)
-        depths = torch.zeros((C, N), device=dev, dtype=torch.float32)
-        conics = torch.zeros((C, N, 3), device=dev, dtype=torch.float32)
-        compensations = torch.zeros((C, N), device=dev, dtype=torch.float32) if calc_compensations else None
+        # one allocation, one fill: radii | means2d | depths | conics (| compensations) as views
+        # of a zeroed flat buffer (culled entries read as zeros; the reference leaves them
+        # uninitialised, CS/fully_fused_projection_fwd.cu:256-260)
+        n = C * N
+        flat = torch.zeros((n * (8 if calc_compensations else 7),), device=dev, dtype=torch.float32)
+        radii = flat[:n].view(torch.int32).view(C, N)
+        means2d = flat[n:3 * n].view(C, N, 2)
+        depths = flat[3 * n:4 * n].view(C, N)
+        conics = flat[4 * n:7 * n].view(C, N, 3)
+        compensations = flat[7 * n:8 * n].view(C, N) if calc_compensations else None
         if C and N:
             native("projection_fwd", lib, dev, C, N, _ptr(means), _ptr(covars), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks),
                     width, height, eps2d, near_plane, far_plane, radius_clip, CAMERA_MODELS[camera_model],
@@ -653,11 +722,15 @@ class _RasterizeToPixels(torch.autograd.Function):
         n_isects = flatten_ids.numel()
         v_render_colors = v_render_colors.contiguous()
         v_render_alphas = v_render_alphas.contiguous()
-        v_means2d = torch.zeros_like(means2d)
-        v_conics = torch.zeros_like(conics)
-        v_colors = torch.zeros_like(colors)
-        v_opacities = torch.zeros_like(opacities)
-        v_means2d_abs = torch.zeros_like(means2d) if ctx.absgrad else None
+        # one allocation, one fill for all accumulated gradients
+        per = 2 + 3 + channels + 1 + (2 if ctx.absgrad else 0)
+        flat = torch.zeros((n_gauss * per,), device=dev, dtype=torch.float32)
+        o = 0
+        v_means2d = flat[o:o + 2 * n_gauss].view_as(means2d); o += 2 * n_gauss
+        v_conics = flat[o:o + 3 * n_gauss].view_as(conics); o += 3 * n_gauss
+        v_colors = flat[o:o + channels * n_gauss].view_as(colors); o += channels * n_gauss
+        v_opacities = flat[o:o + n_gauss].view_as(opacities); o += n_gauss
+        v_means2d_abs = flat[o:o + 2 * n_gauss].view_as(means2d) if ctx.absgrad else None
         means2d_a = _aligned16(means2d) if means2d.data_ptr() % 8 else means2d
         if n_isects and render_alphas.numel():
             native("rasterize_bwd", lib, dev, C, n_gauss, n_isects, channels, _ptr(means2d_a), _ptr(conics), _ptr(colors), _ptr(opacities),

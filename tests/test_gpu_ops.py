@@ -412,3 +412,32 @@ def test_raster_fast_and_generic_kernels_agree(monkeypatch):
     assert ((ra0 - ra1).abs() > 1e-4).float().mean() < 1e-3
     for a, b in zip(g0, g1):
         assert_grad_close(a, b, rtol=2e-3, frac_ok=0.995)
+
+
+@pytest.mark.parametrize("per_view", [False, True])
+@pytest.mark.parametrize("deg", [0, 2, 3])
+def test_sh_view_colors_fused(per_view, deg):
+    """Fused dirs + SH + 0.5 + clamp (+ its backward) == the unfused reference chain."""
+    from splat_one_b200.wrapper import camera_centers, sh_view_colors
+
+    torch.manual_seed(deg)
+    C, N, K = 3, 2000, 16
+    means = torch.randn(N, 3)
+    vm = _cams(C)
+    vm[2, :3, :3] = vm[2, :3, :3] * 1.3  # non-rigid view matrix: the centre needs a general inverse
+    table = torch.randn(C, N, K, 3) * 0.4 if per_view else torch.randn(N, K, 3) * 0.4
+    radii = (torch.rand(C, N) > 0.25).int() * 5
+    v = torch.randn(C, N, 3)
+    torch.testing.assert_close(camera_centers(vm.to(DEV)).cpu(), torch.inverse(vm)[:, :3, 3], rtol=1e-5, atol=1e-5)
+    m_c, t_c = means.clone().requires_grad_(), table.clone().requires_grad_()
+    dirs = m_c[None] - torch.inverse(vm)[:, None, :3, 3]
+    shs = t_c if per_view else t_c.expand(C, -1, -1, -1)
+    ref = torch.clamp_min(O.spherical_harmonics(deg, dirs, shs, radii > 0) + 0.5, 0.0)
+    ref = torch.where((radii > 0)[..., None], ref, torch.zeros_like(ref))
+    g_ref = torch.autograd.grad((ref * v).sum(), (m_c, t_c))
+    m_g, t_g = means.to(DEV).requires_grad_(), table.to(DEV).requires_grad_()
+    got = sh_view_colors(deg, m_g, vm.to(DEV), t_g, radii.to(DEV))
+    torch.testing.assert_close(got.cpu(), ref, rtol=1e-4, atol=1e-4)
+    g_got = torch.autograd.grad((got * v.to(DEV)).sum(), (m_g, t_g))
+    torch.testing.assert_close(g_got[0].cpu(), g_ref[0], rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(g_got[1].cpu(), g_ref[1], rtol=1e-4, atol=1e-4)
