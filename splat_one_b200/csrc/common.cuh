@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string>
 
 #include "../../include/b200splat.h"
@@ -28,6 +29,12 @@ int fail_cuda(const char *where, cudaError_t e);
     do {                                                                                \
         if (!(cond)) return b2s::fail(where, msg);                                      \
     } while (0)
+
+// Developer A/B switch for kernel variants (tools/raster_bench.py); 0 = the shipped default.
+static inline int tuning_variant() {
+    const char *e = getenv("B200SPLAT_TUNING_VARIANT");
+    return e ? atoi(e) : 0;
+}
 
 static inline unsigned div_up(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
 

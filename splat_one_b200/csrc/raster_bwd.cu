@@ -10,7 +10,7 @@
 // (reduce-scatter) butterfly — 16 SHFL for up to 16 values — which leaves value k in
 // lane 2k, so a single RED instruction with <= 16 active lanes commits all of them.
 #include "raster_common.cuh"
-#include "raster_v2.cuh"
+#include "raster_v3.cuh"
 
 namespace b2s {
 
@@ -221,15 +221,16 @@ static void launch_bwd(uint32_t C, uint64_t n_isects, uint32_t channels, const f
 
 
 // ---------------------------------------------------------------------------------------
-// v2: warp-per-tile, 8 pixels per lane, culled staging (see raster_v2.cuh).
-// Per (tile, Gaussian): each lane folds its 8 pixels into 3 colour sums and the moments
+// v3: warp-per-tile, 8 sub-block slots per lane, exact sub-block culling (raster_v3.cuh).
+// Per (tile, Gaussian): each lane folds its (up to) 8 pixels into CDIM colour sums and, per
+// column half (dx is shared by the four slots of a half), the moments
 //   W0 = sum v_sigma,  W1 = sum v_sigma·dy,  W2 = sum v_sigma·dy²
-// (dx is shared by the lane's pixels), converts them to the 9 gradient values, and ONE
-// reduce-scatter butterfly + one RED per value commits them.
+// converts them to the 9 gradient values, and ONE reduce-scatter butterfly + one RED per
+// value commits them.
 // ---------------------------------------------------------------------------------------
-template <int CDIM, bool ABS>
-__global__ void __launch_bounds__(kV2Warps * 32)
-raster_bwd_v2_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channels, const float4 *__restrict__ rec,
+template <int CDIM, bool ABS, int NS, int MINB>
+__global__ void __launch_bounds__(32 * (kV3Slots / NS), MINB)
+raster_bwd_v3_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channels, const float4 *__restrict__ rec,
                      const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks, uint32_t W, uint32_t H,
                      uint32_t tile_width, uint32_t tile_height, const int32_t *__restrict__ tile_offsets,
                      const int32_t *__restrict__ flatten_ids, const float *__restrict__ render_alphas,
@@ -238,46 +239,47 @@ raster_bwd_v2_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channel
                      float *__restrict__ v_means2d, float *__restrict__ v_conics, float *__restrict__ v_colors,
                      float *__restrict__ v_opacities) {
     constexpr int NV = CDIM + 6 + (ABS ? 2 : 0);
-    __shared__ float4 s_rec[kV2Warps][32 * 3];
-    __shared__ int32_t s_idx[kV2Warps][32];
-    __shared__ int32_t s_gid[kV2Warps][32];
-    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint32_t tile_lin = blockIdx.x * kV2Warps + wid;
-    if (tile_lin >= n_tiles_total) return;
+    // a CTA is one tile; each of its warps owns NS of the 8 sub-blocks and works on its own
+    __shared__ float4 s_rec_all[kV3Slots / NS][32 * 3];
+    __shared__ int4 s_im_all[kV3Slots / NS][32];  // {sorted index, sub-block mask, Gaussian row, -}
+    const unsigned lane = threadIdx.x & 31, sub = threadIdx.x >> 5;
+    float4 *s_rec = s_rec_all[sub];
+    int4 *s_im = s_im_all[sub];
+    const uint32_t tile_lin = blockIdx.x;
     if (masks != nullptr && !masks[tile_lin]) return;
-    const V2Tile tc = v2_tile(tile_lin, tile_width, tile_height, W, H, lane);
-    const size_t pix0 = ((size_t)tc.cam * H + tc.y0) * W + tc.x;
-
     const int32_t range_start = tile_offsets[tile_lin];
     const int32_t range_end = (tile_lin == n_tiles_total - 1) ? (int32_t)n_isects : tile_offsets[tile_lin + 1];
     if (range_end <= range_start) return;
+    const V3Tile tc = v3_tile<NS>(tile_lin, tile_width, tile_height, lane, sub);
+    const size_t cam_pix = (size_t)tc.cam * H * W;
 
-    // per-pixel state.  bv = sum_k buffer_k * v_c_k replaces the reference's per-channel
-    // `buffer` (CS/rasterize_to_pixels_bwd.cu:203-241): v_alpha only ever needs that dot product.
-    float T[kV2Rows], tfa[kV2Rows], bv[kV2Rows];  // tfa = T_final * (v_alpha_out - sum_k bg_k v_c_k)
-    float v_c[kV2Rows][CDIM];
-    int32_t binf[kV2Rows];
+    // per-pixel state.  tb = T_final (v_alpha_out - sum_k bg_k v_c_k) - sum_k buffer_k v_c_k folds
+    // the reference's per-channel `buffer` (CS/rasterize_to_pixels_bwd.cu:203-241): v_alpha only
+    // ever needs that dot product.
+    float T[NS], tb[NS], v_c[NS][CDIM];
+    int32_t binf[NS];
     int32_t max_bin = -1;
 #pragma unroll
-    for (int j = 0; j < kV2Rows; ++j) {
-        T[j] = 1.f; tfa[j] = 0.f; bv[j] = 0.f; binf[j] = -1;
+    for (int s = 0; s < NS; ++s) {
+        T[s] = 1.f; tb[s] = 0.f; binf[s] = -1;
 #pragma unroll
-        for (int k = 0; k < CDIM; ++k) v_c[j][k] = 0.f;
-        if (tc.row_mask >> j & 1) {
-            const size_t p = pix0 + (size_t)j * W;
+        for (int k = 0; k < CDIM; ++k) v_c[s][k] = 0.f;
+        const uint32_t x = tc.x + 8u * (s & 1), y = tc.y + 4u * (s >> 1);
+        if (x < W && y < H) {
+            const size_t p = cam_pix + (size_t)y * W + x;
             const float T_final = 1.f - render_alphas[p];
-            T[j] = T_final;
-            binf[j] = last_ids[p];
+            T[s] = T_final;
+            binf[s] = last_ids[p];
             float bg_dot = 0.f;
 #pragma unroll
             for (int k = 0; k < CDIM; ++k) {
                 if (k < (int)channels) {
-                    v_c[j][k] = v_render_colors[p * channels + k];
-                    if (backgrounds != nullptr) bg_dot += backgrounds[(size_t)tc.cam * channels + k] * v_c[j][k];
+                    v_c[s][k] = v_render_colors[p * channels + k];
+                    if (backgrounds != nullptr) bg_dot += backgrounds[(size_t)tc.cam * channels + k] * v_c[s][k];
                 }
             }
-            tfa[j] = T_final * (v_render_alphas[p] - bg_dot);
-            max_bin = max(max_bin, binf[j]);
+            tb[s] = T_final * (v_render_alphas[p] - bg_dot);
+            max_bin = max(max_bin, binf[s]);
         }
     }
     max_bin = warp_max(max_bin);
@@ -291,17 +293,22 @@ raster_bwd_v2_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channel
         my_g = flatten_ids[my_idx];
         r0 = __ldg(rec + 3 * (size_t)my_g); r1 = __ldg(rec + 3 * (size_t)my_g + 1); r2 = __ldg(rec + 3 * (size_t)my_g + 2);
     }
+    uint32_t act = 0;  // warp-uniform: slots with a pixel whose last contributor is inside the batches seen so far
     for (int32_t hi = hi0; hi >= range_start; hi -= 32) {
-        const bool keep = (my_idx >= range_start) &&
-                          tile_may_contribute(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tc.rx0, tc.ry0, tc.rx1, tc.ry1);
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        const int32_t lo = max(hi - 31, range_start);
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+            if (!(act >> s & 1) && __any_sync(0xffffffffu, binf[s] >= lo)) act |= 1u << s;
+        uint32_t my_mask = 0;
+        if (my_idx >= range_start)
+            my_mask = subblock_mask<NS>(r0.x, r0.y, r0.z, r0.w, r1.x, r2.z, tc.ox, tc.oy, W, H) & act;
+        const unsigned bal = __ballot_sync(0xffffffffu, my_mask != 0);
         const int n = __popc(bal);
         __syncwarp();
-        if (keep) {
+        if (my_mask != 0) {
             const int pos = __popc(bal & ((1u << lane) - 1u));
-            s_rec[wid][3 * pos] = r0; s_rec[wid][3 * pos + 1] = r1; s_rec[wid][3 * pos + 2] = r2;
-            s_idx[wid][pos] = my_idx;
-            s_gid[wid][pos] = my_g;
+            s_rec[3 * pos] = r0; s_rec[3 * pos + 1] = r1; s_rec[3 * pos + 2] = r2;
+            s_im[pos] = make_int4(my_idx, (int)my_mask, my_g, 0);
         }
         __syncwarp();
         my_idx = hi - 32 - (int32_t)lane;
@@ -310,67 +317,67 @@ raster_bwd_v2_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channel
             r0 = __ldg(rec + 3 * (size_t)my_g); r1 = __ldg(rec + 3 * (size_t)my_g + 1); r2 = __ldg(rec + 3 * (size_t)my_g + 2);
         }
         for (int t = 0; t < n; ++t) {
-            const float4 a = s_rec[wid][3 * t], b4 = s_rec[wid][3 * t + 1], c4 = s_rec[wid][3 * t + 2];
-            const int32_t idx = s_idx[wid][t];
-            const float dx = a.x - tc.px, dy0 = a.y - tc.py0;
+            const float4 a = s_rec[3 * t], b4 = s_rec[3 * t + 1], c4 = s_rec[3 * t + 2];
+            const int4 im = s_im[t];
+            const int32_t idx = im.x;
+            const uint32_t m = (uint32_t)im.y;
+            const float dxa = a.x - tc.px, dxb = dxa - 8.f, dyv = a.y - tc.py;
             const float hA = a.z, cb = a.w, hC = b4.x, opac = b4.y;
-            const float A = hA * dx * dx, B = cb * dx;
+            const float Aa = hA * dxa * dxa, Ba = cb * dxa, Ab = hA * dxb * dxb, Bb = cb * dxb;
             const float col[4] = {b4.z, b4.w, c4.x, c4.y};
-            // phase 1 (branch-free, 8 independent chains): which of the lane's pixels accept
-            float ovs[kV2Rows];
-            uint32_t acc = 0;
-#pragma unroll
-            for (int j = 0; j < kV2Rows; ++j) {
-                const float dy = dy0 - (float)j;
-                const float sigma = A + dy * (B + hC * dy);
-                ovs[j] = opac * __expf(-sigma);
-                if (sigma >= 0.f && fminf(kAlphaMax, ovs[j]) >= kAlphaMin && idx <= binf[j]) acc |= 1u << j;
-            }
-            const uint32_t rows = __reduce_or_sync(0xffffffffu, acc);
-            if (rows == 0) continue;
-            // phase 2: a pixel row is skipped with a WARP-UNIFORM branch when no lane needs it
-            // and runs predicated otherwise (a rejected pixel has alpha = 0: ra = 1, fac = 0,
-            // v_sigma = 0), so there is no divergence and the chains interleave
             float v[NV];
 #pragma unroll
             for (int k = 0; k < NV; ++k) v[k] = 0.f;
-            float W0 = 0.f, W1 = 0.f, W2 = 0.f;
+            float W0[2] = {0.f, 0.f}, W1[2] = {0.f, 0.f}, W2[2] = {0.f, 0.f};
+            bool hit = false;
 #pragma unroll
-            for (int j = 0; j < kV2Rows; ++j) {
-                if (rows >> j & 1) {
-                    const bool ok = acc >> j & 1;
-                    const float dy = dy0 - (float)j;
-                    const float ov = ovs[j];
-                    const float alpha = ok ? fminf(kAlphaMax, ov) : 0.f;
-                    const float ra = __fdividef(1.f, 1.f - alpha);
-                    const float Tn = T[j] * ra;
-                    T[j] = Tn;
-                    const float fac = alpha * Tn;
+            for (int s = 0; s < NS; ++s) {
+                if (m >> s & 1) {  // warp-uniform
+                    const float dy = dyv - 4.f * (float)(s >> 1);
+                    const float A = (s & 1) ? Ab : Aa, B = (s & 1) ? Bb : Ba;
+                    const float sigma = fmaf(dy, fmaf(hC, dy, B), A);
+                    const float ov = opac * ex2_approx(-sigma);
+                    const float alpha = fminf(kAlphaMax, ov);
+                    const bool ok = !(sigma < 0.f) && (alpha >= kAlphaMin) && (idx <= binf[s]);
+                    hit |= ok;
+                    // a rejected pixel runs with alpha = 0: ra = 1, fac = 0, v_sigma = 0
+                    const float a_e = ok ? alpha : 0.f;
+                    const float ra = rcp_approx(1.f - a_e);
+                    const float Tn = T[s] * ra;
+                    T[s] = Tn;
+                    const float fac = a_e * Tn;
                     float cv = 0.f;
 #pragma unroll
                     for (int k = 0; k < CDIM; ++k) {
-                        v[k] += fac * v_c[j][k];
-                        cv += col[k] * v_c[j][k];
+                        v[k] = fmaf(fac, v_c[s][k], v[k]);
+                        cv = fmaf(col[k], v_c[s][k], cv);
                     }
-                    const float v_alpha = Tn * cv + ra * (tfa[j] - bv[j]);
-                    bv[j] += fac * cv;
+                    const float v_alpha = fmaf(Tn, cv, ra * tb[s]);
+                    tb[s] = fmaf(-fac, cv, tb[s]);
                     const float v_sigma = (ok && ov <= kAlphaMax) ? -ov * v_alpha : 0.f;
                     const float wy = v_sigma * dy;
-                    W0 += v_sigma; W1 += wy; W2 += wy * dy;
+                    W0[s & 1] += v_sigma;
+                    W1[s & 1] += wy;
+                    W2[s & 1] = fmaf(wy, dy, W2[s & 1]);
                     if (ABS) {
+                        const float dx = (s & 1) ? dxb : dxa;
                         v[CDIM + 6] += fabsf(v_sigma * (2.f * hA * dx + cb * dy));
                         v[CDIM + 7] += fabsf(v_sigma * (cb * dx + 2.f * hC * dy));
                     }
                 }
             }
-            const float S1x = dx * W0;
-            v[CDIM + 0] = 0.5f * dx * S1x;                 // 1/2 sum v_sigma dx²
-            v[CDIM + 1] = dx * W1;                         // sum v_sigma dx dy
-            v[CDIM + 2] = 0.5f * W2;                       // 1/2 sum v_sigma dy²
-            v[CDIM + 3] = 2.f * hA * S1x + cb * W1;        // sum v_sigma (a dx + b dy)
-            v[CDIM + 4] = cb * S1x + 2.f * hC * W1;        // sum v_sigma (b dx + c dy)
-            v[CDIM + 5] = -W0 / opac;                      // sum vis·v_alpha
-            const int32_t g = s_gid[wid][t];
+            if (!__any_sync(0xffffffffu, hit)) continue;
+            // moments -> gradients (conic entries in the record are scaled by log2 e)
+            const float ua = dxa * W0[0], ub = dxb * W0[1];
+            const float S1x = ua + ub, S1y = W1[0] + W1[1];
+            v[CDIM + 0] = 0.5f * fmaf(dxa, ua, dxb * ub);                 // 1/2 sum v_sigma dx²
+            v[CDIM + 1] = fmaf(dxa, W1[0], dxb * W1[1]);                  // sum v_sigma dx dy
+            v[CDIM + 2] = 0.5f * (W2[0] + W2[1]);                         // 1/2 sum v_sigma dy²
+            v[CDIM + 3] = kInvLog2e * fmaf(2.f * hA, S1x, cb * S1y);      // sum v_sigma (a dx + b dy)
+            v[CDIM + 4] = kInvLog2e * fmaf(cb, S1x, 2.f * hC * S1y);      // sum v_sigma (b dx + c dy)
+            v[CDIM + 5] = -(W0[0] + W0[1]) * rcp_approx(opac);            // sum vis·v_alpha
+            if (ABS) { v[CDIM + 6] *= kInvLog2e; v[CDIM + 7] *= kInvLog2e; }
+            const int32_t g = im.z;
             warp_reduce_commit<NV>(v, lane, [&](int k, float val) {
                 float *dst;
                 if (k < CDIM) {
@@ -387,17 +394,25 @@ raster_bwd_v2_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channel
 }
 
 template <int CDIM, bool ABS>
-static void launch_bwd_v2(uint32_t C, uint64_t n_isects, uint32_t channels, const float4 *rec,
+static void launch_bwd_v3(uint32_t C, uint64_t n_isects, uint32_t channels, const float4 *rec,
                           const float *backgrounds, const uint8_t *masks, uint32_t W, uint32_t H, uint32_t tile_width,
                           uint32_t tile_height, const int32_t *tile_offsets, const int32_t *flatten_ids,
                           const float *render_alphas, const int32_t *last_ids, const float *v_render_colors,
                           const float *v_render_alphas, float *v_means2d_abs, float *v_means2d, float *v_conics,
                           float *v_colors, float *v_opacities, cudaStream_t st) {
     const uint32_t total = C * tile_width * tile_height;
-    raster_bwd_v2_kernel<CDIM, ABS><<<div_up(total, kV2Warps), kV2Warps * 32, 0, st>>>(
-        total, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids,
-        render_alphas, last_ids, v_render_colors, v_render_alphas, v_means2d_abs, v_means2d, v_conics, v_colors,
-        v_opacities);
+#define B2S_BWD3(NS_, MINB_)                                                                                         \
+    raster_bwd_v3_kernel<CDIM, ABS, NS_, MINB_><<<total, 32 * (kV3Slots / NS_), 0, st>>>(                             \
+        total, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, \
+        render_alphas, last_ids, v_render_colors, v_render_alphas, v_means2d_abs, v_means2d, v_conics, v_colors,     \
+        v_opacities)
+    switch (tuning_variant()) {
+        case 1: B2S_BWD3(8, 20); break;
+        case 2: B2S_BWD3(4, 16); break;
+        case 3: B2S_BWD3(4, 10); break;
+        default: B2S_BWD3(8, 16); break;
+    }
+#undef B2S_BWD3
 }
 
 }  // namespace b2s
@@ -417,7 +432,7 @@ extern "C" int b200splat_rasterize_bwd(uint32_t C, uint32_t n_gauss, uint64_t n_
     const char *where = "b200splat_rasterize_bwd";
     (void)n_gauss;
     if (records != nullptr) {
-        B2S_REQUIRE(tile_size == kV2Tile && channels >= 1 && channels <= 4, where,
+        B2S_REQUIRE(tile_size == kV3Tile && channels >= 1 && channels <= 4, where,
                     "packed records are only valid for tile_size 16 and <= 4 channels");
         B2S_REQUIRE(n_isects <= 0x7fffffffull, where, "n_isects exceeds int32 offsets");
         if ((uint64_t)C * tile_width * tile_height == 0 || n_isects == 0) return 0;
@@ -427,11 +442,11 @@ extern "C" int b200splat_rasterize_bwd(uint32_t C, uint32_t n_gauss, uint64_t n_
 #define B2S_BWD2(D)                                                                                                    \
     case D:                                                                                                            \
         if (ab)                                                                                                        \
-            launch_bwd_v2<D, true>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height,      \
+            launch_bwd_v3<D, true>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height,      \
                                    tile_offsets, flatten_ids, render_alphas, last_ids, v_render_colors,                \
                                    v_render_alphas, v_means2d_abs, v_means2d, v_conics, v_colors, v_opacities, st2);   \
         else                                                                                                           \
-            launch_bwd_v2<D, false>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height,     \
+            launch_bwd_v3<D, false>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height,     \
                                     tile_offsets, flatten_ids, render_alphas, last_ids, v_render_colors,               \
                                     v_render_alphas, v_means2d_abs, v_means2d, v_conics, v_colors, v_opacities, st2);  \
         break;

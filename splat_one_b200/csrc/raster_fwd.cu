@@ -12,7 +12,7 @@
 // consumed with coalesced loads.  The loop body is the fp32/MUFU critical path; see
 // DESIGN.md for the measured limits.
 #include "raster_common.cuh"
-#include "raster_v2.cuh"
+#include "raster_v3.cuh"
 
 namespace b2s {
 
@@ -149,46 +149,60 @@ static int launch_fwd(uint32_t C, uint64_t n_isects, uint32_t channels, const fl
 
 
 // ---------------------------------------------------------------------------------------
-// v2: warp-per-tile, 8 pixels per lane, culled staging (see raster_v2.cuh)
+// v3: warp-per-tile, 8 sub-block slots per lane, exact sub-block culling (raster_v3.cuh)
 // ---------------------------------------------------------------------------------------
-template <int CDIM>
-__global__ void __launch_bounds__(kV2Warps * 32)
-raster_fwd_v2_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channels, const float4 *__restrict__ rec,
+template <int CDIM, int NS, int MINB>
+__global__ void __launch_bounds__(32 * (kV3Slots / NS), MINB)
+raster_fwd_v3_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channels, const float4 *__restrict__ rec,
                      const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks, uint32_t W, uint32_t H,
                      uint32_t tile_width, uint32_t tile_height, const int32_t *__restrict__ tile_offsets,
                      const int32_t *__restrict__ flatten_ids, float *__restrict__ render_colors,
                      float *__restrict__ render_alphas, int32_t *__restrict__ last_ids) {
-    __shared__ float4 s_rec[kV2Warps][32 * 3];
-    __shared__ int32_t s_idx[kV2Warps][32];
-    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint32_t tile_lin = blockIdx.x * kV2Warps + wid;
-    if (tile_lin >= n_tiles_total) return;  // warp-uniform; no block-level sync is used below
-    const V2Tile tc = v2_tile(tile_lin, tile_width, tile_height, W, H, lane);
+    // a CTA is one tile; each of its warps owns NS of the 8 sub-blocks and works on its own
+    // (no block-level synchronisation anywhere)
+    __shared__ float4 s_rec_all[kV3Slots / NS][32 * 3];
+    __shared__ int2 s_im_all[kV3Slots / NS][32];  // {sorted index, sub-block mask}
+    const unsigned lane = threadIdx.x & 31, sub = threadIdx.x >> 5;
+    float4 *s_rec = s_rec_all[sub];
+    int2 *s_im = s_im_all[sub];
+    const uint32_t tile_lin = blockIdx.x;
+    const V3Tile tc = v3_tile<NS>(tile_lin, tile_width, tile_height, lane, sub);
     if (backgrounds != nullptr) backgrounds += (size_t)tc.cam * channels;
-    const size_t pix0 = ((size_t)tc.cam * H + tc.y0) * W + tc.x;
+    const size_t cam_pix = (size_t)tc.cam * H * W;
+
+    // pixel of slot s: (tc.x + 8 (s & 1), tc.y + 4 (s >> 1))
+    uint32_t in_mask = 0;  // bit s: this lane's pixel of slot s is inside the image
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+        if (tc.x + 8u * (s & 1) < W && tc.y + 4u * (s >> 1) < H) in_mask |= 1u << s;
 
     if (masks != nullptr && !masks[tile_lin]) {
 #pragma unroll
-        for (int j = 0; j < kV2Rows; ++j)
-            if (tc.row_mask >> j & 1)
+        for (int s = 0; s < NS; ++s)
+            if (in_mask >> s & 1) {
+                const size_t p = cam_pix + (size_t)(tc.y + 4u * (s >> 1)) * W + tc.x + 8u * (s & 1);
                 for (uint32_t k = 0; k < channels; ++k)
-                    render_colors[(pix0 + (size_t)j * W) * channels + k] = backgrounds == nullptr ? 0.f : backgrounds[k];
+                    render_colors[p * channels + k] = backgrounds == nullptr ? 0.f : backgrounds[k];
+            }
         return;
     }
 
     const int32_t range_start = tile_offsets[tile_lin];
     const int32_t range_end = (tile_lin == n_tiles_total - 1) ? (int32_t)n_isects : tile_offsets[tile_lin + 1];
 
-    float T[kV2Rows], pix[kV2Rows][CDIM];
-    int32_t cur[kV2Rows];
+    // the sign of T is the liveness flag: T > 0 while the pixel accumulates, -T_final once it has
+    // stopped (or lies outside the image).  A dead pixel then "stops" again on every Gaussian:
+    // next_T = T (1 - alpha) < 0 <= 1e-4, so it composites nothing and keeps its T.
+    float T[NS], pix[NS][CDIM];
+    int32_t cur[NS];
 #pragma unroll
-    for (int j = 0; j < kV2Rows; ++j) {
-        T[j] = 1.f;
-        cur[j] = 0;
+    for (int s = 0; s < NS; ++s) {
+        T[s] = (in_mask >> s & 1) ? 1.f : -1.f;
+        cur[s] = 0;
 #pragma unroll
-        for (int k = 0; k < CDIM; ++k) pix[j][k] = 0.f;
+        for (int k = 0; k < CDIM; ++k) pix[s][k] = 0.f;
     }
-    uint32_t live = tc.row_mask;  // bit j: pixel j still accumulating
+    uint32_t live = __reduce_or_sync(0xffffffffu, in_mask);  // warp-uniform: slots with a live pixel
 
     // software prefetch of this lane's record for the first batch
     float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
@@ -197,16 +211,17 @@ raster_fwd_v2_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channel
         const int32_t g = flatten_ids[my_idx];
         r0 = __ldg(rec + 3 * (size_t)g); r1 = __ldg(rec + 3 * (size_t)g + 1); r2 = __ldg(rec + 3 * (size_t)g + 2);
     }
-    for (int32_t base = range_start; base < range_end; base += 32) {
-        const bool keep = (my_idx < range_end) &&
-                          tile_may_contribute(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tc.rx0, tc.ry0, tc.rx1, tc.ry1);
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    for (int32_t base = range_start; base < range_end && live != 0; base += 32) {
+        uint32_t my_mask = 0;
+        if (my_idx < range_end)
+            my_mask = subblock_mask<NS>(r0.x, r0.y, r0.z, r0.w, r1.x, r2.z, tc.ox, tc.oy, W, H) & live;
+        const unsigned bal = __ballot_sync(0xffffffffu, my_mask != 0);
         const int n = __popc(bal);
         __syncwarp();  // readers of the previous batch are done
-        if (keep) {
+        if (my_mask != 0) {
             const int pos = __popc(bal & ((1u << lane) - 1u));
-            s_rec[wid][3 * pos] = r0; s_rec[wid][3 * pos + 1] = r1; s_rec[wid][3 * pos + 2] = r2;
-            s_idx[wid][pos] = my_idx;
+            s_rec[3 * pos] = r0; s_rec[3 * pos + 1] = r1; s_rec[3 * pos + 2] = r2;
+            s_im[pos] = make_int2(my_idx, (int)my_mask);
         }
         __syncwarp();
         // prefetch the next batch while this one is composited
@@ -216,68 +231,73 @@ raster_fwd_v2_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channel
             r0 = __ldg(rec + 3 * (size_t)g); r1 = __ldg(rec + 3 * (size_t)g + 1); r2 = __ldg(rec + 3 * (size_t)g + 2);
         }
         for (int t = 0; t < n; ++t) {
-            const float4 a = s_rec[wid][3 * t], b4 = s_rec[wid][3 * t + 1], c4 = s_rec[wid][3 * t + 2];
-            const int32_t idx = s_idx[wid][t];
-            const float dx = a.x - tc.px;
-            const float dy0 = a.y - tc.py0;
-            const float A = a.z * dx * dx, B = a.w * dx, hC = b4.x, opac = b4.y;
+            const float4 a = s_rec[3 * t], b4 = s_rec[3 * t + 1], c4 = s_rec[3 * t + 2];
+            const int2 im = s_im[t];
+            const int32_t idx = im.x;
+            const uint32_t m = (uint32_t)im.y;
+            const float dxa = a.x - tc.px, dxb = dxa - 8.f, dyv = a.y - tc.py;
+            const float hC = b4.x, opac = b4.y;
+            const float Aa = a.z * dxa * dxa, Ba = a.w * dxa, Ab = a.z * dxb * dxb, Bb = a.w * dxb;
             const float col[4] = {b4.z, b4.w, c4.x, c4.y};
-            // phase 1 (branch-free, 8 independent chains): alpha of the lane's 8 pixels
-            float alpha[kV2Rows];
-            uint32_t acc = 0;
 #pragma unroll
-            for (int j = 0; j < kV2Rows; ++j) {
-                const float dy = dy0 - (float)j;
-                const float sigma = A + dy * (B + hC * dy);
-                alpha[j] = fminf(kAlphaMax, opac * __expf(-sigma));
-                if (sigma >= 0.f && alpha[j] >= kAlphaMin) acc |= 1u << j;
-            }
-            acc &= live;
-            // phase 2: composite; a pixel row is skipped with a WARP-UNIFORM branch when no
-            // lane needs it, and runs predicated (weight 0) otherwise — no divergence
-            const uint32_t rows = __reduce_or_sync(0xffffffffu, acc);
+            for (int s = 0; s < NS; ++s) {
+                if (m >> s & 1) {  // warp-uniform
+                    const float dy = dyv - 4.f * (float)(s >> 1);
+                    const float A = (s & 1) ? Ab : Aa, B = (s & 1) ? Bb : Ba;
+                    const float nsigma = fmaf(-dy, fmaf(hC, dy, B), -A);  // -sigma'
+                    const float alpha = fminf(kAlphaMax, opac * ex2_approx(nsigma));
+                    const bool ok = !(nsigma > 0.f) && (alpha >= kAlphaMin);
+                    const float a_e = ok ? alpha : 0.f;
+                    const float next_T = T[s] * (1.f - a_e);         // == T exactly when rejected
+                    const bool stop = next_T <= kTransmittanceEps;   // exclusive stop (implies ok, or dead)
+                    const float vis = (stop ? 0.f : a_e) * T[s];
 #pragma unroll
-            for (int j = 0; j < kV2Rows; ++j) {
-                if (rows >> j & 1) {
-                    const bool ok = acc >> j & 1;
-                    const float next_T = T[j] * (1.f - alpha[j]);
-                    const bool stop = ok && (next_T <= kTransmittanceEps);  // exclusive stop
-                    const bool comp = ok && !stop;
-                    if (stop) live &= ~(1u << j);
-                    const float vis = comp ? alpha[j] * T[j] : 0.f;
-#pragma unroll
-                    for (int k = 0; k < CDIM; ++k) pix[j][k] += col[k] * vis;
-                    cur[j] = comp ? idx : cur[j];
-                    T[j] = comp ? next_T : T[j];
+                    for (int k = 0; k < CDIM; ++k) pix[s][k] = fmaf(col[k], vis, pix[s][k]);
+                    cur[s] = (ok && !stop) ? idx : cur[s];
+                    T[s] = stop ? -fabsf(T[s]) : next_T;
                 }
             }
         }
-        if (__all_sync(0xffffffffu, live == 0)) break;
+        // slots whose pixels have all stopped are skipped from now on
+        uint32_t nl = 0;
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+            if ((live >> s & 1) && __any_sync(0xffffffffu, T[s] > 0.f)) nl |= 1u << s;
+        live = nl;
     }
 
 #pragma unroll
-    for (int j = 0; j < kV2Rows; ++j) {
-        if (tc.row_mask >> j & 1) {
-            const size_t p = pix0 + (size_t)j * W;
-            render_alphas[p] = 1.f - T[j];
+    for (int s = 0; s < NS; ++s) {
+        if (in_mask >> s & 1) {
+            const size_t p = cam_pix + (size_t)(tc.y + 4u * (s >> 1)) * W + tc.x + 8u * (s & 1);
+            const float Tf = fabsf(T[s]);
+            render_alphas[p] = 1.f - Tf;
 #pragma unroll
             for (int k = 0; k < CDIM; ++k)
                 if (k < (int)channels)
-                    render_colors[p * channels + k] = backgrounds == nullptr ? pix[j][k] : (pix[j][k] + T[j] * backgrounds[k]);
-            last_ids[p] = cur[j];
+                    render_colors[p * channels + k] = backgrounds == nullptr ? pix[s][k] : (pix[s][k] + Tf * backgrounds[k]);
+            last_ids[p] = cur[s];
         }
     }
 }
 
 template <int CDIM>
-static void launch_fwd_v2(uint32_t C, uint64_t n_isects, uint32_t channels, const float4 *rec,
+static void launch_fwd_v3(uint32_t C, uint64_t n_isects, uint32_t channels, const float4 *rec,
                           const float *backgrounds, const uint8_t *masks, uint32_t W, uint32_t H, uint32_t tile_width,
                           uint32_t tile_height, const int32_t *tile_offsets, const int32_t *flatten_ids,
                           float *render_colors, float *render_alphas, int32_t *last_ids, cudaStream_t st) {
     const uint32_t total = C * tile_width * tile_height;
-    raster_fwd_v2_kernel<CDIM><<<div_up(total, kV2Warps), kV2Warps * 32, 0, st>>>(
-        total, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids,
-        render_colors, render_alphas, last_ids);
+#define B2S_FWD3(NS_, MINB_)                                                                                        \
+    raster_fwd_v3_kernel<CDIM, NS_, MINB_><<<total, 32 * (kV3Slots / NS_), 0, st>>>(                                 \
+        total, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, \
+        render_colors, render_alphas, last_ids)
+    switch (tuning_variant()) {
+        case 1: B2S_FWD3(8, 16); break;
+        case 2: B2S_FWD3(4, 16); break;
+        case 3: B2S_FWD3(4, 10); break;
+        default: B2S_FWD3(8, 20); break;
+    }
+#undef B2S_FWD3
 }
 
 }  // namespace b2s
@@ -285,7 +305,7 @@ static void launch_fwd_v2(uint32_t C, uint64_t n_isects, uint32_t channels, cons
 using namespace b2s;
 
 extern "C" size_t b200splat_rasterize_records_bytes(uint32_t n_gauss, uint32_t channels, uint32_t tile_size) {
-    if (tile_size != kV2Tile || channels < 1 || channels > 4) return 0;  // generic path: no records
+    if (tile_size != kV3Tile || channels < 1 || channels > 4) return 0;  // generic path: no records
     return (size_t)n_gauss * 3 * sizeof(float4);
 }
 
@@ -313,7 +333,7 @@ extern "C" int b200splat_rasterize_fwd(uint32_t C, uint32_t n_gauss, uint64_t n_
     const char *where = "b200splat_rasterize_fwd";
     (void)n_gauss;
     if (records != nullptr) {
-        B2S_REQUIRE(tile_size == kV2Tile && channels >= 1 && channels <= 4, where,
+        B2S_REQUIRE(tile_size == kV3Tile && channels >= 1 && channels <= 4, where,
                     "packed records are only valid for tile_size 16 and <= 4 channels");
         B2S_REQUIRE((uint64_t)tile_width * tile_size >= W && (uint64_t)tile_height * tile_size >= H, where,
                     "tile grid does not cover the image");
@@ -322,10 +342,10 @@ extern "C" int b200splat_rasterize_fwd(uint32_t C, uint32_t n_gauss, uint64_t n_
         const float4 *rec = reinterpret_cast<const float4 *>(records);
         cudaStream_t st2 = (cudaStream_t)stream;
         switch (channels) {
-            case 1: launch_fwd_v2<1>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids, st2); break;
-            case 2: launch_fwd_v2<2>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids, st2); break;
-            case 3: launch_fwd_v2<3>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids, st2); break;
-            default: launch_fwd_v2<4>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids, st2); break;
+            case 1: launch_fwd_v3<1>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids, st2); break;
+            case 2: launch_fwd_v3<2>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids, st2); break;
+            case 3: launch_fwd_v3<3>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids, st2); break;
+            default: launch_fwd_v3<4>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids, st2); break;
         }
         B2S_CHECK_LAUNCH(where);
         return 0;
