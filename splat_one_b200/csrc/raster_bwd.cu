@@ -10,7 +10,7 @@
 // (reduce-scatter) butterfly — 16 SHFL for up to 16 values — which leaves value k in
 // lane 2k, so a single RED instruction with <= 16 active lanes commits all of them.
 #include "raster_common.cuh"
-#include "raster_v3.cuh"
+#include "raster_quad.cuh"
 
 namespace b2s {
 
@@ -55,6 +55,59 @@ __device__ __forceinline__ void warp_reduce_commit(const float *v, const unsigne
     if ((lane % stride) == 0 && k < CH) commit(OFF + k, r);
     if constexpr (OFF + CH < NV) warp_reduce_commit<NV, OFF + CH>(v, lane, commit);
 }
+
+// Branch-free commit for the quad kernels: the NV per-pair values are reduced in two chunks
+// (values 0..7 with an 8-wide reduce-scatter, which leaves value i in lanes 4i..4i+3, and the
+// remaining R = NV - 8 values with a P1-wide one, value 8+i in lanes (32/P1)·i ..), and every
+// value is handed to ONE lane chosen so that no lane gets two: chunk 0 commits from lanes 4i,
+// chunk 1 from lanes (32/P1)·i + 1.  Each lane resolves its destination array once, before
+// the loop over Gaussians; the per-pair commit is then a single predicated RED.
+template <int NV>
+struct GradSink {
+    static constexpr int N0 = NV < 8 ? NV : 8;
+    static constexpr int R = NV - N0;
+    static constexpr int P1 = next_pow2(R);
+    float *base;       // nullptr: this lane commits nothing
+    uint32_t stride;   // floats per Gaussian row of the destination array
+    bool from_chunk1;
+
+    template <int CDIM>
+    __device__ __forceinline__ void init(unsigned lane, uint32_t channels, float *v_colors, float *v_conics,
+                                         float *v_means2d, float *v_opacities, float *v_means2d_abs) {
+        int k = -1;
+        from_chunk1 = false;
+        if ((lane & 3) == 0) {
+            if ((int)(lane >> 2) < N0) k = (int)(lane >> 2);
+        } else if (R > 0 && (lane % (32 / P1)) == 1) {
+            const int i = (int)(lane / (32 / P1));
+            if (i < R) { k = 8 + i; from_chunk1 = true; }
+        }
+        base = nullptr;
+        stride = 0;
+        if (k < 0) return;
+        if (k < CDIM) {
+            if (k < (int)channels) { base = v_colors + k; stride = channels; }
+        } else if (k < CDIM + 3) { base = v_conics + (k - CDIM); stride = 3; }
+        else if (k < CDIM + 5) { base = v_means2d + (k - CDIM - 3); stride = 2; }
+        else if (k == CDIM + 5) { base = v_opacities; stride = 1; }
+        else { base = v_means2d_abs + (k - CDIM - 6); stride = 2; }
+    }
+
+    __device__ __forceinline__ void commit(const float (&v)[NV], unsigned lane, int32_t g) const {
+        float w0[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w0[i] = (i < N0) ? v[i] : 0.f;
+        float val = warp_reduce_scatter<8>(w0, lane);
+        if (R > 0) {
+            float w1[P1];
+#pragma unroll
+            for (int i = 0; i < P1; ++i) w1[i] = (i < R) ? v[8 + i] : 0.f;
+            const float r1 = warp_reduce_scatter<P1>(w1, lane);
+            val = from_chunk1 ? r1 : val;
+        }
+        if (base != nullptr) atomicAdd(base + (size_t)g * stride, val);
+    }
+};
 
 template <int CDIM, bool ABS, int MAXT>
 __global__ void __launch_bounds__(MAXT)
@@ -221,27 +274,79 @@ static void launch_bwd(uint32_t C, uint64_t n_isects, uint32_t channels, const f
 
 
 // ---------------------------------------------------------------------------------------
-// v3: warp-per-tile, 8 sub-block slots per lane, exact sub-block culling (raster_v3.cuh).
-// Per (tile, Gaussian): each lane folds its (up to) 8 pixels into CDIM colour sums and, per
-// column half (dx is shared by the four slots of a half), the moments
+// quad kernels: warp-per-tile (or per half tile), 8x8 quads, packed fp32x2 (raster_quad.cuh).
+// Per (tile, Gaussian): each lane folds its pixels into CDIM colour sums and, per column
+// half (dx is shared by the pixels of a half), the moments
 //   W0 = sum v_sigma,  W1 = sum v_sigma·dy,  W2 = sum v_sigma·dy²
 // converts them to the 9 gradient values, and ONE reduce-scatter butterfly + one RED per
-// value commits them.
+// value commits them.  Everything is accumulated NEGATED (the record carries -opacity and
+// -colour, raster_quad.cuh) and the sign is restored once per pair.
 // ---------------------------------------------------------------------------------------
-template <int CDIM, bool ABS, int NS, int MINB>
-__global__ void __launch_bounds__(32 * (kV3Slots / NS), MINB)
-raster_bwd_v3_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channels, const float4 *__restrict__ rec,
-                     const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks, uint32_t W, uint32_t H,
-                     uint32_t tile_width, uint32_t tile_height, const int32_t *__restrict__ tile_offsets,
-                     const int32_t *__restrict__ flatten_ids, const float *__restrict__ render_alphas,
-                     const int32_t *__restrict__ last_ids, const float *__restrict__ v_render_colors,
-                     const float *__restrict__ v_render_alphas, float *__restrict__ v_means2d_abs,
-                     float *__restrict__ v_means2d, float *__restrict__ v_conics, float *__restrict__ v_colors,
-                     float *__restrict__ v_opacities) {
+struct BwdAcc {
+    float2 nW0, nW1, nW2;  // negated moments of one column half, one entry per pixel row pair
+};
+
+// One Gaussian against one quad.  State per pixel: T, ntb = -(T_final (v_alpha_out - bg·v_c) -
+// sum_k buffer_k v_c_k), which folds the reference's per-channel `buffer`
+// (CS/rasterize_to_pixels_bwd.cu:203-241): v_alpha only ever needs that dot product.
+template <int CDIM, bool ABS, bool SIGN>
+__device__ __forceinline__ bool bwd_quad(float2 &T2, float2 &ntb2, const float2 (&v_c2)[CDIM], const int32_t (&binf)[2],
+                                         float2 (&nvacc2)[CDIM], BwdAcc &acc, float2 &abs2x, float2 &abs2y,
+                                         const float2 dy2, const float2 ndy2, const float dx, const float hA,
+                                         const float cb, const float nA, const float B, const float hC,
+                                         const float nopac, const float (&ncol)[4], const int32_t idx) {
+    const float2 u2 = __ffma2_rn(bc2(hC), dy2, bc2(B));
+    const float2 ns2 = __ffma2_rn(ndy2, u2, bc2(nA));  // -sigma'
+    const float2 nov2 = __fmul2_rn(bc2(nopac), make_float2(ex2_approx(ns2.x), ex2_approx(ns2.y)));  // -opac·vis
+    const float nal0 = fmaxf(-kAlphaMax, nov2.x), nal1 = fmaxf(-kAlphaMax, nov2.y);  // -alpha
+    bool ok0 = (nal0 <= -kAlphaMin) && (idx <= binf[0]), ok1 = (nal1 <= -kAlphaMin) && (idx <= binf[1]);
+    if (SIGN) { ok0 = ok0 && !(ns2.x > 0.f); ok1 = ok1 && !(ns2.y > 0.f); }
+    // a rejected pixel runs with alpha = 0: ra = 1, fac = 0, v_sigma = 0
+    const float2 nae2 = make_float2(ok0 ? nal0 : 0.f, ok1 ? nal1 : 0.f);
+    const float2 om2 = __fadd2_rn(nae2, bc2(1.f));
+    const float2 ra2 = make_float2(rcp_approx(om2.x), rcp_approx(om2.y));
+    T2 = __fmul2_rn(T2, ra2);
+    const float2 nfac2 = __fmul2_rn(nae2, T2);  // -alpha T
+    float2 ncv2 = make_float2(0.f, 0.f);        // -sum_k c_k v_c_k
+#pragma unroll
+    for (int k = 0; k < CDIM; ++k) {
+        nvacc2[k] = __ffma2_rn(nfac2, v_c2[k], nvacc2[k]);
+        ncv2 = (k == 0) ? __fmul2_rn(bc2(ncol[0]), v_c2[0]) : __ffma2_rn(bc2(ncol[k]), v_c2[k], ncv2);
+    }
+    const float2 nv_alpha2 = __ffma2_rn(T2, ncv2, __fmul2_rn(ra2, ntb2));  // -v_alpha
+    ntb2 = __ffma2_rn(nfac2, ncv2, ntb2);
+    float2 nvs2 = __fmul2_rn(nov2, nv_alpha2);  // ov·v_alpha = -v_sigma
+    nvs2.x = (ok0 && nov2.x >= -kAlphaMax) ? nvs2.x : 0.f;
+    nvs2.y = (ok1 && nov2.y >= -kAlphaMax) ? nvs2.y : 0.f;
+    const float2 nwy2 = __fmul2_rn(nvs2, dy2);
+    acc.nW0 = __fadd2_rn(acc.nW0, nvs2);
+    acc.nW1 = __fadd2_rn(acc.nW1, nwy2);
+    acc.nW2 = __ffma2_rn(nwy2, dy2, acc.nW2);
+    if (ABS) {
+        // |v_sigma (a' dx + b' dy)|, |v_sigma (b' dx + c' dy)| (still scaled by log2 e)
+        const float2 gx2 = __ffma2_rn(bc2(cb), dy2, bc2(2.f * hA * dx));
+        const float2 gy2 = __ffma2_rn(bc2(2.f * hC), dy2, bc2(cb * dx));
+        abs2x.x += fabsf(nvs2.x * gx2.x); abs2x.y += fabsf(nvs2.y * gx2.y);
+        abs2y.x += fabsf(nvs2.x * gy2.x); abs2y.y += fabsf(nvs2.y * gy2.y);
+    }
+    return ok0 || ok1;
+}
+
+template <int CDIM, bool ABS, int NQ, int MINB>
+__global__ void __launch_bounds__(32 * (4 / NQ), MINB)
+raster_bwd_quad_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channels, const float4 *__restrict__ rec,
+                       const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks, uint32_t W,
+                       uint32_t H, uint32_t tile_width, uint32_t tile_height,
+                       const int32_t *__restrict__ tile_offsets, const int32_t *__restrict__ flatten_ids,
+                       const float *__restrict__ render_alphas, const int32_t *__restrict__ last_ids,
+                       const float *__restrict__ v_render_colors, const float *__restrict__ v_render_alphas,
+                       float *__restrict__ v_means2d_abs, float *__restrict__ v_means2d, float *__restrict__ v_conics,
+                       float *__restrict__ v_colors, float *__restrict__ v_opacities) {
     constexpr int NV = CDIM + 6 + (ABS ? 2 : 0);
-    // a CTA is one tile; each of its warps owns NS of the 8 sub-blocks and works on its own
-    __shared__ float4 s_rec_all[kV3Slots / NS][32 * 3];
-    __shared__ int4 s_im_all[kV3Slots / NS][32];  // {sorted index, sub-block mask, Gaussian row, -}
+    constexpr int NW = 4 / NQ;    // warps per CTA; each works on its own (no block-level sync)
+    constexpr int NQY = NQ / 2;   // quad rows per warp
+    __shared__ float4 s_rec_all[NW][32 * 3];
+    __shared__ int4 s_im_all[NW][32];  // {sorted index, quad mask, Gaussian row, -}
     const unsigned lane = threadIdx.x & 31, sub = threadIdx.x >> 5;
     float4 *s_rec = s_rec_all[sub];
     int4 *s_im = s_im_all[sub];
@@ -250,42 +355,58 @@ raster_bwd_v3_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channel
     const int32_t range_start = tile_offsets[tile_lin];
     const int32_t range_end = (tile_lin == n_tiles_total - 1) ? (int32_t)n_isects : tile_offsets[tile_lin + 1];
     if (range_end <= range_start) return;
-    const V3Tile tc = v3_tile<NS>(tile_lin, tile_width, tile_height, lane, sub);
+    const QuadTile tc = quad_tile<NQ>(tile_lin, tile_width, tile_height, lane, sub);
     const size_t cam_pix = (size_t)tc.cam * H * W;
 
-    // per-pixel state.  tb = T_final (v_alpha_out - sum_k bg_k v_c_k) - sum_k buffer_k v_c_k folds
-    // the reference's per-channel `buffer` (CS/rasterize_to_pixels_bwd.cu:203-241): v_alpha only
-    // ever needs that dot product.
-    float T[NS], tb[NS], v_c[NS][CDIM];
-    int32_t binf[NS];
+    float2 T2[NQ], ntb2[NQ], v_c2[NQ][CDIM];
+    int32_t binf[NQ][2];
     int32_t max_bin = -1;
 #pragma unroll
-    for (int s = 0; s < NS; ++s) {
-        T[s] = 1.f; tb[s] = 0.f; binf[s] = -1;
+    for (int q = 0; q < NQ; ++q) {
+        float Tq[2] = {1.f, 1.f}, tb[2] = {0.f, 0.f}, vc[2][CDIM];
 #pragma unroll
-        for (int k = 0; k < CDIM; ++k) v_c[s][k] = 0.f;
-        const uint32_t x = tc.x + 8u * (s & 1), y = tc.y + 4u * (s >> 1);
-        if (x < W && y < H) {
-            const size_t p = cam_pix + (size_t)y * W + x;
-            const float T_final = 1.f - render_alphas[p];
-            T[s] = T_final;
-            binf[s] = last_ids[p];
-            float bg_dot = 0.f;
+        for (int j = 0; j < 2; ++j) {
+            binf[q][j] = -1;
 #pragma unroll
-            for (int k = 0; k < CDIM; ++k) {
-                if (k < (int)channels) {
-                    v_c[s][k] = v_render_colors[p * channels + k];
-                    if (backgrounds != nullptr) bg_dot += backgrounds[(size_t)tc.cam * channels + k] * v_c[s][k];
+            for (int k = 0; k < CDIM; ++k) vc[j][k] = 0.f;
+            const uint32_t x = tc.x + 8u * (q & 1), y = tc.y + 8u * (q >> 1) + 4u * j;
+            if (x < W && y < H) {
+                const size_t p = cam_pix + (size_t)y * W + x;
+                const float T_final = 1.f - render_alphas[p];
+                Tq[j] = T_final;
+                binf[q][j] = last_ids[p];
+                float bg_dot = 0.f;
+#pragma unroll
+                for (int k = 0; k < CDIM; ++k) {
+                    if (k < (int)channels) {
+                        vc[j][k] = v_render_colors[p * channels + k];
+                        if (backgrounds != nullptr) bg_dot += backgrounds[(size_t)tc.cam * channels + k] * vc[j][k];
+                    }
                 }
+                tb[j] = T_final * (v_render_alphas[p] - bg_dot);
+                max_bin = max(max_bin, binf[q][j]);
             }
-            tb[s] = T_final * (v_render_alphas[p] - bg_dot);
-            max_bin = max(max_bin, binf[s]);
         }
+        T2[q] = make_float2(Tq[0], Tq[1]);
+        ntb2[q] = make_float2(-tb[0], -tb[1]);
+#pragma unroll
+        for (int k = 0; k < CDIM; ++k) v_c2[q][k] = make_float2(vc[0][k], vc[1][k]);
     }
     max_bin = warp_max(max_bin);
-    // nothing behind the last contributor of any pixel of this tile matters
+    // nothing behind the last contributor of any pixel of this warp's region matters
     const int32_t hi0 = min(range_end - 1, max_bin);
     if (hi0 < range_start) return;
+
+    float2 pyc2[NQY], npyc2[NQY];
+#pragma unroll
+    for (int qy = 0; qy < NQY; ++qy) {
+        pyc2[qy] = make_float2(tc.py + 8.f * qy, tc.py + 8.f * qy + 4.f);
+        npyc2[qy] = make_float2(-pyc2[qy].x, -pyc2[qy].y);
+    }
+    const float pxa = tc.px, pxb = tc.px + 8.f;
+
+    GradSink<NV> sink;
+    sink.template init<CDIM>(lane, channels, v_colors, v_conics, v_means2d, v_opacities, v_means2d_abs);
 
     float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
     int32_t my_idx = hi0 - (int32_t)lane, my_g = 0;
@@ -293,21 +414,24 @@ raster_bwd_v3_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channel
         my_g = flatten_ids[my_idx];
         r0 = __ldg(rec + 3 * (size_t)my_g); r1 = __ldg(rec + 3 * (size_t)my_g + 1); r2 = __ldg(rec + 3 * (size_t)my_g + 2);
     }
-    uint32_t act = 0;  // warp-uniform: slots with a pixel whose last contributor is inside the batches seen so far
+    uint32_t act = 0;  // warp-uniform: quads with a pixel whose last contributor is inside the batches seen so far
     for (int32_t hi = hi0; hi >= range_start; hi -= 32) {
         const int32_t lo = max(hi - 31, range_start);
 #pragma unroll
-        for (int s = 0; s < NS; ++s)
-            if (!(act >> s & 1) && __any_sync(0xffffffffu, binf[s] >= lo)) act |= 1u << s;
+        for (int q = 0; q < NQ; ++q)
+            if (!(act >> q & 1) && __any_sync(0xffffffffu, max(binf[q][0], binf[q][1]) >= lo)) act |= 1u << q;
         uint32_t my_mask = 0;
-        if (my_idx >= range_start)
-            my_mask = subblock_mask<NS>(r0.x, r0.y, r0.z, r0.w, r1.x, r2.z, tc.ox, tc.oy, W, H) & act;
+        if (my_idx >= range_start) {
+            my_mask = quad_mask<NQ>(r0.x, r0.y, r0.z, r0.w, r1.x, r2.z, tc.ox, tc.oy, W, H);
+            if ((my_mask & act) == 0) my_mask = 0; else my_mask &= (act | kNonPD);
+        }
         const unsigned bal = __ballot_sync(0xffffffffu, my_mask != 0);
         const int n = __popc(bal);
         __syncwarp();
         if (my_mask != 0) {
             const int pos = __popc(bal & ((1u << lane) - 1u));
-            s_rec[3 * pos] = r0; s_rec[3 * pos + 1] = r1; s_rec[3 * pos + 2] = r2;
+            s_rec[3 * pos] = r0; s_rec[3 * pos + 1] = r1;
+            s_rec[3 * pos + 2] = make_float4(r2.x, r2.y, -r0.y, 0.f);
             s_im[pos] = make_int4(my_idx, (int)my_mask, my_g, 0);
         }
         __syncwarp();
@@ -321,98 +445,83 @@ raster_bwd_v3_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channel
             const int4 im = s_im[t];
             const int32_t idx = im.x;
             const uint32_t m = (uint32_t)im.y;
-            const float dxa = a.x - tc.px, dxb = dxa - 8.f, dyv = a.y - tc.py;
-            const float hA = a.z, cb = a.w, hC = b4.x, opac = b4.y;
-            const float Aa = hA * dxa * dxa, Ba = cb * dxa, Ab = hA * dxb * dxb, Bb = cb * dxb;
-            const float col[4] = {b4.z, b4.w, c4.x, c4.y};
-            float v[NV];
+            const float dxa = a.x - pxa, dxb = a.x - pxb;
+            const float hA = a.z, cb = a.w, hC = b4.x, nopac = b4.y;
+            const float nAa = -(hA * dxa) * dxa, Ba = cb * dxa, nAb = -(hA * dxb) * dxb, Bb = cb * dxb;
+            const float ncol[4] = {b4.z, b4.w, c4.x, c4.y};
+            float2 dy2[NQY], ndy2[NQY];
 #pragma unroll
-            for (int k = 0; k < NV; ++k) v[k] = 0.f;
-            float W0[2] = {0.f, 0.f}, W1[2] = {0.f, 0.f}, W2[2] = {0.f, 0.f};
+            for (int qy = 0; qy < NQY; ++qy) {
+                ndy2[qy] = __fadd2_rn(pyc2[qy], bc2(c4.z));   // p_y - g_y
+                dy2[qy] = __fadd2_rn(npyc2[qy], bc2(a.y));    // g_y - p_y
+            }
+            float2 nvacc2[CDIM];
+#pragma unroll
+            for (int k = 0; k < CDIM; ++k) nvacc2[k] = make_float2(0.f, 0.f);
+            BwdAcc acc[2];
+            acc[0].nW0 = acc[0].nW1 = acc[0].nW2 = acc[1].nW0 = acc[1].nW1 = acc[1].nW2 = make_float2(0.f, 0.f);
+            float2 abs2x = make_float2(0.f, 0.f), abs2y = abs2x;
             bool hit = false;
+            if (m & kNonPD) {
 #pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                if (m >> s & 1) {  // warp-uniform
-                    const float dy = dyv - 4.f * (float)(s >> 1);
-                    const float A = (s & 1) ? Ab : Aa, B = (s & 1) ? Bb : Ba;
-                    const float sigma = fmaf(dy, fmaf(hC, dy, B), A);
-                    const float ov = opac * ex2_approx(-sigma);
-                    const float alpha = fminf(kAlphaMax, ov);
-                    const bool ok = !(sigma < 0.f) && (alpha >= kAlphaMin) && (idx <= binf[s]);
-                    hit |= ok;
-                    // a rejected pixel runs with alpha = 0: ra = 1, fac = 0, v_sigma = 0
-                    const float a_e = ok ? alpha : 0.f;
-                    const float ra = rcp_approx(1.f - a_e);
-                    const float Tn = T[s] * ra;
-                    T[s] = Tn;
-                    const float fac = a_e * Tn;
-                    float cv = 0.f;
+                for (int q = 0; q < NQ; ++q)
+                    if (m >> q & 1)  // warp-uniform
+                        hit |= bwd_quad<CDIM, ABS, true>(T2[q], ntb2[q], v_c2[q], binf[q], nvacc2, acc[q & 1], abs2x, abs2y,
+                                                         dy2[q >> 1], ndy2[q >> 1], (q & 1) ? dxb : dxa, hA, cb,
+                                                         (q & 1) ? nAb : nAa, (q & 1) ? Bb : Ba, hC, nopac, ncol, idx);
+            } else {
 #pragma unroll
-                    for (int k = 0; k < CDIM; ++k) {
-                        v[k] = fmaf(fac, v_c[s][k], v[k]);
-                        cv = fmaf(col[k], v_c[s][k], cv);
-                    }
-                    const float v_alpha = fmaf(Tn, cv, ra * tb[s]);
-                    tb[s] = fmaf(-fac, cv, tb[s]);
-                    const float v_sigma = (ok && ov <= kAlphaMax) ? -ov * v_alpha : 0.f;
-                    const float wy = v_sigma * dy;
-                    W0[s & 1] += v_sigma;
-                    W1[s & 1] += wy;
-                    W2[s & 1] = fmaf(wy, dy, W2[s & 1]);
-                    if (ABS) {
-                        const float dx = (s & 1) ? dxb : dxa;
-                        v[CDIM + 6] += fabsf(v_sigma * (2.f * hA * dx + cb * dy));
-                        v[CDIM + 7] += fabsf(v_sigma * (cb * dx + 2.f * hC * dy));
-                    }
-                }
+                for (int q = 0; q < NQ; ++q)
+                    if (m >> q & 1)  // warp-uniform
+                        hit |= bwd_quad<CDIM, ABS, false>(T2[q], ntb2[q], v_c2[q], binf[q], nvacc2, acc[q & 1], abs2x, abs2y,
+                                                          dy2[q >> 1], ndy2[q >> 1], (q & 1) ? dxb : dxa, hA, cb,
+                                                          (q & 1) ? nAb : nAa, (q & 1) ? Bb : Ba, hC, nopac, ncol, idx);
             }
             if (!__any_sync(0xffffffffu, hit)) continue;
-            // moments -> gradients (conic entries in the record are scaled by log2 e)
-            const float ua = dxa * W0[0], ub = dxb * W0[1];
-            const float S1x = ua + ub, S1y = W1[0] + W1[1];
+            // negated moments -> gradients (conic entries in the record are scaled by log2 e)
+            float v[NV];
+#pragma unroll
+            for (int k = 0; k < CDIM; ++k) v[k] = -(nvacc2[k].x + nvacc2[k].y);
+            const float W0a = -(acc[0].nW0.x + acc[0].nW0.y), W0b = -(acc[1].nW0.x + acc[1].nW0.y);
+            const float W1a = -(acc[0].nW1.x + acc[0].nW1.y), W1b = -(acc[1].nW1.x + acc[1].nW1.y);
+            const float W2s = -((acc[0].nW2.x + acc[0].nW2.y) + (acc[1].nW2.x + acc[1].nW2.y));
+            const float ua = dxa * W0a, ub = dxb * W0b;
+            const float S1x = ua + ub, S1y = W1a + W1b;
             v[CDIM + 0] = 0.5f * fmaf(dxa, ua, dxb * ub);                 // 1/2 sum v_sigma dx²
-            v[CDIM + 1] = fmaf(dxa, W1[0], dxb * W1[1]);                  // sum v_sigma dx dy
-            v[CDIM + 2] = 0.5f * (W2[0] + W2[1]);                         // 1/2 sum v_sigma dy²
+            v[CDIM + 1] = fmaf(dxa, W1a, dxb * W1b);                      // sum v_sigma dx dy
+            v[CDIM + 2] = 0.5f * W2s;                                     // 1/2 sum v_sigma dy²
             v[CDIM + 3] = kInvLog2e * fmaf(2.f * hA, S1x, cb * S1y);      // sum v_sigma (a dx + b dy)
             v[CDIM + 4] = kInvLog2e * fmaf(cb, S1x, 2.f * hC * S1y);      // sum v_sigma (b dx + c dy)
-            v[CDIM + 5] = -(W0[0] + W0[1]) * rcp_approx(opac);            // sum vis·v_alpha
-            if (ABS) { v[CDIM + 6] *= kInvLog2e; v[CDIM + 7] *= kInvLog2e; }
-            const int32_t g = im.z;
-            warp_reduce_commit<NV>(v, lane, [&](int k, float val) {
-                float *dst;
-                if (k < CDIM) {
-                    if (k >= (int)channels) return;
-                    dst = v_colors + (size_t)g * channels + k;
-                } else if (k < CDIM + 3) dst = v_conics + 3 * (size_t)g + (k - CDIM);
-                else if (k < CDIM + 5) dst = v_means2d + 2 * (size_t)g + (k - CDIM - 3);
-                else if (k == CDIM + 5) dst = v_opacities + g;
-                else dst = v_means2d_abs + 2 * (size_t)g + (k - CDIM - 6);
-                atomicAdd(dst, val);
-            });
+            v[CDIM + 5] = (W0a + W0b) * rcp_approx(nopac);                // sum vis·v_alpha = -S0 / opac
+            if (ABS) {
+                v[CDIM + 6] = kInvLog2e * (abs2x.x + abs2x.y);
+                v[CDIM + 7] = kInvLog2e * (abs2y.x + abs2y.y);
+            }
+            sink.commit(v, lane, im.z);
         }
     }
 }
 
 template <int CDIM, bool ABS>
-static void launch_bwd_v3(uint32_t C, uint64_t n_isects, uint32_t channels, const float4 *rec,
-                          const float *backgrounds, const uint8_t *masks, uint32_t W, uint32_t H, uint32_t tile_width,
-                          uint32_t tile_height, const int32_t *tile_offsets, const int32_t *flatten_ids,
-                          const float *render_alphas, const int32_t *last_ids, const float *v_render_colors,
-                          const float *v_render_alphas, float *v_means2d_abs, float *v_means2d, float *v_conics,
-                          float *v_colors, float *v_opacities, cudaStream_t st) {
+static void launch_bwd_quad(uint32_t C, uint64_t n_isects, uint32_t channels, const float4 *rec,
+                            const float *backgrounds, const uint8_t *masks, uint32_t W, uint32_t H,
+                            uint32_t tile_width, uint32_t tile_height, const int32_t *tile_offsets,
+                            const int32_t *flatten_ids, const float *render_alphas, const int32_t *last_ids,
+                            const float *v_render_colors, const float *v_render_alphas, float *v_means2d_abs,
+                            float *v_means2d, float *v_conics, float *v_colors, float *v_opacities, cudaStream_t st) {
     const uint32_t total = C * tile_width * tile_height;
-#define B2S_BWD3(NS_, MINB_)                                                                                         \
-    raster_bwd_v3_kernel<CDIM, ABS, NS_, MINB_><<<total, 32 * (kV3Slots / NS_), 0, st>>>(                             \
+#define B2S_BWDQ(NQ_, MINB_)                                                                                         \
+    raster_bwd_quad_kernel<CDIM, ABS, NQ_, MINB_><<<total, 32 * (4 / NQ_), 0, st>>>(                                  \
         total, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, \
         render_alphas, last_ids, v_render_colors, v_render_alphas, v_means2d_abs, v_means2d, v_conics, v_colors,     \
         v_opacities)
     switch (tuning_variant()) {
-        case 1: B2S_BWD3(8, 20); break;
-        case 2: B2S_BWD3(4, 16); break;
-        case 3: B2S_BWD3(4, 10); break;
-        default: B2S_BWD3(8, 16); break;
+        case 1: B2S_BWDQ(4, 20); break;
+        case 2: B2S_BWDQ(2, 16); break;
+        case 3: B2S_BWDQ(2, 10); break;
+        default: B2S_BWDQ(4, 16); break;
     }
-#undef B2S_BWD3
+#undef B2S_BWDQ
 }
 
 }  // namespace b2s
@@ -432,7 +541,7 @@ extern "C" int b200splat_rasterize_bwd(uint32_t C, uint32_t n_gauss, uint64_t n_
     const char *where = "b200splat_rasterize_bwd";
     (void)n_gauss;
     if (records != nullptr) {
-        B2S_REQUIRE(tile_size == kV3Tile && channels >= 1 && channels <= 4, where,
+        B2S_REQUIRE(tile_size == kQTile && channels >= 1 && channels <= 4, where,
                     "packed records are only valid for tile_size 16 and <= 4 channels");
         B2S_REQUIRE(n_isects <= 0x7fffffffull, where, "n_isects exceeds int32 offsets");
         if ((uint64_t)C * tile_width * tile_height == 0 || n_isects == 0) return 0;
@@ -442,11 +551,11 @@ extern "C" int b200splat_rasterize_bwd(uint32_t C, uint32_t n_gauss, uint64_t n_
 #define B2S_BWD2(D)                                                                                                    \
     case D:                                                                                                            \
         if (ab)                                                                                                        \
-            launch_bwd_v3<D, true>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height,      \
+            launch_bwd_quad<D, true>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height,      \
                                    tile_offsets, flatten_ids, render_alphas, last_ids, v_render_colors,                \
                                    v_render_alphas, v_means2d_abs, v_means2d, v_conics, v_colors, v_opacities, st2);   \
         else                                                                                                           \
-            launch_bwd_v3<D, false>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height,     \
+            launch_bwd_quad<D, false>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height,     \
                                     tile_offsets, flatten_ids, render_alphas, last_ids, v_render_colors,               \
                                     v_render_alphas, v_means2d_abs, v_means2d, v_conics, v_colors, v_opacities, st2);  \
         break;

@@ -12,7 +12,7 @@
 // consumed with coalesced loads.  The loop body is the fp32/MUFU critical path; see
 // DESIGN.md for the measured limits.
 #include "raster_common.cuh"
-#include "raster_v3.cuh"
+#include "raster_quad.cuh"
 
 namespace b2s {
 
@@ -149,38 +149,69 @@ static int launch_fwd(uint32_t C, uint64_t n_isects, uint32_t channels, const fl
 
 
 // ---------------------------------------------------------------------------------------
-// v3: warp-per-tile, 8 sub-block slots per lane, exact sub-block culling (raster_v3.cuh)
+// quad kernels: warp-per-tile (or per half tile), 8x8 quads, packed fp32x2 (raster_quad.cuh)
 // ---------------------------------------------------------------------------------------
-template <int CDIM, int NS, int MINB>
-__global__ void __launch_bounds__(32 * (kV3Slots / NS), MINB)
-raster_fwd_v3_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channels, const float4 *__restrict__ rec,
-                     const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks, uint32_t W, uint32_t H,
-                     uint32_t tile_width, uint32_t tile_height, const int32_t *__restrict__ tile_offsets,
-                     const int32_t *__restrict__ flatten_ids, float *__restrict__ render_colors,
-                     float *__restrict__ render_alphas, int32_t *__restrict__ last_ids) {
-    // a CTA is one tile; each of its warps owns NS of the 8 sub-blocks and works on its own
-    // (no block-level synchronisation anywhere)
-    __shared__ float4 s_rec_all[kV3Slots / NS][32 * 3];
-    __shared__ int2 s_im_all[kV3Slots / NS][32];  // {sorted index, sub-block mask}
+// One Gaussian against one quad: the lane's two pixels (rows v and v + 4 of the quad).
+// SIGN: the conic is not positive definite, so sigma may be negative and is tested like the
+// reference does (CS/rasterize_to_pixels_fwd.cu:147); for a positive definite conic the
+// test can never fire and is compiled out.
+template <int CDIM, bool SIGN>
+__device__ __forceinline__ void fwd_quad(float2 &T2, float2 (&pix2)[CDIM], int32_t (&cur)[2], const float2 dy2,
+                                         const float2 ndy2, const float nA, const float B, const float hC,
+                                         const float nopac, const float (&ncol)[4], const int32_t idx) {
+    const float2 u2 = __ffma2_rn(bc2(hC), dy2, bc2(B));
+    const float2 ns2 = __ffma2_rn(ndy2, u2, bc2(nA));  // -sigma'
+    const float2 nov2 = __fmul2_rn(bc2(nopac), make_float2(ex2_approx(ns2.x), ex2_approx(ns2.y)));
+    const float nal0 = fmaxf(-kAlphaMax, nov2.x), nal1 = fmaxf(-kAlphaMax, nov2.y);  // -alpha
+    bool ok0 = nal0 <= -kAlphaMin, ok1 = nal1 <= -kAlphaMin;
+    if (SIGN) { ok0 = ok0 && !(ns2.x > 0.f); ok1 = ok1 && !(ns2.y > 0.f); }
+    const float2 nae2 = make_float2(ok0 ? nal0 : 0.f, ok1 ? nal1 : 0.f);
+    const float2 next_T2 = __fmul2_rn(T2, __fadd2_rn(nae2, bc2(1.f)));  // == T exactly when rejected
+    // exclusive stop; also fires for a dead pixel (T < 0), which therefore composites nothing
+    const bool st0 = next_T2.x <= kTransmittanceEps, st1 = next_T2.y <= kTransmittanceEps;
+    const float2 nac2 = make_float2(st0 ? 0.f : nae2.x, st1 ? 0.f : nae2.y);
+    const float2 nvis2 = __fmul2_rn(nac2, T2);  // -alpha T
+#pragma unroll
+    for (int k = 0; k < CDIM; ++k) pix2[k] = __ffma2_rn(bc2(ncol[k]), nvis2, pix2[k]);
+    cur[0] = (nac2.x < 0.f) ? idx : cur[0];
+    cur[1] = (nac2.y < 0.f) ? idx : cur[1];
+    T2.x = st0 ? fminf(T2.x, -T2.x) : next_T2.x;  // -|T|
+    T2.y = st1 ? fminf(T2.y, -T2.y) : next_T2.y;
+}
+
+template <int CDIM, int NQ, int MINB>
+__global__ void __launch_bounds__(32 * (4 / NQ), MINB)
+raster_fwd_quad_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channels, const float4 *__restrict__ rec,
+                       const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks, uint32_t W,
+                       uint32_t H, uint32_t tile_width, uint32_t tile_height,
+                       const int32_t *__restrict__ tile_offsets, const int32_t *__restrict__ flatten_ids,
+                       float *__restrict__ render_colors, float *__restrict__ render_alphas,
+                       int32_t *__restrict__ last_ids) {
+    constexpr int NW = 4 / NQ;    // warps per CTA; each works on its own (no block-level sync)
+    constexpr int NQY = NQ / 2;   // quad rows per warp
+    __shared__ float4 s_rec_all[NW][32 * 3];
+    __shared__ int2 s_im_all[NW][32];  // {sorted index, quad mask}
     const unsigned lane = threadIdx.x & 31, sub = threadIdx.x >> 5;
     float4 *s_rec = s_rec_all[sub];
     int2 *s_im = s_im_all[sub];
     const uint32_t tile_lin = blockIdx.x;
-    const V3Tile tc = v3_tile<NS>(tile_lin, tile_width, tile_height, lane, sub);
+    const QuadTile tc = quad_tile<NQ>(tile_lin, tile_width, tile_height, lane, sub);
     if (backgrounds != nullptr) backgrounds += (size_t)tc.cam * channels;
     const size_t cam_pix = (size_t)tc.cam * H * W;
 
-    // pixel of slot s: (tc.x + 8 (s & 1), tc.y + 4 (s >> 1))
-    uint32_t in_mask = 0;  // bit s: this lane's pixel of slot s is inside the image
+    // pixel j of quad q: (tc.x + 8 (q & 1), tc.y + 8 (q >> 1) + 4 j)
+    uint32_t in_mask = 0;  // bit 2q + j: that pixel is inside the image
 #pragma unroll
-    for (int s = 0; s < NS; ++s)
-        if (tc.x + 8u * (s & 1) < W && tc.y + 4u * (s >> 1) < H) in_mask |= 1u << s;
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            if (tc.x + 8u * (q & 1) < W && tc.y + 8u * (q >> 1) + 4u * j < H) in_mask |= 1u << (2 * q + j);
 
     if (masks != nullptr && !masks[tile_lin]) {
 #pragma unroll
-        for (int s = 0; s < NS; ++s)
+        for (int s = 0; s < 2 * NQ; ++s)
             if (in_mask >> s & 1) {
-                const size_t p = cam_pix + (size_t)(tc.y + 4u * (s >> 1)) * W + tc.x + 8u * (s & 1);
+                const size_t p = cam_pix + (size_t)(tc.y + 8u * (s >> 2) + 4u * (s & 1)) * W + tc.x + 8u * (s >> 1 & 1);
                 for (uint32_t k = 0; k < channels; ++k)
                     render_colors[p * channels + k] = backgrounds == nullptr ? 0.f : backgrounds[k];
             }
@@ -193,16 +224,25 @@ raster_fwd_v3_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channel
     // the sign of T is the liveness flag: T > 0 while the pixel accumulates, -T_final once it has
     // stopped (or lies outside the image).  A dead pixel then "stops" again on every Gaussian:
     // next_T = T (1 - alpha) < 0 <= 1e-4, so it composites nothing and keeps its T.
-    float T[NS], pix[NS][CDIM];
-    int32_t cur[NS];
+    float2 T2[NQ], pix2[NQ][CDIM];
+    int32_t cur[NQ][2];
+    uint32_t live = 0;  // warp-uniform: quads with a live pixel
 #pragma unroll
-    for (int s = 0; s < NS; ++s) {
-        T[s] = (in_mask >> s & 1) ? 1.f : -1.f;
-        cur[s] = 0;
+    for (int q = 0; q < NQ; ++q) {
+        T2[q] = make_float2((in_mask >> (2 * q) & 1) ? 1.f : -1.f, (in_mask >> (2 * q + 1) & 1) ? 1.f : -1.f);
+        cur[q][0] = cur[q][1] = 0;
 #pragma unroll
-        for (int k = 0; k < CDIM; ++k) pix[s][k] = 0.f;
+        for (int k = 0; k < CDIM; ++k) pix2[q][k] = make_float2(0.f, 0.f);
+        if (__any_sync(0xffffffffu, (in_mask >> (2 * q) & 3) != 0)) live |= 1u << q;
     }
-    uint32_t live = __reduce_or_sync(0xffffffffu, in_mask);  // warp-uniform: slots with a live pixel
+    // per-lane constants: centres of the lane's pixel rows (and their negatives), per quad row
+    float2 pyc2[NQY], npyc2[NQY];
+#pragma unroll
+    for (int qy = 0; qy < NQY; ++qy) {
+        pyc2[qy] = make_float2(tc.py + 8.f * qy, tc.py + 8.f * qy + 4.f);
+        npyc2[qy] = make_float2(-pyc2[qy].x, -pyc2[qy].y);
+    }
+    const float pxa = tc.px, pxb = tc.px + 8.f;
 
     // software prefetch of this lane's record for the first batch
     float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
@@ -213,14 +253,17 @@ raster_fwd_v3_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channel
     }
     for (int32_t base = range_start; base < range_end && live != 0; base += 32) {
         uint32_t my_mask = 0;
-        if (my_idx < range_end)
-            my_mask = subblock_mask<NS>(r0.x, r0.y, r0.z, r0.w, r1.x, r2.z, tc.ox, tc.oy, W, H) & live;
+        if (my_idx < range_end) {
+            my_mask = quad_mask<NQ>(r0.x, r0.y, r0.z, r0.w, r1.x, r2.z, tc.ox, tc.oy, W, H);
+            if ((my_mask & live) == 0) my_mask = 0; else my_mask &= (live | kNonPD);
+        }
         const unsigned bal = __ballot_sync(0xffffffffu, my_mask != 0);
         const int n = __popc(bal);
         __syncwarp();  // readers of the previous batch are done
         if (my_mask != 0) {
             const int pos = __popc(bal & ((1u << lane) - 1u));
-            s_rec[3 * pos] = r0; s_rec[3 * pos + 1] = r1; s_rec[3 * pos + 2] = r2;
+            s_rec[3 * pos] = r0; s_rec[3 * pos + 1] = r1;
+            s_rec[3 * pos + 2] = make_float4(r2.x, r2.y, -r0.y, 0.f);
             s_im[pos] = make_int2(my_idx, (int)my_mask);
         }
         __syncwarp();
@@ -235,69 +278,76 @@ raster_fwd_v3_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channel
             const int2 im = s_im[t];
             const int32_t idx = im.x;
             const uint32_t m = (uint32_t)im.y;
-            const float dxa = a.x - tc.px, dxb = dxa - 8.f, dyv = a.y - tc.py;
-            const float hC = b4.x, opac = b4.y;
-            const float Aa = a.z * dxa * dxa, Ba = a.w * dxa, Ab = a.z * dxb * dxb, Bb = a.w * dxb;
-            const float col[4] = {b4.z, b4.w, c4.x, c4.y};
+            const float dxa = a.x - pxa, dxb = a.x - pxb;
+            const float hC = b4.x, nopac = b4.y;
+            const float nAa = -(a.z * dxa) * dxa, Ba = a.w * dxa, nAb = -(a.z * dxb) * dxb, Bb = a.w * dxb;
+            const float ncol[4] = {b4.z, b4.w, c4.x, c4.y};
+            float2 dy2[NQY], ndy2[NQY];
 #pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                if (m >> s & 1) {  // warp-uniform
-                    const float dy = dyv - 4.f * (float)(s >> 1);
-                    const float A = (s & 1) ? Ab : Aa, B = (s & 1) ? Bb : Ba;
-                    const float nsigma = fmaf(-dy, fmaf(hC, dy, B), -A);  // -sigma'
-                    const float alpha = fminf(kAlphaMax, opac * ex2_approx(nsigma));
-                    const bool ok = !(nsigma > 0.f) && (alpha >= kAlphaMin);
-                    const float a_e = ok ? alpha : 0.f;
-                    const float next_T = T[s] * (1.f - a_e);         // == T exactly when rejected
-                    const bool stop = next_T <= kTransmittanceEps;   // exclusive stop (implies ok, or dead)
-                    const float vis = (stop ? 0.f : a_e) * T[s];
+            for (int qy = 0; qy < NQY; ++qy) {
+                ndy2[qy] = __fadd2_rn(pyc2[qy], bc2(c4.z));   // p_y - g_y
+                dy2[qy] = __fadd2_rn(npyc2[qy], bc2(a.y));    // g_y - p_y
+            }
+            if (m & kNonPD) {
 #pragma unroll
-                    for (int k = 0; k < CDIM; ++k) pix[s][k] = fmaf(col[k], vis, pix[s][k]);
-                    cur[s] = (ok && !stop) ? idx : cur[s];
-                    T[s] = stop ? -fabsf(T[s]) : next_T;
-                }
+                for (int q = 0; q < NQ; ++q)
+                    if (m >> q & 1)  // warp-uniform
+                        fwd_quad<CDIM, true>(T2[q], pix2[q], cur[q], dy2[q >> 1], ndy2[q >> 1], (q & 1) ? nAb : nAa,
+                                             (q & 1) ? Bb : Ba, hC, nopac, ncol, idx);
+            } else {
+#pragma unroll
+                for (int q = 0; q < NQ; ++q)
+                    if (m >> q & 1)  // warp-uniform
+                        fwd_quad<CDIM, false>(T2[q], pix2[q], cur[q], dy2[q >> 1], ndy2[q >> 1], (q & 1) ? nAb : nAa,
+                                              (q & 1) ? Bb : Ba, hC, nopac, ncol, idx);
             }
         }
-        // slots whose pixels have all stopped are skipped from now on
+        // quads whose pixels have all stopped are skipped from now on
         uint32_t nl = 0;
 #pragma unroll
-        for (int s = 0; s < NS; ++s)
-            if ((live >> s & 1) && __any_sync(0xffffffffu, T[s] > 0.f)) nl |= 1u << s;
+        for (int q = 0; q < NQ; ++q)
+            if ((live >> q & 1) && __any_sync(0xffffffffu, T2[q].x > 0.f || T2[q].y > 0.f)) nl |= 1u << q;
         live = nl;
     }
 
 #pragma unroll
-    for (int s = 0; s < NS; ++s) {
-        if (in_mask >> s & 1) {
-            const size_t p = cam_pix + (size_t)(tc.y + 4u * (s >> 1)) * W + tc.x + 8u * (s & 1);
-            const float Tf = fabsf(T[s]);
-            render_alphas[p] = 1.f - Tf;
+    for (int q = 0; q < NQ; ++q) {
 #pragma unroll
-            for (int k = 0; k < CDIM; ++k)
-                if (k < (int)channels)
-                    render_colors[p * channels + k] = backgrounds == nullptr ? pix[s][k] : (pix[s][k] + Tf * backgrounds[k]);
-            last_ids[p] = cur[s];
+        for (int j = 0; j < 2; ++j) {
+            if (in_mask >> (2 * q + j) & 1) {
+                const size_t p = cam_pix + (size_t)(tc.y + 8u * (q >> 1) + 4u * j) * W + tc.x + 8u * (q & 1);
+                const float Tf = fabsf(j ? T2[q].y : T2[q].x);
+                render_alphas[p] = 1.f - Tf;
+#pragma unroll
+                for (int k = 0; k < CDIM; ++k)
+                    if (k < (int)channels) {
+                        const float c = j ? pix2[q][k].y : pix2[q][k].x;
+                        render_colors[p * channels + k] = backgrounds == nullptr ? c : (c + Tf * backgrounds[k]);
+                    }
+                last_ids[p] = cur[q][j];
+            }
         }
     }
 }
 
 template <int CDIM>
-static void launch_fwd_v3(uint32_t C, uint64_t n_isects, uint32_t channels, const float4 *rec,
-                          const float *backgrounds, const uint8_t *masks, uint32_t W, uint32_t H, uint32_t tile_width,
-                          uint32_t tile_height, const int32_t *tile_offsets, const int32_t *flatten_ids,
-                          float *render_colors, float *render_alphas, int32_t *last_ids, cudaStream_t st) {
+static void launch_fwd_quad(uint32_t C, uint64_t n_isects, uint32_t channels, const float4 *rec,
+                            const float *backgrounds, const uint8_t *masks, uint32_t W, uint32_t H,
+                            uint32_t tile_width, uint32_t tile_height, const int32_t *tile_offsets,
+                            const int32_t *flatten_ids, float *render_colors, float *render_alphas, int32_t *last_ids,
+                            cudaStream_t st) {
     const uint32_t total = C * tile_width * tile_height;
-#define B2S_FWD3(NS_, MINB_)                                                                                        \
-    raster_fwd_v3_kernel<CDIM, NS_, MINB_><<<total, 32 * (kV3Slots / NS_), 0, st>>>(                                 \
+#define B2S_FWDQ(NQ_, MINB_)                                                                                        \
+    raster_fwd_quad_kernel<CDIM, NQ_, MINB_><<<total, 32 * (4 / NQ_), 0, st>>>(                                      \
         total, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, \
         render_colors, render_alphas, last_ids)
     switch (tuning_variant()) {
-        case 1: B2S_FWD3(8, 16); break;
-        case 2: B2S_FWD3(4, 16); break;
-        case 3: B2S_FWD3(4, 10); break;
-        default: B2S_FWD3(8, 20); break;
+        case 1: B2S_FWDQ(4, 16); break;
+        case 2: B2S_FWDQ(2, 16); break;
+        case 3: B2S_FWDQ(2, 10); break;
+        default: B2S_FWDQ(4, 20); break;
     }
-#undef B2S_FWD3
+#undef B2S_FWDQ
 }
 
 }  // namespace b2s
@@ -305,7 +355,7 @@ static void launch_fwd_v3(uint32_t C, uint64_t n_isects, uint32_t channels, cons
 using namespace b2s;
 
 extern "C" size_t b200splat_rasterize_records_bytes(uint32_t n_gauss, uint32_t channels, uint32_t tile_size) {
-    if (tile_size != kV3Tile || channels < 1 || channels > 4) return 0;  // generic path: no records
+    if (tile_size != kQTile || channels < 1 || channels > 4) return 0;  // generic path: no records
     return (size_t)n_gauss * 3 * sizeof(float4);
 }
 
@@ -333,7 +383,7 @@ extern "C" int b200splat_rasterize_fwd(uint32_t C, uint32_t n_gauss, uint64_t n_
     const char *where = "b200splat_rasterize_fwd";
     (void)n_gauss;
     if (records != nullptr) {
-        B2S_REQUIRE(tile_size == kV3Tile && channels >= 1 && channels <= 4, where,
+        B2S_REQUIRE(tile_size == kQTile && channels >= 1 && channels <= 4, where,
                     "packed records are only valid for tile_size 16 and <= 4 channels");
         B2S_REQUIRE((uint64_t)tile_width * tile_size >= W && (uint64_t)tile_height * tile_size >= H, where,
                     "tile grid does not cover the image");
@@ -342,10 +392,10 @@ extern "C" int b200splat_rasterize_fwd(uint32_t C, uint32_t n_gauss, uint64_t n_
         const float4 *rec = reinterpret_cast<const float4 *>(records);
         cudaStream_t st2 = (cudaStream_t)stream;
         switch (channels) {
-            case 1: launch_fwd_v3<1>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids, st2); break;
-            case 2: launch_fwd_v3<2>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids, st2); break;
-            case 3: launch_fwd_v3<3>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids, st2); break;
-            default: launch_fwd_v3<4>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids, st2); break;
+            case 1: launch_fwd_quad<1>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids, st2); break;
+            case 2: launch_fwd_quad<2>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids, st2); break;
+            case 3: launch_fwd_quad<3>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids, st2); break;
+            default: launch_fwd_quad<4>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids, st2); break;
         }
         B2S_CHECK_LAUNCH(where);
         return 0;

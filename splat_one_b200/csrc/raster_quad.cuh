@@ -1,33 +1,33 @@
-// raster_v3.cuh — shared pieces of the B200 "warp-per-tile" rasterizer (tile_size 16,
+// raster_quad.cuh — shared pieces of the B200 "warp-per-tile" rasterizer (tile_size 16,
 // <= 4 channels: the RGB / RGB+depth cases splat_one renders).
 //
-// Mapping: one warp (= one 32-thread CTA, so the hardware scheduler balances tiles one by
-// one) owns one 16x16 tile.  The tile is cut into 8 sub-blocks of 8x4 pixels ("slots");
-// lane l owns pixel (l & 7, l >> 3) of EVERY sub-block, i.e. 8 pixels whose state (T,
-// colour, last id) lives in registers.  Slot s covers columns 8·(s&1).. and rows 4·(s>>1)..
+// Mapping: a CTA is one 16x16 tile.  The tile is cut into four 8x8 "quads"; a warp owns NQ
+// of them (NQ = 4: one warp per tile; NQ = 2: two warps, upper / lower 16x8 half, working
+// independently).  Lane l owns the two pixels (l & 7, l >> 3) and (l & 7, (l >> 3) + 4) of
+// EVERY quad of its warp; their state (T, colour, last id) lives in registers as float2
+// pairs, and all per-pixel arithmetic of a quad is issued as packed fp32x2 instructions
+// (FFMA2 / FMUL2 / FADD2, new in sm_100): one issue slot does two pixels.
 //
-// Why sub-blocks: the reference's intersection list is a 3-sigma bounding SQUARE per
-// Gaussian; measured on the benchmark scene only 28 % of the (pair, pixel) evaluations it
-// implies can pass the alpha >= 1/255 test, and 31 % of the pairs have no such pixel at
-// all.  At staging time each lane takes one Gaussian of the batch and computes, exactly
-// (minimum of the quadratic form over the rectangle of pixel centres, plus a rounding
-// slack), which of the 8 sub-blocks it can reach.  Pairs with an empty mask are dropped;
-// the others are compacted into shared memory with their 8-bit mask, and the compositing
-// loop runs only the slots in the mask (a warp-uniform branch per slot — no divergence).
-// Culling never changes a result: a culled (pixel, Gaussian) pair is one the per-pixel
-// alpha test would have rejected.
+// Why quads: the reference's intersection list is a 3-sigma bounding SQUARE per Gaussian;
+// measured on the benchmark scene only 28 % of the (pair, pixel) evaluations it implies
+// can pass the alpha >= 1/255 test, and 31 % of the pairs have no such pixel at all.  At
+// staging time each lane takes one Gaussian of the batch and computes, exactly (minimum
+// of the quadratic form over the rectangle of pixel centres, plus a rounding slack), which
+// quads it can reach.  Pairs with an empty mask are dropped; the others are compacted into
+// shared memory with their mask, and the compositing loop runs only the quads in the mask
+// (a warp-uniform branch per quad — no divergence).  Culling never changes a result: a
+// culled (pixel, Gaussian) pair is one the per-pixel alpha test would have rejected.
 //
-// Arithmetic: the packed record carries the conic pre-multiplied by log2(e), so
-// alpha = opacity * ex2(-sigma') with sigma' = A + dy (B + C dy), A = a'/2 dx², B = b' dx,
-// C = c'/2: one lane evaluates a slot with 2 FFMA + 1 MUFU, the dx-dependent terms being
-// shared by the four slots of a column half.
+// Arithmetic: the packed record carries the conic pre-multiplied by log2(e) and the
+// opacity / colours NEGATED (fp32x2 instructions have no negate modifier), so with
+// ndy = -dy:   -sigma' = ndy (B + C dy) - A,   -alpha = max(-0.999, (-o) ex2(-sigma')),
+// 1 - alpha = (-alpha) + 1,   colour += (-c)(-alpha T).  A = a'/2 dx², B = b' dx, C = c'/2.
 #pragma once
 #include "raster_common.cuh"
 
 namespace b2s {
 
-constexpr int kV3Tile = 16;
-constexpr int kV3Slots = 8;
+constexpr int kQTile = 16;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kInvLog2e = 0.6931471805599453f;
 
@@ -45,8 +45,8 @@ __device__ __forceinline__ float rcp_approx(float x) {
 
 // record of Gaussian g (48 bytes, three 16-byte loads):
 //   rec[3g]   = {x, y, L·a/2, L·b}          L = log2(e)
-//   rec[3g+1] = {L·c/2, opacity, c0, c1}
-//   rec[3g+2] = {c2, c3, log2(255·opacity), 0}
+//   rec[3g+1] = {L·c/2, -opacity, -c0, -c1}
+//   rec[3g+2] = {-c2, -c3, log2(255·opacity), 0}
 static __global__ void __launch_bounds__(kThreads)
 pack_records_kernel(uint32_t n, uint32_t channels, const float2 *__restrict__ means2d,
                     const float *__restrict__ conics, const float *__restrict__ colors,
@@ -61,8 +61,8 @@ pack_records_kernel(uint32_t n, uint32_t channels, const float2 *__restrict__ me
     // alpha = op·2^(-sigma') >= 1/255  <=>  sigma' <= log2(255·op); -inf / NaN for op <= 0 / NaN
     const float tau = log2f(255.f * op);
     rec[3 * (size_t)g] = make_float4(xy.x, xy.y, 0.5f * kLog2e * a, kLog2e * b);
-    rec[3 * (size_t)g + 1] = make_float4(0.5f * kLog2e * c, op, col[0], col[1]);
-    rec[3 * (size_t)g + 2] = make_float4(col[2], col[3], tau, 0.f);
+    rec[3 * (size_t)g + 1] = make_float4(0.5f * kLog2e * c, -op, -col[0], -col[1]);
+    rec[3 * (size_t)g + 2] = make_float4(-col[2], -col[3], tau, 0.f);
 }
 
 // Minimum of q(dx,dy) = hA dx² + b dx dy + hC dy² (positive definite) over the rectangle
@@ -79,51 +79,57 @@ __device__ __forceinline__ float rect_qmin(float hA, float b, float hC, float ih
     return qmin;
 }
 
-// Which of the 8 sub-blocks of the tile at pixel origin (ox, oy) can this Gaussian reach
-// with alpha >= 1/255 at some pixel centre?  Conservative: answers "yes" whenever unsure
-// (non positive-definite conic, NaNs); never "yes" for a sub-block outside the image.
-template <int NS>
-__device__ __forceinline__ uint32_t subblock_mask(float gx, float gy, float hA, float b, float hC, float tau,
-                                                  uint32_t ox, uint32_t oy, uint32_t W, uint32_t H) {
+constexpr uint32_t kNonPD = 0x80000000u;  // mask flag: conic not positive definite (sigma may be < 0)
+
+// Which of the NQ 8x8 quads of the region at pixel origin (ox, oy) can this Gaussian reach
+// with alpha >= 1/255 at some pixel centre?  Quad q sits at (ox + 8 (q & 1), oy + 8 (q >> 1)).
+// Conservative: answers "yes" whenever unsure (non positive-definite conic, NaNs); never
+// "yes" for a quad outside the image.  Bit 31 flags a non positive-definite conic.
+template <int NQ>
+__device__ __forceinline__ uint32_t quad_mask(float gx, float gy, float hA, float b, float hC, float tau, uint32_t ox,
+                                              uint32_t oy, uint32_t W, uint32_t H) {
     const bool pd = (hA > 0.f) && (hC > 0.f) && (4.f * hA * hC - b * b > 0.f);
     const float ihC = -0.5f * b / hC, ihA = -0.5f * b / hA;
     uint32_t m = 0;
 #pragma unroll
-    for (int s = 0; s < NS; ++s) {
-        const uint32_t bx = ox + 8u * (s & 1), by = oy + 4u * (s >> 1);
+    for (int q = 0; q < NQ; ++q) {
+        const uint32_t bx = ox + 8u * (q & 1), by = oy + 8u * (q >> 1);
         if (bx >= W || by >= H) continue;
         const float x0 = (float)bx + 0.5f, y0 = (float)by + 0.5f;
-        const float x1 = (float)min(bx + 7u, W - 1u) + 0.5f, y1 = (float)min(by + 3u, H - 1u) + 0.5f;
+        const float x1 = (float)min(bx + 7u, W - 1u) + 0.5f, y1 = (float)min(by + 7u, H - 1u) + 0.5f;
         const float dx0 = gx - x1, dx1 = gx - x0, dy0 = gy - y1, dy1 = gy - y0;
         const float qmin = rect_qmin(hA, b, hC, ihA, ihC, dx0, dx1, dy0, dy1);
         // slack: fp32 rounding of the per-pixel sigma' (terms up to `mag`) plus ~2 % in alpha
         const float mx = fmaxf(fabsf(dx0), fabsf(dx1)), my = fmaxf(fabsf(dy0), fabsf(dy1));
         const float mag = hA * mx * mx + hC * my * my + fabsf(b) * mx * my;
         const bool drop = pd && (qmin - (0.03f + 2e-6f * mag) > tau);  // NaN-safe: keeps on NaN
-        if (!drop) m |= 1u << s;
+        if (!drop) m |= 1u << q;
     }
+    if (m != 0 && !pd) m |= kNonPD;
     return m;
 }
 
-struct V3Tile {
+__device__ __forceinline__ float2 bc2(float s) { return make_float2(s, s); }
+
+struct QuadTile {
     uint32_t cam;
-    uint32_t ox, oy;       // pixel origin of the tile
-    uint32_t x, y;         // this lane's pixel in slot 0
+    uint32_t ox, oy;       // pixel origin of this warp's region
+    uint32_t x, y;         // this lane's first pixel in quad 0
     float px, py;          // its centre
 };
 
-// `sub`: which NS-slot part of the tile this warp owns (0 when NS == 8; 0/1 = upper/lower
-// 16x8 half when NS == 4)
-template <int NS>
-__device__ __forceinline__ V3Tile v3_tile(uint32_t tile_lin, uint32_t tile_width, uint32_t tile_height, unsigned lane,
-                                          uint32_t sub) {
-    V3Tile t;
+// `sub`: which part of the tile this warp owns (0 when NQ == 4; 0/1 = upper/lower 16x8 half
+// when NQ == 2)
+template <int NQ>
+__device__ __forceinline__ QuadTile quad_tile(uint32_t tile_lin, uint32_t tile_width, uint32_t tile_height,
+                                              unsigned lane, uint32_t sub) {
+    QuadTile t;
     const uint32_t n_tiles = tile_width * tile_height;
     t.cam = tile_lin / n_tiles;
     const uint32_t tid = tile_lin - t.cam * n_tiles;
     const uint32_t ty = tid / tile_width, tx = tid - ty * tile_width;
-    t.ox = tx * kV3Tile;
-    t.oy = ty * kV3Tile + sub * (NS / 2) * 4;
+    t.ox = tx * kQTile;
+    t.oy = ty * kQTile + sub * 8u;
     t.x = t.ox + (lane & 7);
     t.y = t.oy + (lane >> 3);
     t.px = (float)t.x + 0.5f;
