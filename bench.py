@@ -47,52 +47,96 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md): an NVML
+    polling thread (10 ms period) in this process; `nvidia-smi -lms` as the fallback."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        import threading
+
+        self.sm, self.mx, self.reasons, self.power = [], [], set(), []
+        self._stop = threading.Event()
+        self._thread = None
+        self._smi = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml as nv
+
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            bits = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                        self.mx.append(float(mx))
+                        r = int(get_reasons(h))
+                        for name, bit in bits.items():
+                            if r & bit:
+                                self.reasons.add(name)
+                        self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                    except Exception:
+                        pass
+                    self._stop.wait(0.01)
+
+            self._thread = threading.Thread(target=poll, daemon=True)
+            self._thread.start()
         except Exception:
-            self.p = None
+            self._thread = None
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            try:
+                self._smi = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                              "-lms", "100", "-i", str(gpu_index)], stdout=self.f,
+                                             stderr=subprocess.DEVNULL)
+            except Exception:
+                self._smi = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        for line in self.f.read().splitlines():
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
-                continue
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+        elif self._smi is not None:
+            self._smi.terminate()
             try:
-                sm.append(float(c[1]))
-                mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                   "samples": len(sm)}
-        try:
-            os.unlink(self.f.name)
-        except OSError:
-            pass
+                self._smi.wait(timeout=5)
+            except Exception:
+                self._smi.kill()
+            self.f.flush()
+            self.f.seek(0)
+            for line in self.f.read().splitlines():
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    self.sm.append(float(c[1]))
+                    self.mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                   c[5:9]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(name)
+            try:
+                os.unlink(self.f.name)
+            except OSError:
+                pass
+        if self.sm:
+            out = {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": max(self.mx), "reasons": sorted(self.reasons),
+                   "samples": len(self.sm)}
+            if self.power:
+                out["power_w"] = round(statistics.median(self.power), 1)
         return out
 
 
@@ -350,7 +394,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

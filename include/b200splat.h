@@ -222,7 +222,10 @@ B200SPLAT_API int b200splat_isect_sort(
 /* Phases 2+3 in one call for non-negative depths — the B200 path used by
  * rasterization(): Gaussians are ordered by depth first (n_elems 32-bit keys), expanded
  * into their tiles in that order, and only the cam|tile bits are sorted at intersection
- * scale; the output is bit-identical to `_fill` + `_sort` (see csrc/sort.cu). */
+ * scale; the output is bit-identical to `_fill` + `_sort` (see csrc/sort.cu).
+ * `offsets` (optional, may be NULL): [C*n_tiles] int32, the result of
+ * `b200splat_isect_offset_encode` on the produced ids, written by the same final pass
+ * (requires n_isects > 0; the caller zero-fills for n_isects == 0). */
 B200SPLAT_API size_t b200splat_isect_sorted_workspace_bytes(uint64_t n_elems, uint64_t n_isects);
 
 B200SPLAT_API int b200splat_isect_sorted(
@@ -231,7 +234,7 @@ B200SPLAT_API int b200splat_isect_sorted(
     const float *means2d, const int32_t *radii, const float *depths,
     const int32_t *tiles_per_gauss, uint64_t n_isects,
     uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
-    int64_t *isect_ids, int32_t *flatten_ids,
+    int64_t *isect_ids, int32_t *flatten_ids, int32_t *offsets,
     void *workspace, size_t workspace_bytes,
     void *stream);
 

@@ -284,13 +284,15 @@ sh_colors_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, int per_v
                 x = dx * inorm; y = dy * inorm; z = dz * inorm;
             }
             if (v_means != nullptr && NB > 1) {
-                const float4 *row4 = reinterpret_cast<const float4 *>(coeffs + (per_view ? e : (uint64_t)n) * K * 3);
-                const float *row = coeffs + (per_view ? e : (uint64_t)n) * K * 3;
+                // the row is read with 128-bit loads (12 per Gaussian at K = 16): a scalar load per
+                // coefficient touches 32 cache lines per warp instruction and is L1-wavefront bound
+                float cf[NB * 3];
+                load_row<NB>(coeffs + (per_view ? e : (uint64_t)n) * K * 3, cf,
+                             ((K * 3) % 4 == 0) && ((reinterpret_cast<uintptr_t>(coeffs) & 15) == 0));
                 float vx = 0.f, vy = 0.f, vz = 0.f;
-                (void)row4;
                 sh_for_each_basis<true>(deg, x, y, z, [&](int k, float B, float Bx, float By, float Bz) {
                     vc[3 * k] += B * vr; vc[3 * k + 1] += B * vg; vc[3 * k + 2] += B * vb;
-                    const float w = __ldg(row + 3 * k) * vr + __ldg(row + 3 * k + 1) * vg + __ldg(row + 3 * k + 2) * vb;
+                    const float w = cf[3 * k] * vr + cf[3 * k + 1] * vg + cf[3 * k + 2] * vb;
                     vx += Bx * w; vy += By * w; vz += Bz * w;
                 });
                 const float d = vx * x + vy * y + vz * z;

@@ -61,8 +61,10 @@ gather_counts_kernel(uint64_t n_elems, const uint32_t *__restrict__ order, const
     counts[i] = tiles_per_gauss[order[i]];
 }
 
-// step 3: one warp expands 32 consecutive Gaussians (in depth order); for each, the 32
-// lanes write its tiles side by side, so a warp's stores cover one contiguous range.
+// step 3: one warp expands 32 consecutive Gaussians (in depth order).  Their intersections
+// occupy one contiguous output range, so the lanes are mapped to OUTPUT positions (lane l
+// writes positions l, l + 32, ...: fully coalesced 128-byte stores) and each finds its
+// Gaussian by a 5-step binary search over the 32 in-warp start offsets (warp shuffles).
 __global__ void __launch_bounds__(kThreads)
 expand_kernel(int packed, uint32_t N, uint64_t n_elems, const uint32_t *__restrict__ order,
               const int64_t *__restrict__ cum_sorted, const int64_t *__restrict__ camera_ids,
@@ -70,48 +72,81 @@ expand_kernel(int packed, uint32_t N, uint64_t n_elems, const uint32_t *__restri
               uint32_t tile_n_bits, uint32_t *__restrict__ tile_keys, uint32_t *__restrict__ vals) {
     const unsigned lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp * 32 >= n_elems) return;  // warp-uniform
     const uint64_t i = warp * 32 + lane;
-    uint32_t idx = 0, x0 = 0, y0 = 0, w = 0, cnt = 0, cam_enc = 0;
-    int64_t start = 0;
+    uint32_t idx = 0, xy0 = 0, w = 1, cnt = 0, cam_enc = 0;
     if (i < n_elems) {
         idx = order[i];
         const float radius = (float)radii[idx];
         if (radius > 0.f) {
             const float2 m = reinterpret_cast<const float2 *>(means2d)[idx];
             const TileRect2 r = tile_rect2(m.x, m.y, radius, ts, tw, th);
-            x0 = r.x0; y0 = r.y0; w = r.x1 - r.x0;
+            w = r.x1 - r.x0;
             cnt = (r.y1 - r.y0) * w;
+            xy0 = r.x0 | (r.y0 << 16);
+            w = max(w, 1u);
             const uint32_t cid = packed ? (uint32_t)camera_ids[idx] : (uint32_t)(idx / N);
             cam_enc = cid << tile_n_bits;
-            start = (i == 0) ? 0 : cum_sorted[i - 1];
         }
     }
-    const unsigned active = __ballot_sync(0xffffffffu, cnt > 0);
-    for (unsigned m = active; m; m &= m - 1) {
-        const int src = __ffs(m) - 1;
-        const uint32_t g_idx = __shfl_sync(0xffffffffu, idx, src);
-        const uint32_t g_x0 = __shfl_sync(0xffffffffu, x0, src), g_y0 = __shfl_sync(0xffffffffu, y0, src);
-        const uint32_t g_w = __shfl_sync(0xffffffffu, w, src), g_cnt = __shfl_sync(0xffffffffu, cnt, src);
-        const uint32_t g_cam = __shfl_sync(0xffffffffu, cam_enc, src);
-        const int64_t g_start = __shfl_sync(0xffffffffu, start, src);
-        for (uint32_t k = lane; k < g_cnt; k += 32) {
-            const uint32_t ry = k / g_w, rx = k - ry * g_w;
-            tile_keys[g_start + k] = g_cam | ((g_y0 + ry) * tw + (g_x0 + rx));
-            vals[g_start + k] = g_idx;
+    // cum_sorted is the inclusive scan of the same counts in the same order
+    const int64_t end = cum_sorted[i < n_elems ? i : n_elems - 1];
+    const int64_t warp_base = __shfl_sync(0xffffffffu, end - (int64_t)cnt, 0);
+    const uint32_t total = (uint32_t)(__shfl_sync(0xffffffffu, end, 31) - warp_base);
+    const uint32_t rel_start = (uint32_t)(end - (int64_t)cnt - warp_base);
+    const float inv_w = 1.f / (float)w;
+    for (uint32_t base = 0; base < total; base += 32) {
+        const uint32_t p = base + lane;
+        // largest j with rel_start[j] <= p: Gaussians without tiles share their successor's
+        // start and are skipped; lanes past the end have rel_start == total > p
+        int pos = 0;
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+            const uint32_t s_ = __shfl_sync(0xffffffffu, rel_start, pos + step);
+            if (s_ <= p) pos += step;
+        }
+        const uint32_t g_idx = __shfl_sync(0xffffffffu, idx, pos), g_xy0 = __shfl_sync(0xffffffffu, xy0, pos);
+        const uint32_t g_w = __shfl_sync(0xffffffffu, w, pos), g_rs = __shfl_sync(0xffffffffu, rel_start, pos);
+        const uint32_t g_cam = __shfl_sync(0xffffffffu, cam_enc, pos);
+        const float g_iw = __shfl_sync(0xffffffffu, inv_w, pos);
+        if (p < total) {
+            const uint32_t k = p - g_rs;
+            uint32_t ry = __float2uint_rz(((float)k + 0.5f) * g_iw);  // k / g_w, fixed up below
+            if (ry * g_w > k) --ry;
+            if ((ry + 1) * g_w <= k) ++ry;
+            const uint32_t rx = k - ry * g_w;
+            tile_keys[warp_base + p] = g_cam | (((g_xy0 >> 16) + ry) * tw + (g_xy0 & 0xffffu) + rx);
+            vals[warp_base + p] = g_idx;
         }
     }
 }
 
-// step 5: 64-bit ids from the sorted (cam|tile, flat index) pairs
+// step 5: 64-bit ids from the sorted (cam|tile, flat index) pairs, and — fused, optional —
+// the per-tile offsets of a7 (same rule as offset_encode_kernel in isect.cu)
 __global__ void __launch_bounds__(kThreads)
 assemble_kernel(uint64_t n_isects, const uint32_t *__restrict__ tile_keys, const uint32_t *__restrict__ vals,
-                const float *__restrict__ depths, int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids) {
+                const float *__restrict__ depths, int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids,
+                uint32_t total_tiles, uint32_t n_tiles, uint32_t tile_n_bits, int32_t *__restrict__ offsets) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_isects) return;
     const uint32_t v = vals[i];
+    const uint32_t key = tile_keys[i];
     const uint32_t d = (uint32_t)__float_as_int(__ldg(depths + v));
-    isect_ids[i] = (int64_t)(((uint64_t)tile_keys[i] << 32) | (uint64_t)d);
+    isect_ids[i] = (int64_t)(((uint64_t)key << 32) | (uint64_t)d);
     flatten_ids[i] = (int32_t)v;
+    if (offsets == nullptr) return;
+    const uint32_t tile_mask = (1u << tile_n_bits) - 1u;
+    const int64_t id_curr = (int64_t)(key >> tile_n_bits) * n_tiles + (key & tile_mask);
+    if (i == 0)
+        for (int64_t k = 0; k <= id_curr && k < total_tiles; ++k) offsets[k] = 0;
+    if (i == n_isects - 1)
+        for (int64_t k = id_curr + 1; k < total_tiles; ++k) offsets[k] = (int32_t)n_isects;
+    if (i > 0) {
+        const uint32_t prev = tile_keys[i - 1];
+        if (prev == key) return;
+        const int64_t id_prev = (int64_t)(prev >> tile_n_bits) * n_tiles + (prev & tile_mask);
+        for (int64_t k = id_prev + 1; k <= id_curr && k < total_tiles; ++k) offsets[k] = (int32_t)i;
+    }
 }
 
 static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -187,7 +222,8 @@ extern "C" int b200splat_isect_sorted(int packed, uint32_t C, uint32_t N, uint32
                                       const float *means2d, const int32_t *radii, const float *depths,
                                       const int32_t *tiles_per_gauss, uint64_t n_isects, uint32_t tile_size,
                                       uint32_t tile_width, uint32_t tile_height, int64_t *isect_ids,
-                                      int32_t *flatten_ids, void *workspace, size_t workspace_bytes, void *stream) {
+                                      int32_t *flatten_ids, int32_t *offsets, void *workspace, size_t workspace_bytes,
+                                      void *stream) {
     const char *where = "b200splat_isect_sorted";
     cudaStream_t st = (cudaStream_t)stream;
     const uint64_t n_elems = packed ? (uint64_t)nnz : (uint64_t)C * N;
@@ -234,7 +270,8 @@ extern "C" int b200splat_isect_sorted(int packed, uint32_t C, uint32_t N, uint32
     if (e != cudaSuccess) return fail_cuda(where, e);
     // 5. assemble
     assemble_kernel<<<div_up(n_isects, kThreads), kThreads, 0, st>>>(n_isects, tk.Current(), tv.Current(), depths,
-                                                                     isect_ids, flatten_ids);
+                                                                     isect_ids, flatten_ids, C * n_tiles, n_tiles,
+                                                                     tile_n_bits, offsets);
     B2S_CHECK_LAUNCH(where);
     return 0;
 }

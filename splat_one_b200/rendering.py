@@ -22,8 +22,7 @@ from typing_extensions import Literal
 
 from .wrapper import (
     fully_fused_projection,
-    isect_offset_encode,
-    isect_tiles,
+    isect_tiles_and_offsets,
     rasterize_to_pixels,
     sh_view_colors,
     spherical_harmonics,
@@ -165,11 +164,10 @@ def rasterization(
     # ---- tile intersection (a6, a7) ---------------------------------------------------
     tile_width = math.ceil(width / float(tile_size))
     tile_height = math.ceil(height / float(tile_size))
-    tiles_per_gauss, isect_ids, flatten_ids = isect_tiles(
+    tiles_per_gauss, isect_ids, flatten_ids, isect_offsets = isect_tiles_and_offsets(
         means2d, radii, depths, tile_size, tile_width, tile_height,
         packed=packed, n_cameras=C, camera_ids=camera_ids, gaussian_ids=gaussian_ids,
     )
-    isect_offsets = isect_offset_encode(isect_ids, C, tile_width, tile_height)
 
     meta.update({
         "tile_width": tile_width,

@@ -486,7 +486,7 @@ class _FullyFusedProjectionPacked(torch.autograd.Function):
 # tile intersection (a6) and offset encode (a7)
 # ----------------------------------------------------------------------------------------
 @torch.no_grad()
-def isect_tiles(
+def _isect_tiles_impl(
     means2d: Tensor,  # [C, N, 2] or [nnz, 2]
     radii: Tensor,  # [C, N] or [nnz]
     depths: Tensor,  # [C, N] or [nnz]
@@ -498,12 +498,10 @@ def isect_tiles(
     n_cameras: Optional[int] = None,
     camera_ids: Optional[Tensor] = None,
     gaussian_ids: Optional[Tensor] = None,
-) -> Tuple[Tensor, Tensor, Tensor]:
-    """Maps projected Gaussians to intersecting tiles (G/cuda/_wrapper.py:342-413).
-
-    Returns (tiles_per_gauss int32 [C,N]|[nnz], isect_ids int64 [n_isects],
-    flatten_ids int32 [n_isects]); bit-exact with the reference given the same inputs.
-    """
+    want_offsets: bool = False,
+):
+    """isect_tiles; with `want_offsets` also the [C, tile_height, tile_width] offsets of
+    isect_offset_encode, which the depth-first path produces in its final pass for free."""
     if packed:
         nnz = means2d.size(0)
         assert means2d.shape == (nnz, 2), means2d.size()
@@ -558,10 +556,12 @@ def isect_tiles(
             # depth-first ordering (csrc/sort.cu): bit-identical to fill + full-key sort
             ws_bytes = lib.b200splat_isect_sorted_workspace_bytes(n_elems, n_isects)
             ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
+            offsets = (torch.empty((C, tile_height, tile_width), device=dev, dtype=torch.int32)
+                       if want_offsets else None)
             native("isect_sorted", lib, dev, int(packed), C, N, nnz, _ptr(camera_ids), _ptr(means2d), _ptr(radii),
                    _ptr(depths), _ptr(tiles_per_gauss), n_isects, tile_size, tile_width, tile_height,
-                   _ptr(isect_ids), _ptr(flatten_ids), _ptr(ws), ws_bytes)
-            return tiles_per_gauss, isect_ids, flatten_ids
+                   _ptr(isect_ids), _ptr(flatten_ids), _ptr(offsets), _ptr(ws), ws_bytes)
+            return tiles_per_gauss, isect_ids, flatten_ids, offsets
         native("isect_fill", lib, dev, int(packed), C, N, nnz, _ptr(camera_ids), _ptr(means2d), _ptr(radii),
                _ptr(depths), _ptr(cum_tiles), tile_size, tile_width, tile_height, _ptr(isect_ids), _ptr(flatten_ids))
         if sort:
@@ -574,7 +574,43 @@ def isect_tiles(
                    _ptr(isect_ids_alt), _ptr(flatten_ids_alt), _ptr(ws), ws_bytes, ctypes.byref(selector))
             if selector.value == 1:
                 isect_ids, flatten_ids = isect_ids_alt, flatten_ids_alt
-    return tiles_per_gauss, isect_ids, flatten_ids
+    return tiles_per_gauss, isect_ids, flatten_ids, None
+
+
+@torch.no_grad()
+def isect_tiles(
+    means2d: Tensor,  # [C, N, 2] or [nnz, 2]
+    radii: Tensor,  # [C, N] or [nnz]
+    depths: Tensor,  # [C, N] or [nnz]
+    tile_size: int,
+    tile_width: int,
+    tile_height: int,
+    sort: bool = True,
+    packed: bool = False,
+    n_cameras: Optional[int] = None,
+    camera_ids: Optional[Tensor] = None,
+    gaussian_ids: Optional[Tensor] = None,
+) -> Tuple[Tensor, Tensor, Tensor]:
+    """Maps projected Gaussians to intersecting tiles (G/cuda/_wrapper.py:342-413).
+
+    Returns (tiles_per_gauss int32 [C,N]|[nnz], isect_ids int64 [n_isects],
+    flatten_ids int32 [n_isects]); bit-exact with the reference given the same inputs.
+    """
+    return _isect_tiles_impl(means2d, radii, depths, tile_size, tile_width, tile_height, sort, packed, n_cameras,
+                             camera_ids, gaussian_ids)[:3]
+
+
+@torch.no_grad()
+def isect_tiles_and_offsets(means2d, radii, depths, tile_size, tile_width, tile_height, packed=False,
+                            n_cameras=None, camera_ids=None, gaussian_ids=None):
+    """`isect_tiles(...)` followed by `isect_offset_encode(...)` (G/rendering.py:497-510) as one
+    operator: returns (tiles_per_gauss, isect_ids, flatten_ids, isect_offsets)."""
+    tpg, ids, flat, offs = _isect_tiles_impl(means2d, radii, depths, tile_size, tile_width, tile_height, True, packed,
+                                             n_cameras, camera_ids, gaussian_ids, want_offsets=True)
+    if offs is None:
+        C = n_cameras if packed else means2d.shape[0]
+        offs = isect_offset_encode(ids, C, tile_width, tile_height)
+    return tpg, ids, flat, offs
 
 
 @torch.no_grad()

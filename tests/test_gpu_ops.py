@@ -244,7 +244,20 @@ def test_isect_random_exact(C, N, W, H, ts):
     got = S.isect_tiles(m2.to(DEV), radii.to(DEV), depths.to(DEV), ts, tw, th)
     for a, b in zip(got, ref):
         assert torch.equal(a.cpu(), b)
-    assert torch.equal(S.isect_offset_encode(got[1], C, tw, th).cpu(), O.isect_offset_encode(ref[1], C, tw, th))
+    ref_offs = O.isect_offset_encode(ref[1], C, tw, th)
+    assert torch.equal(S.isect_offset_encode(got[1], C, tw, th).cpu(), ref_offs)
+    # fused variant used by rasterization(): same four tensors from one call
+    from splat_one_b200.wrapper import isect_tiles_and_offsets
+    fused = isect_tiles_and_offsets(m2.to(DEV), radii.to(DEV), depths.to(DEV), ts, tw, th)
+    for a, b in zip(fused, list(ref) + [ref_offs]):
+        assert torch.equal(a.cpu(), b)
+    # wide rectangles: radii up to the whole image (long per-Gaussian tile runs)
+    radii2 = torch.randint(0, max(W, H), (C, N), generator=g, dtype=torch.int32)
+    radii2[:, N // 4:] = 0
+    ref2 = O.isect_tiles(m2, radii2, depths, ts, tw, th)
+    fused2 = isect_tiles_and_offsets(m2.to(DEV), radii2.to(DEV), depths.to(DEV), ts, tw, th)
+    for a, b in zip(fused2, list(ref2) + [O.isect_offset_encode(ref2[1], C, tw, th)]):
+        assert torch.equal(a.cpu(), b)
 
 
 def test_isect_packed_and_edges():
@@ -262,6 +275,13 @@ def test_isect_packed_and_edges():
     for a, b in zip(got, ref):
         assert torch.equal(a.cpu(), b)
     assert torch.equal(S.isect_offset_encode(got[1], C, tw, th).cpu(), O.isect_offset_encode(ref[1], C, tw, th))
+    from splat_one_b200.wrapper import isect_tiles_and_offsets
+    fused = isect_tiles_and_offsets(m2.to(DEV), radii.to(DEV), depths.to(DEV), ts, tw, th, packed=True, n_cameras=C,
+                                    camera_ids=cam.to(DEV), gaussian_ids=gau.to(DEV))
+    assert torch.equal(fused[3].cpu(), O.isect_offset_encode(ref[1], C, tw, th))
+    zf = isect_tiles_and_offsets(torch.zeros(2, 9, 2, device=DEV), torch.zeros(2, 9, dtype=torch.int32, device=DEV),
+                                 torch.ones(2, 9, device=DEV), 16, 2, 2)
+    assert zf[3].shape == (2, 2, 2) and zf[3].abs().sum() == 0
     # empty inputs and all-invisible inputs
     e = S.isect_tiles(torch.zeros(2, 0, 2, device=DEV), torch.zeros(2, 0, dtype=torch.int32, device=DEV),
                       torch.zeros(2, 0, device=DEV), 16, 2, 2)
