@@ -359,8 +359,16 @@ def run_gpu(args):
         if dom is not None:
             dur = stages[dom]["avg_ms"] * 1e-3
             ach = alg_bytes.get(dom, 0) / dur / 1e9
+            traffic, traffic_src = None, None
+            try:  # dram bytes per launch from the committed ncu --set full capture of the same kernel
+                with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+                    t = json.load(f).get(dom)
+                if t:
+                    traffic, traffic_src = t["traffic_bytes"], t["source"]
+            except Exception:
+                pass
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "algorithmic_bytes": alg_bytes.get(dom, 0), "avg_launch_ms": stages[dom]["avg_ms"]}
         stage_report = {k: {"avg_ms": round(v["avg_ms"], 4),
                             "GBps": round(alg_bytes.get(k, 0) / (v["avg_ms"] * 1e-3) / 1e9, 1) if v["avg_ms"] > 0 else None}
