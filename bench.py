@@ -238,10 +238,24 @@ def run_gpu(args):
         for p in params:
             p.grad = None
         rc, ra, meta = S.rasterization(*params, vm, Ks, WIDTH, HEIGHT, sh_degree=SH_DEGREE, packed=False)
-        torch.autograd.backward([rc, ra], [vc, va])
         if arena is not None:
+            with arena.sink():  # SH / quats / scales gradients are produced inside the arena
+                torch.autograd.backward([rc, ra], [vc, va])
+        else:
+            torch.autograd.backward([rc, ra], [vc, va])
+        if arena is not None:
+            prof = wrapper.profiler
+            if prof.enabled:
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                ev[0].record()
             arena.gather_from_params()
+            if prof.enabled:
+                ev[1].record()
             arena.all_reduce()
+            if prof.enabled:
+                ev[2].record()
+                prof.events.setdefault("grad_gather", []).append((ev[0], ev[1]))
+                prof.events.setdefault("grad_allreduce", []).append((ev[1], ev[2]))
         return rc, ra, meta
 
     def barrier():
@@ -312,10 +326,13 @@ def run_gpu(args):
         main.wait_event(cot_ready)
         vc_d.record_stream(main)
         va_d.record_stream(main)
-        torch.autograd.backward([rc_, ra_], [vc_d, va_d])
         if arena is not None:
+            with arena.sink():
+                torch.autograd.backward([rc_, ra_], [vc_d, va_d])
             arena.gather_from_params()
             arena.all_reduce()
+        else:
+            torch.autograd.backward([rc_, ra_], [vc_d, va_d])
         gnorm_host.copy_(params[0].grad.norm().reshape(1), non_blocking=True)
         main.wait_stream(copy_stream)
 
@@ -337,7 +354,8 @@ def run_gpu(args):
     if rank == 0:
         peak, peak_src = _peaks()
         # dominant kernel = the longest native call per step
-        dom = max(stages.items(), key=lambda kv: kv[1]["total_ms"])[0] if stages else None
+        native_stages = {k: v for k, v in stages.items() if not k.startswith("grad_")}
+        dom = max(native_stages.items(), key=lambda kv: kv[1]["total_ms"])[0] if native_stages else None
         N, C = N_GAUSS, C_local
         alg_bytes = {  # SURVEY.md §8(d), per launch
             "projection_fwd": 40 * N + 4 * C * N + 24 * V,
@@ -345,6 +363,8 @@ def run_gpu(args):
             "sh_colors_fwd": 216 * V + 4 * C * N,
             "sh_colors_bwd": 228 * V + 192 * N + 4 * C * N,
             "isect_sorted": 16 * V + 8 * C * N + 12 * I + 24 * I,
+            "grad_gather": 2 * 236 * N,
+            "grad_allreduce": 236 * N,
             "rasterize_pack": 36 * C * N + 48 * C * N,
             "isect_count": 4 * C * N + 8 * V + 4 * C * N + 8 * C * N,
             "isect_fill": 16 * V + 8 * C * N + 12 * I,

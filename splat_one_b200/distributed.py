@@ -46,10 +46,21 @@ class GradArena:
     def nbytes(self) -> int:
         return self.flat.numel() * 4
 
+    def sink(self):
+        """Context manager for the backward pass: gradients that the CUDA kernels fully overwrite
+        are produced directly inside the arena (see `wrapper.gradient_sink`), so
+        `gather_from_params` has nothing to copy for them."""
+        from .wrapper import gradient_sink
+
+        return gradient_sink(zip(self.params, self.views))
+
     def gather_from_params(self, zero_missing: bool = True) -> None:
-        """Copy p.grad (dense or sparse COO) of every parameter into the arena."""
+        """Copy p.grad (dense or sparse COO) of every parameter into the arena (skipping the
+        ones that already live there)."""
         for p, v in zip(self.params, self.views):
             g = p.grad
+            if g is not None and not g.is_sparse and g.data_ptr() == v.data_ptr() and g.shape == v.shape:
+                continue
             if g is None:
                 if zero_missing:
                     v.zero_()

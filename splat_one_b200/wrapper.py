@@ -116,6 +116,46 @@ def _f32(t: Optional[Tensor]) -> Optional[Tensor]:
     return t
 
 
+# ----------------------------------------------------------------------------------------
+# gradient sink: let the backward kernels write parameter gradients in place
+# ----------------------------------------------------------------------------------------
+_GRAD_SINK: dict = {}  # param.data_ptr() -> destination buffer (global: autograd runs backward on its own threads)
+
+
+class gradient_sink:
+    """Context manager.  While active, parameter gradients that a backward kernel fully
+    OVERWRITES (means / quats / scales / covars of the unpacked projection, the SH table of the
+    fused colour stage) are written straight into the given buffers — e.g. the views of the
+    flat all-reduce arena of `splat_one_b200.distributed.GradArena` — instead of into fresh
+    allocations, so no gather copy is needed before the collective.  `pairs`: iterable of
+    (parameter, destination) with equal shapes; destinations must be contiguous fp32."""
+
+    def __init__(self, pairs):
+        self.pairs = [(p, d) for p, d in pairs]
+
+    def __enter__(self):
+        for p, d in self.pairs:
+            assert p.shape == d.shape and d.is_contiguous() and d.dtype == torch.float32, (p.shape, d.shape)
+            _GRAD_SINK[p.data_ptr()] = d
+        return self
+
+    def __exit__(self, *exc):
+        for p, _ in self.pairs:
+            _GRAD_SINK.pop(p.data_ptr(), None)
+        return False
+
+
+def _grad_out(like: Tensor) -> Tensor:
+    """Destination for a gradient the kernel fully overwrites: the registered sink buffer of
+    this parameter if there is one, else a fresh allocation."""
+    d = _GRAD_SINK.get(like.data_ptr()) if _GRAD_SINK else None
+    if d is not None and d.shape == like.shape and d.device == like.device:
+        # a fresh alias of the buffer: autograd adopts a gradient without cloning it only when
+        # nothing else references the tensor object it is handed
+        return d.detach()
+    return torch.empty_like(like)
+
+
 def _aligned16(t: Optional[Tensor]) -> Optional[Tensor]:
     """128-bit loads need 16-byte aligned bases; views into odd offsets are re-packed."""
     if t is None or t.data_ptr() % 16 == 0:
@@ -272,7 +312,7 @@ class _ShViewColors(torch.autograd.Function):
         C, N = radii.shape
         K = coeffs.shape[-2]
         per_view = int(coeffs.dim() == 4)
-        v_coeffs = torch.empty_like(coeffs)
+        v_coeffs = _grad_out(coeffs)
         v_means = torch.empty_like(means) if ctx.needs_input_grad[1] else None
         if N:
             native("sh_colors_bwd", lib, means.device, C, N, K, ctx.sh_degree, per_view, _ptr(means), _ptr(campos),
@@ -381,10 +421,12 @@ class _FullyFusedProjection(torch.autograd.Function):
             v_compensations = None
         elif v_compensations is not None:
             v_compensations = v_compensations.contiguous()
+        # `means` also receives a gradient from the colour stage, so autograd sums two tensors and
+        # its sink (if any) cannot be written here; the other three have a single producer
         v_means = torch.empty_like(means)
-        v_covars = torch.empty_like(covars) if covars is not None else None
-        v_quats = torch.empty_like(quats) if covars is None else None
-        v_scales = torch.empty_like(scales) if covars is None else None
+        v_covars = _grad_out(covars) if covars is not None else None
+        v_quats = _grad_out(quats) if covars is None else None
+        v_scales = _grad_out(scales) if covars is None else None
         v_viewmats = torch.zeros_like(viewmats) if ctx.needs_input_grad[4] else None
         if N:
             native("projection_bwd", lib, dev, C, N, _ptr(means), _ptr(covars), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks),

@@ -142,40 +142,115 @@ def test_garden_fixture_renders(golden):
     assert_image_close(got[1], ref[1], margin[..., None], what="garden alphas")
 
 
-def test_config_b_full_size_properties():
-    """1 M Gaussians, SH3, 1920x1080 (BASELINE config B): size-independent properties."""
-    scene = synthetic.to_device(synthetic.pinhole_scene(1_000_000, 1920, 1080, seed=42), DEV)
+def _full_size_properties(scene, W, H, camera_model="pinhole", packed=False, sparse_grad=False, min_isects=1_000_000):
+    """Size-independent properties of one full-size rasterization() + backward()."""
+    scene = synthetic.to_device(scene, DEV)
     P = [scene[k].clone().requires_grad_() for k in ("means", "quats", "scales", "opacities", "sh")]
-    rc, ra, m = S.rasterization(*P, scene["viewmats"], scene["Ks"], 1920, 1080, sh_degree=3, packed=False)
+    N = P[0].shape[0]
+    rc, ra, m = S.rasterization(*P, scene["viewmats"], scene["Ks"], W, H, sh_degree=3, packed=packed,
+                                sparse_grad=sparse_grad, camera_model=camera_model)
+    assert rc.shape == (1, H, W, 3) and ra.shape == (1, H, W, 1)
     assert torch.isfinite(rc).all() and torch.isfinite(ra).all()
     assert (ra >= 0).all() and (ra <= 1.0).all() and (rc >= -1e-6).all()
     ids, fl, offs = m["isect_ids"], m["flatten_ids"], m["isect_offsets"].flatten().long()
     n_isects = ids.numel()
-    assert n_isects == int(m["tiles_per_gauss"].sum()) and n_isects > 1_000_000
+    assert n_isects == int(m["tiles_per_gauss"].sum()) and n_isects > min_isects
     assert (ids[1:] >= ids[:-1]).all(), "isect_ids must be sorted"
     # stable: equal keys keep ascending flat index
     eq = ids[1:] == ids[:-1]
     assert (fl[1:][eq] > fl[:-1][eq]).all()
     assert (offs[1:] >= offs[:-1]).all() and offs[0] == 0 and offs[-1] <= n_isects
-    # offsets really are the first index of each tile
+    # the fused offsets equal the stand-alone operator's, and really are the first index of each tile
+    assert torch.equal(m["isect_offsets"], S.isect_offset_encode(ids, 1, m["tile_width"], m["tile_height"]))
     tile_of = (ids >> 32)
     k = torch.randint(0, offs.numel(), (2000,), device=DEV)
     start = offs[k]
     end = torch.where(k + 1 < offs.numel(), offs[(k + 1).clamp(max=offs.numel() - 1)], torch.full_like(start, n_isects))
     nz = end > start
     assert (tile_of[start[nz]] == k[nz]).all() and (tile_of[end[nz] - 1] == k[nz]).all()
-    # depth bits of every key equal the depth of the Gaussian it points to
+    # depth bits of every key equal the depth of the Gaussian row it points to
     assert torch.equal((ids & 0xFFFFFFFF).int(), m["depths"].flatten()[fl.long()].view(torch.int32))
-    # linearity in the colours for fixed geometry: render(a*c) = a*render(c)
-    rc2, _ = S.rasterize_to_pixels(m["means2d"].detach(), m["conics"].detach(),
-                                   torch.ones_like(m["means2d"][..., :1]).expand(-1, -1, 3).contiguous() * 0.5,
-                                   m["opacities"].detach(), 1920, 1080, 16, m["isect_offsets"], fl)
+    if packed:
+        gi, ci = m["gaussian_ids"], m["camera_ids"]
+        assert gi.dtype == torch.int64 and (gi[1:] > gi[:-1]).all() and (ci == 0).all()  # (camera, gaussian) order
+        assert (m["radii"] > 0).all()
+    # linearity in the colours for fixed geometry: render(0.5) = 0.5 * alpha
+    half = torch.full(m["means2d"].shape[:-1] + (3,), 0.5, device=DEV)
+    rc2, ra2 = S.rasterize_to_pixels(m["means2d"].detach(), m["conics"].detach(), half, m["opacities"].detach(),
+                                     W, H, 16, m["isect_offsets"], fl, packed=packed)
+    torch.testing.assert_close(ra2, ra.detach(), rtol=0, atol=0)  # same kernel, same inputs: deterministic forward
     torch.testing.assert_close(rc2, (ra * 0.5).expand(-1, -1, -1, 3), rtol=1e-4, atol=1e-5)
-    # gradients: finite, SH0 gradient equals C0 * d(colour) summed, opacity grads only on visible Gaussians
+    # gradients: finite, zero on invisible Gaussians, linear in the cotangent
     vc = torch.randn_like(rc)
-    g = torch.autograd.grad((rc * vc).sum() + ra.sum(), P)
-    for t in g:
-        assert torch.isfinite(t).all()
-    invisible = (m["radii"][0] == 0)
-    assert g[3][invisible].abs().max() == 0 and g[0][invisible].abs().max() == 0
-    assert (g[3].abs() > 0).float().mean() > 0.05
+    g1 = torch.autograd.grad((rc * vc).sum() + ra.sum(), P, retain_graph=True)
+    g2 = torch.autograd.grad((rc * (2 * vc)).sum() + (2 * ra).sum(), P)
+    visible = torch.zeros(N, dtype=torch.bool, device=DEV)
+    if packed:
+        visible[m["gaussian_ids"]] = True
+    else:
+        visible = m["radii"][0] > 0
+    for a, b in zip(g1, g2):
+        if a.is_sparse:
+            assert sparse_grad and a.values().shape[0] == m["gaussian_ids"].numel()
+            a, b = a.to_dense(), b.to_dense()
+        assert torch.isfinite(a).all()
+        if (~visible).any():
+            assert a[~visible].abs().max() == 0
+        scale = a.abs().max()
+        assert ((2 * a - b).abs().max() <= 2e-3 * scale), "gradient is not linear in the cotangent"
+    assert (g1[3].to_dense() if g1[3].is_sparse else g1[3]).abs().gt(0).float().mean() > 0.05
+    return m
+
+
+def test_config_b_full_size_properties():
+    """BASELINE config B: 1 M Gaussians, SH3, 1920x1080 pinhole."""
+    _full_size_properties(synthetic.pinhole_scene(1_000_000, 1920, 1080, seed=42), 1920, 1080)
+
+
+def test_config_c_per_rank_full_size_properties():
+    """BASELINE config C, one rank's share: 3 M Gaussians, one 1080p camera."""
+    _full_size_properties(synthetic.pinhole_scene(3_000_000, 1920, 1080, seed=43), 1920, 1080, min_isects=5_000_000)
+
+
+def test_config_d_spherical_full_size_properties():
+    """BASELINE config D: 2 M Gaussians, equirectangular 2048x1024 (the fork's camera model)."""
+    _full_size_properties(synthetic.spherical_scene(2_000_000, 2048, 1024, seed=44), 2048, 1024,
+                          camera_model="spherical")
+
+
+def test_config_e_packed_sparse_full_size_properties():
+    """BASELINE config E: 6 M Gaussians, 3840x2160, packed mode with sparse gradients."""
+    m = _full_size_properties(synthetic.pinhole_scene(6_000_000, 3840, 2160, seed=45), 3840, 2160, packed=True,
+                              sparse_grad=True, min_isects=10_000_000)
+    assert m["tile_width"] == 240 and m["tile_height"] == 135
+
+
+def test_gradient_sink_writes_parameter_grads_in_place():
+    """With a GradArena sink the backward kernels produce quats/scales/SH gradients inside the
+    flat all-reduce arena (no gather copy); values are identical to the plain path."""
+    from splat_one_b200.distributed import GradArena
+
+    scene = synthetic.to_device(synthetic.pinhole_scene(30000, 320, 240, seed=3, n_cameras=2), DEV)
+    names = ("means", "quats", "scales", "opacities", "sh")
+
+    def run(use_sink):
+        P = [scene[k].clone().requires_grad_() for k in names]
+        rc, ra, _ = S.rasterization(*P, scene["viewmats"], scene["Ks"], 320, 240, sh_degree=3, packed=False)
+        g = torch.Generator(device="cpu").manual_seed(1)
+        vc = torch.randn(rc.shape, generator=g).to(DEV)
+        arena = GradArena(P)
+        if use_sink:
+            with arena.sink():
+                torch.autograd.backward([rc, ra], [vc, torch.ones_like(ra)])
+        else:
+            torch.autograd.backward([rc, ra], [vc, torch.ones_like(ra)])
+        in_place = [p.grad.data_ptr() == v.data_ptr() for p, v in zip(P, arena.views)]
+        arena.gather_from_params()
+        return [p.grad.clone() for p in P], in_place, arena.flat.clone()
+
+    g0, in0, flat0 = run(False)
+    g1, in1, flat1 = run(True)
+    assert in0 == [False] * 5 and in1 == [False, True, True, False, True]
+    for n, a, b in zip(names, g0, g1):
+        assert_grad_close(b, a, rtol=1e-4, what=n)
+    assert_grad_close(flat1, flat0, rtol=1e-4, what="arena")
