@@ -175,6 +175,25 @@ B200SPLAT_API int b200splat_sh_colors_bwd(
     const float *colors, const float *v_colors,
     float *v_coeffs, float *v_means, void *stream);
 
+/* Packed (COO) variants of the fused colour stage (packed=True branch of G/rendering.py:
+ * 370-392: `means[gaussian_ids] - campos[camera_ids]`, `colors[gaussian_ids]`, SH, +0.5, clamp).
+ * Rows i = 0..nnz-1 name (camera_ids[i], gaussian_ids[i]) (int64, as the packed projection
+ * emits them).  colors [nnz,3].  bwd: v_coeffs ([N,K,3] or [C,N,K,3]) and v_means [N,3] (may be
+ * NULL) must be ZEROED by the caller; rows of invisible Gaussians stay zero, rows seen by
+ * several cameras are summed with atomics (direct stores when C == 1 or per_view). */
+B200SPLAT_API int b200splat_sh_colors_packed_fwd(
+    uint32_t nnz, uint32_t C, uint32_t N, uint32_t K, uint32_t degrees_to_use, int per_view,
+    const float *means, const float *campos, const float *coeffs,
+    const int64_t *camera_ids, const int64_t *gaussian_ids,
+    float *colors, void *stream);
+
+B200SPLAT_API int b200splat_sh_colors_packed_bwd(
+    uint32_t nnz, uint32_t C, uint32_t N, uint32_t K, uint32_t degrees_to_use, int per_view,
+    const float *means, const float *campos, const float *coeffs,
+    const int64_t *camera_ids, const int64_t *gaussian_ids,
+    const float *colors, const float *v_colors,
+    float *v_coeffs, float *v_means, void *stream);
+
 /* ------------------------------------------------------------------------------------
  * a6  isect_tiles                         CS/bindings.h:148-160, kernel
  *     CS/isect_tiles.cu:17-105, host :107-307.

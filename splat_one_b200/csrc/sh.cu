@@ -313,6 +313,105 @@ sh_colors_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, int per_v
     if (v_means != nullptr) { v_means[3 * n] = vmx; v_means[3 * n + 1] = vmy; v_means[3 * n + 2] = vmz; }
 }
 
+// Packed (COO) variants of the fused colour stage: one thread per visible (camera, Gaussian)
+// row; the row's Gaussian / camera come from gaussian_ids / camera_ids (int64, as the
+// reference's packed projection emits them).  This replaces, for packed=True, the chain
+// `means[gaussian_ids] - campos[camera_ids]`, `colors[gaussian_ids]` (a [nnz,K,3] gather copy),
+// spherical_harmonics, +0.5, clamp (G/rendering.py:370-392) and — in the backward — the
+// sort-based index_put of the gathered coefficient gradient.
+template <int NB>
+__global__ void __launch_bounds__(kThreads)
+sh_colors_packed_fwd_kernel(uint32_t nnz, uint32_t N, uint32_t K, uint32_t deg, int per_view,
+                            const float *__restrict__ means, const float *__restrict__ campos,
+                            const float *__restrict__ coeffs, const int64_t *__restrict__ camera_ids,
+                            const int64_t *__restrict__ gaussian_ids, float *__restrict__ colors) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnz) return;
+    const uint64_t n = (uint64_t)gaussian_ids[i], c = (uint64_t)camera_ids[i];
+    const float *row = coeffs + (per_view ? c * N + n : n) * K * 3;
+    float cf[NB * 3];
+    load_row<NB>(row, cf, ((K * 3) % 4 == 0) && ((reinterpret_cast<uintptr_t>(coeffs) & 15) == 0));
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (NB > 1) {
+        const float dx = __ldg(means + 3 * n) - campos[3 * c], dy = __ldg(means + 3 * n + 1) - campos[3 * c + 1],
+                    dz = __ldg(means + 3 * n + 2) - campos[3 * c + 2];
+        const float inorm = rsqrtf(dx * dx + dy * dy + dz * dz);
+        x = dx * inorm; y = dy * inorm; z = dz * inorm;
+    }
+    float r = 0.f, g = 0.f, b = 0.f;
+    sh_for_each_basis<false>(deg, x, y, z, [&](int k, float B, float, float, float) {
+        r += B * cf[3 * k]; g += B * cf[3 * k + 1]; b += B * cf[3 * k + 2];
+    });
+    colors[3 * (size_t)i] = fmaxf(r + 0.5f, 0.f);
+    colors[3 * (size_t)i + 1] = fmaxf(g + 0.5f, 0.f);
+    colors[3 * (size_t)i + 2] = fmaxf(b + 0.5f, 0.f);
+}
+
+// v_coeffs / v_means are ZERO-INITIALISED by the caller.  `unique` != 0: every destination row
+// is produced by at most one thread (one camera, or per-view tables) and is stored directly;
+// otherwise rows of one Gaussian seen by several cameras are summed with atomics.
+template <int NB>
+__global__ void __launch_bounds__(kThreads)
+sh_colors_packed_bwd_kernel(uint32_t nnz, uint32_t N, uint32_t K, uint32_t deg, int per_view, int unique,
+                            int means_unique, const float *__restrict__ means, const float *__restrict__ campos,
+                            const float *__restrict__ coeffs, const int64_t *__restrict__ camera_ids,
+                            const int64_t *__restrict__ gaussian_ids, const float *__restrict__ colors,
+                            const float *__restrict__ v_colors, float *__restrict__ v_coeffs,
+                            float *__restrict__ v_means) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnz) return;
+    const uint64_t n = (uint64_t)gaussian_ids[i], c = (uint64_t)camera_ids[i];
+    const uint64_t row_id = per_view ? c * N + n : n;
+    const bool vec_ok = ((K * 3) % 4 == 0) && ((reinterpret_cast<uintptr_t>(v_coeffs) & 15) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(coeffs) & 15) == 0);
+    const float vr = colors[3 * (size_t)i] > 0.f ? v_colors[3 * (size_t)i] : 0.f;
+    const float vg = colors[3 * (size_t)i + 1] > 0.f ? v_colors[3 * (size_t)i + 1] : 0.f;
+    const float vb = colors[3 * (size_t)i + 2] > 0.f ? v_colors[3 * (size_t)i + 2] : 0.f;
+    float x = 0.f, y = 0.f, z = 0.f, inorm = 0.f;
+    if (NB > 1) {
+        const float dx = __ldg(means + 3 * n) - campos[3 * c], dy = __ldg(means + 3 * n + 1) - campos[3 * c + 1],
+                    dz = __ldg(means + 3 * n + 2) - campos[3 * c + 2];
+        inorm = rsqrtf(dx * dx + dy * dy + dz * dz);
+        x = dx * inorm; y = dy * inorm; z = dz * inorm;
+    }
+    float vc[NB * 3];
+    if (v_means != nullptr && NB > 1) {
+        float cf[NB * 3];
+        load_row<NB>(coeffs + row_id * K * 3, cf, vec_ok);
+        float vx = 0.f, vy = 0.f, vz = 0.f;
+        sh_for_each_basis<true>(deg, x, y, z, [&](int k, float B, float Bx, float By, float Bz) {
+            vc[3 * k] = B * vr; vc[3 * k + 1] = B * vg; vc[3 * k + 2] = B * vb;
+            const float w = cf[3 * k] * vr + cf[3 * k + 1] * vg + cf[3 * k + 2] * vb;
+            vx += Bx * w; vy += By * w; vz += Bz * w;
+        });
+        const float d = vx * x + vy * y + vz * z;
+        const float mx = (vx - d * x) * inorm, my = (vy - d * y) * inorm, mz = (vz - d * z) * inorm;
+        if (means_unique) {
+            v_means[3 * n] = mx; v_means[3 * n + 1] = my; v_means[3 * n + 2] = mz;
+        } else {
+            atomicAdd(v_means + 3 * n, mx); atomicAdd(v_means + 3 * n + 1, my); atomicAdd(v_means + 3 * n + 2, mz);
+        }
+    } else {
+        sh_for_each_basis<false>(deg, x, y, z, [&](int k, float B, float, float, float) {
+            vc[3 * k] = B * vr; vc[3 * k + 1] = B * vg; vc[3 * k + 2] = B * vb;
+        });
+    }
+    float *vrow = v_coeffs + row_id * K * 3;
+    if (unique) {
+        if ((NB * 3) % 4 == 0 && vec_ok) {
+            float4 *o = reinterpret_cast<float4 *>(vrow);
+#pragma unroll
+            for (int k = 0; k < NB * 3 / 4; k++) o[k] = make_float4(vc[4 * k], vc[4 * k + 1], vc[4 * k + 2], vc[4 * k + 3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < NB * 3; k++) vrow[k] = vc[k];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < NB * 3; k++) atomicAdd(vrow + k, vc[k]);
+    }
+}
+
 }  // namespace b2s
 
 using namespace b2s;
@@ -406,6 +505,55 @@ extern "C" int b200splat_sh_colors_bwd(uint32_t C, uint32_t N, uint32_t K, uint3
         default: B2S_SHC(25); break;
     }
 #undef B2S_SHC
+    B2S_CHECK_LAUNCH(where);
+    return 0;
+}
+
+extern "C" int b200splat_sh_colors_packed_fwd(uint32_t nnz, uint32_t C, uint32_t N, uint32_t K, uint32_t deg,
+                                              int per_view, const float *means, const float *campos,
+                                              const float *coeffs, const int64_t *camera_ids,
+                                              const int64_t *gaussian_ids, float *colors, void *stream) {
+    const char *where = "b200splat_sh_colors_packed_fwd";
+    (void)C;
+    B2S_REQUIRE(deg <= 4, where, "degrees_to_use must be <= 4");
+    B2S_REQUIRE((deg + 1) * (deg + 1) <= K, where, "K too small for degrees_to_use");
+    if (nnz == 0) return 0;
+    const unsigned grid = div_up(nnz, kThreads);
+    cudaStream_t st = (cudaStream_t)stream;
+#define B2S_SHP(NB) sh_colors_packed_fwd_kernel<NB><<<grid, kThreads, 0, st>>>(nnz, N, K, deg, per_view, means, campos, coeffs, camera_ids, gaussian_ids, colors)
+    switch (deg) {
+        case 0: B2S_SHP(1); break;
+        case 1: B2S_SHP(4); break;
+        case 2: B2S_SHP(9); break;
+        case 3: B2S_SHP(16); break;
+        default: B2S_SHP(25); break;
+    }
+#undef B2S_SHP
+    B2S_CHECK_LAUNCH(where);
+    return 0;
+}
+
+extern "C" int b200splat_sh_colors_packed_bwd(uint32_t nnz, uint32_t C, uint32_t N, uint32_t K, uint32_t deg,
+                                              int per_view, const float *means, const float *campos,
+                                              const float *coeffs, const int64_t *camera_ids,
+                                              const int64_t *gaussian_ids, const float *colors,
+                                              const float *v_colors, float *v_coeffs, float *v_means, void *stream) {
+    const char *where = "b200splat_sh_colors_packed_bwd";
+    B2S_REQUIRE(deg <= 4, where, "degrees_to_use must be <= 4");
+    B2S_REQUIRE((deg + 1) * (deg + 1) <= K, where, "K too small for degrees_to_use");
+    if (nnz == 0) return 0;
+    const unsigned grid = div_up(nnz, kThreads);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int unique = (per_view || C == 1) ? 1 : 0, means_unique = (C == 1) ? 1 : 0;
+#define B2S_SHP(NB) sh_colors_packed_bwd_kernel<NB><<<grid, kThreads, 0, st>>>(nnz, N, K, deg, per_view, unique, means_unique, means, campos, coeffs, camera_ids, gaussian_ids, colors, v_colors, v_coeffs, v_means)
+    switch (deg) {
+        case 0: B2S_SHP(1); break;
+        case 1: B2S_SHP(4); break;
+        case 2: B2S_SHP(9); break;
+        case 3: B2S_SHP(16); break;
+        default: B2S_SHP(25); break;
+    }
+#undef B2S_SHP
     B2S_CHECK_LAUNCH(where);
     return 0;
 }

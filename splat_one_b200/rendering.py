@@ -22,6 +22,8 @@ from typing_extensions import Literal
 
 from .wrapper import (
     fully_fused_projection,
+    gather_rows,
+    sh_view_colors_packed,
     isect_tiles_and_offsets,
     rasterize_to_pixels,
     sh_view_colors,
@@ -108,10 +110,12 @@ def rasterization(
         eps2d=eps2d, packed=packed, near_plane=near_plane, far_plane=far_plane,
         radius_clip=radius_clip, sparse_grad=sparse_grad,
         calc_compensations=(rasterize_mode == "antialiased"), camera_model=camera_model,
+        # with SH colours `means` also receives a dense gradient from the view directions
+        _dense_means_grad=(sparse_grad and sh_degree is not None),
     )
     if packed:
         camera_ids, gaussian_ids, radii, means2d, depths, conics, compensations = proj_results
-        opacities = opacities[gaussian_ids]  # [nnz]
+        opacities = gather_rows(opacities, gaussian_ids)  # [nnz]
     else:
         radii, means2d, depths, conics, compensations = proj_results
         opacities = opacities[None].expand(C, -1)  # [C, N]; no copy when C == 1 (reference: .repeat)
@@ -133,11 +137,14 @@ def rasterization(
     # ---- colours (a5) -----------------------------------------------------------------
     if sh_degree is None:
         if packed:
-            colors = colors[gaussian_ids] if colors.dim() == 2 else colors[camera_ids, gaussian_ids]
+            colors = gather_rows(colors, gaussian_ids) if colors.dim() == 2 else colors[camera_ids, gaussian_ids]
         else:
             colors = colors.expand(C, -1, -1) if colors.dim() == 2 else colors
     else:
-        if packed or viewmats.requires_grad:
+        if packed and not viewmats.requires_grad:
+            # same maths, one fused kernel per direction over the COO rows
+            colors = sh_view_colors_packed(sh_degree, means, viewmats, colors, camera_ids, gaussian_ids)  # [nnz, 3]
+        elif viewmats.requires_grad:
             camtoworlds = torch.inverse(viewmats)  # [C, 4, 4]
             if packed:
                 dirs = means[gaussian_ids, :] - camtoworlds[camera_ids, :3, 3]  # [nnz, 3]

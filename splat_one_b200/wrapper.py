@@ -46,7 +46,7 @@ class _Profiler:
     KERNELS = {
         "projection_fwd": 1, "projection_bwd": 1, "projection_packed_count": 3, "projection_packed_fill": 1,
         "projection_packed_bwd": 1, "sh_fwd": 1, "sh_bwd": 1, "camera_centers": 1, "sh_colors_fwd": 1,
-        "sh_colors_bwd": 1, "isect_count": 2, "isect_fill": 1,
+        "sh_colors_bwd": 1, "sh_colors_packed_fwd": 1, "sh_colors_packed_bwd": 1, "isect_count": 2, "isect_fill": 1,
         "isect_sort": 0, "isect_sorted": 5, "isect_offset_encode": 1, "rasterize_pack": 1, "rasterize_fwd": 1, "rasterize_bwd": 1,
     }
 
@@ -321,6 +321,84 @@ class _ShViewColors(torch.autograd.Function):
         return None, v_means, None, (v_coeffs if ctx.needs_input_grad[3] else None), None
 
 
+def sh_view_colors_packed(sh_degree: int, means: Tensor, viewmats: Tensor, coeffs: Tensor, camera_ids: Tensor,
+                          gaussian_ids: Tensor) -> Tensor:
+    """The colour stage of `rasterization()` for the packed (COO) layout, fused:
+
+        dirs = means[gaussian_ids] - inverse(viewmats)[camera_ids, :3, 3]
+        shs = coeffs[gaussian_ids]            (or coeffs[camera_ids, gaussian_ids])
+        colors = clamp_min(spherical_harmonics(deg, dirs, shs) + 0.5, 0)
+
+    (G/rendering.py:370-392) -> colors [nnz,3], without the [nnz,K,3] gather copy and, in the
+    backward, without the sort-based index_put of its gradient.  Differentiable w.r.t. means
+    and coeffs."""
+    C, N = viewmats.shape[0], means.shape[0]
+    assert means.shape == (N, 3), means.shape
+    assert coeffs.shape[-1] == 3 and (coeffs.shape[:-2] == (N,) or coeffs.shape[:-2] == (C, N)), coeffs.shape
+    assert (sh_degree + 1) ** 2 <= coeffs.shape[-2], coeffs.shape
+    assert camera_ids.shape == gaussian_ids.shape and camera_ids.dim() == 1
+    campos = camera_centers(viewmats)
+    return _ShViewColorsPacked.apply(sh_degree, means.contiguous(), campos, coeffs.contiguous(),
+                                     camera_ids.contiguous(), gaussian_ids.contiguous())
+
+
+class _ShViewColorsPacked(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sh_degree, means, campos, coeffs, camera_ids, gaussian_ids):
+        _check_cuda(means, campos, coeffs, camera_ids, gaussian_ids)
+        _f32(means), _f32(coeffs)
+        if camera_ids.dtype != torch.int64 or gaussian_ids.dtype != torch.int64:
+            raise RuntimeError("b200splat: camera_ids / gaussian_ids must be int64")
+        lib = get_lib()
+        C, N, nnz = campos.shape[0], means.shape[0], gaussian_ids.shape[0]
+        K = coeffs.shape[-2]
+        per_view = int(coeffs.dim() == 4)
+        colors = torch.empty((nnz, 3), device=means.device, dtype=torch.float32)
+        if nnz:
+            native("sh_colors_packed_fwd", lib, means.device, nnz, C, N, K, sh_degree, per_view, _ptr(means),
+                   _ptr(campos), _ptr(coeffs), _ptr(camera_ids), _ptr(gaussian_ids), _ptr(colors))
+        ctx.save_for_backward(means, campos, coeffs, camera_ids, gaussian_ids, colors)
+        ctx.sh_degree = sh_degree
+        return colors
+
+    @staticmethod
+    def backward(ctx, v_colors):
+        means, campos, coeffs, camera_ids, gaussian_ids, colors = ctx.saved_tensors
+        lib = get_lib()
+        C, N, nnz = campos.shape[0], means.shape[0], gaussian_ids.shape[0]
+        K = coeffs.shape[-2]
+        per_view = int(coeffs.dim() == 4)
+        v_coeffs = torch.zeros_like(coeffs)
+        v_means = torch.zeros_like(means) if ctx.needs_input_grad[1] else None
+        if nnz:
+            native("sh_colors_packed_bwd", lib, means.device, nnz, C, N, K, ctx.sh_degree, per_view, _ptr(means),
+                   _ptr(campos), _ptr(coeffs), _ptr(camera_ids), _ptr(gaussian_ids), _ptr(colors),
+                   _ptr(v_colors.contiguous()), _ptr(v_coeffs), _ptr(v_means))
+        return None, v_means, None, (v_coeffs if ctx.needs_input_grad[3] else None), None, None
+
+
+class _GatherRows(torch.autograd.Function):
+    """`x[ids]` along dim 0 (the packed-mode gathers of G/rendering.py:327-329, 366) with an
+    atomic `index_add_` backward instead of autograd's sort-based index_put."""
+
+    @staticmethod
+    def forward(ctx, x, ids):
+        ctx.save_for_backward(ids)
+        ctx.n = x.shape[0]
+        return x.index_select(0, ids)
+
+    @staticmethod
+    def backward(ctx, v):
+        (ids,) = ctx.saved_tensors
+        out = torch.zeros((ctx.n,) + v.shape[1:], device=v.device, dtype=v.dtype)
+        out.index_add_(0, ids, v.contiguous())
+        return out, None
+
+
+def gather_rows(x: Tensor, ids: Tensor) -> Tensor:
+    return _GatherRows.apply(x, ids)
+
+
 # ----------------------------------------------------------------------------------------
 # projection (a2, a3, a4)
 # ----------------------------------------------------------------------------------------
@@ -341,8 +419,14 @@ def fully_fused_projection(
     sparse_grad: bool = False,
     calc_compensations: bool = False,
     camera_model: Literal["pinhole", "ortho", "fisheye", "spherical"] = "pinhole",
+    _dense_means_grad: bool = False,
 ) -> Tuple[Tensor, ...]:
     """Projects Gaussians to 2D (G/cuda/_wrapper.py:203-339).
+
+    `_dense_means_grad` (private, used by `rasterization()`): with sparse_grad, return the
+    gradient of `means` dense.  When `means` also feeds the view-dependent colours, autograd
+    has to add that dense gradient to this one anyway (and the reference's result is dense);
+    adding dense + sparse costs ~13 ms at 6 M Gaussians, dense + dense does not.
 
     packed=False: (radii [C,N] int32, means2d [C,N,2], depths [C,N], conics [C,N,3],
     compensations [C,N] | None).  packed=True: (camera_ids, gaussian_ids [nnz] int64, radii,
@@ -374,7 +458,7 @@ def fully_fused_projection(
     if packed:
         return _FullyFusedProjectionPacked.apply(
             means, covars, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
-            radius_clip, sparse_grad, calc_compensations, camera_model)
+            radius_clip, sparse_grad, calc_compensations, camera_model, _dense_means_grad)
     return _FullyFusedProjection.apply(
         means, covars, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
         radius_clip, calc_compensations, camera_model)
@@ -443,7 +527,7 @@ class _FullyFusedProjection(torch.autograd.Function):
 class _FullyFusedProjectionPacked(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means, covars, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
-                radius_clip, sparse_grad, calc_compensations, camera_model="pinhole"):
+                radius_clip, sparse_grad, calc_compensations, camera_model="pinhole", dense_means_grad=False):
         _check_cuda(means, covars, quats, scales, viewmats, Ks)
         for t in (means, covars, quats, scales, viewmats, Ks):
             _f32(t)
@@ -478,6 +562,7 @@ class _FullyFusedProjectionPacked(torch.autograd.Function):
                               compensations)
         ctx.width, ctx.height, ctx.eps2d = width, height, eps2d
         ctx.sparse_grad = sparse_grad
+        ctx.dense_means_grad = dense_means_grad
         ctx.camera_model = cm
         ctx.indptr = indptr
         ctx.mark_non_differentiable(camera_ids, gaussian_ids, radii)
@@ -516,12 +601,16 @@ class _FullyFusedProjectionPacked(torch.autograd.Function):
             return torch.sparse_coo_tensor(indices=gaussian_ids[None], values=values, size=like.size(),
                                            is_coalesced=len(viewmats) == 1)
 
-        return (_coo(v_means, means) if need[0] else None,
+        if sparse_grad and ctx.dense_means_grad and need[0]:
+            g_means = torch.zeros_like(means).index_add_(0, gaussian_ids, v_means)
+        else:
+            g_means = _coo(v_means, means) if need[0] else None
+        return (g_means,
                 _coo(v_covars, covars) if need[1] else None,
                 _coo(v_quats, quats) if need[2] else None,
                 _coo(v_scales, scales) if need[3] else None,
                 v_viewmats if need[4] else None,
-                None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None)
 
 
 # ----------------------------------------------------------------------------------------

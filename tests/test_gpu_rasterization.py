@@ -100,17 +100,25 @@ def test_rasterization_spherical_matches_oracle(packed):
         assert_grad_close(a, b, rtol=2e-3, what=f"spherical/{n}", frac_ok=0.995)
 
 
-def test_rasterization_antialiased_per_view_colors_absgrad():
+@pytest.mark.parametrize("packed", [False, True])
+def test_rasterization_antialiased_per_view_colors_absgrad(packed):
     scene = synthetic.pinhole_scene(4000, 160, 128, seed=9, n_cameras=3)
-    ref, got, P_c, P_g = _run_both(scene, False, True, "RGB", bg=False, rasterize_mode="antialiased", absgrad=True,
+    ref, got, P_c, P_g = _run_both(scene, packed, True, "RGB", bg=False, rasterize_mode="antialiased", absgrad=True,
                                    per_view_color=True)
     (rc_r, ra_r, m_r), (rc, ra, m) = ref, got
     margin = _margin_of(m_r, scene)
     assert_image_close(rc, rc_r, margin, what="colors")
+    g = torch.Generator().manual_seed(4)
+    keep = (margin >= 1e-3).float()[..., None]
+    vc = torch.randn(rc_r.shape, generator=g) * keep
+    g_ref = torch.autograd.grad((rc_r * vc).sum(), P_c)
     m["means2d"].retain_grad()
-    (rc.sum() + ra.sum()).backward()
-    assert m["means2d"].grad is not None and m["means2d"].grad.shape == (3, 4000, 2)
-    assert m["means2d"].absgrad.shape == (3, 4000, 2)
+    (rc * vc.to(DEV)).sum().backward()
+    for n, a, b in zip(["means", "quats", "scales", "opacities", "colors"], [p.grad for p in P_g], g_ref):
+        assert_grad_close(a, b, rtol=2e-3, what=f"per-view/{n}", frac_ok=0.995)
+    shape = (m["gaussian_ids"].numel(), 2) if packed else (3, 4000, 2)
+    assert m["means2d"].grad is not None and m["means2d"].grad.shape == shape
+    assert m["means2d"].absgrad.shape == shape
     assert (m["means2d"].absgrad >= m["means2d"].grad.abs() - 1e-4).all()
 
 
@@ -254,3 +262,30 @@ def test_gradient_sink_writes_parameter_grads_in_place():
     for n, a, b in zip(names, g0, g1):
         assert_grad_close(b, a, rtol=1e-4, what=n)
     assert_grad_close(flat1, flat0, rtol=1e-4, what="arena")
+
+
+@pytest.mark.parametrize("n_cameras", [1, 2])
+def test_rasterization_packed_sparse_grad_matches_oracle(n_cameras):
+    """packed=True, sparse_grad=True through rasterization(): quats / scales gradients are COO
+    tensors over gaussian_ids (G/cuda/_wrapper.py:1163-1203), means is dense (it also feeds the
+    SH view directions); values equal the oracle's dense gradients."""
+    scene = synthetic.pinhole_scene(5000, 176, 144, seed=11, n_cameras=n_cameras)
+    names = ["means", "quats", "scales", "opacities", "sh"]
+    P_c = [scene[k].clone().requires_grad_() for k in names]
+    P_g = [scene[k].to(DEV).requires_grad_() for k in names]
+    kw = dict(width=176, height=144, sh_degree=3, packed=True)
+    rc_r, ra_r, m_r = O.rasterization(*P_c, scene["viewmats"], scene["Ks"], raster_fn=RC.rasterize_to_pixels, **kw)
+    rc, ra, m = S.rasterization(*P_g, scene["viewmats"].to(DEV), scene["Ks"].to(DEV), sparse_grad=True, **kw)
+    margin = _margin_of(m_r, scene)
+    assert_image_close(rc, rc_r, margin, what="colors")
+    g = torch.Generator().manual_seed(4)
+    keep = (margin >= 1e-3).float()[..., None]
+    vc = torch.randn(rc_r.shape, generator=g) * keep
+    g_ref = torch.autograd.grad((rc_r * vc).sum() + (ra_r * keep).sum(), P_c)
+    g_got = torch.autograd.grad((rc * vc.to(DEV)).sum() + (ra * keep.to(DEV)).sum(), P_g)
+    assert not g_got[0].is_sparse and g_got[1].is_sparse and g_got[2].is_sparse
+    assert g_got[1].is_coalesced() == (n_cameras == 1)
+    assert torch.equal(g_got[1]._indices()[0], m["gaussian_ids"])
+    for n, a, b in zip(names, g_got, g_ref):
+        a = a.to_dense() if a.is_sparse else a
+        assert_grad_close(a, b, rtol=2e-3, what=f"sparse/{n}", frac_ok=0.995)
