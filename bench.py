@@ -208,7 +208,7 @@ def run_gpu(args):
 
     import splat_one_b200 as S
     from splat_one_b200 import synthetic, wrapper
-    from splat_one_b200.distributed import GradArena
+    from splat_one_b200.distributed import GradArena, camera_parallel
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -238,9 +238,13 @@ def run_gpu(args):
         for p in params:
             p.grad = None
         rc, ra, meta = S.rasterization(*params, vm, Ks, WIDTH, HEIGHT, sh_degree=SH_DEGREE, packed=False)
+        skip = ()
         if arena is not None:
-            with arena.sink():  # SH / quats / scales gradients are produced inside the arena
+            # SH / quats / scales gradients are produced inside the arena; the SH gradient comes
+            # out already summed over ranks (colour-cotangent all-gather, distributed.py)
+            with arena.sink(), camera_parallel() as cp:
                 torch.autograd.backward([rc, ra], [vc, va])
+            skip = cp.reduced_ptrs
         else:
             torch.autograd.backward([rc, ra], [vc, va])
         if arena is not None:
@@ -251,7 +255,7 @@ def run_gpu(args):
             arena.gather_from_params()
             if prof.enabled:
                 ev[1].record()
-            arena.all_reduce()
+            arena.all_reduce(skip_ptrs=skip)
             if prof.enabled:
                 ev[2].record()
                 prof.events.setdefault("grad_gather", []).append((ev[0], ev[1]))
@@ -327,10 +331,10 @@ def run_gpu(args):
         vc_d.record_stream(main)
         va_d.record_stream(main)
         if arena is not None:
-            with arena.sink():
+            with arena.sink(), camera_parallel() as cp:
                 torch.autograd.backward([rc_, ra_], [vc_d, va_d])
             arena.gather_from_params()
-            arena.all_reduce()
+            arena.all_reduce(skip_ptrs=cp.reduced_ptrs)
         else:
             torch.autograd.backward([rc_, ra_], [vc_d, va_d])
         gnorm_host.copy_(params[0].grad.norm().reshape(1), non_blocking=True)
@@ -403,7 +407,7 @@ def run_gpu(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "n_gaussians": N_GAUSS, "cameras_per_gpu": C_local,
                        "visible_pairs": V, "n_isects": I, "l2_policy": "per-step working set ~1 GB > 126 MB L2",
-                       "parallelism": f"camera-sharded dp{world}" + (" + NCCL allreduce of 236 MB grads" if world > 1 else "")},
+                       "parallelism": f"camera-sharded dp{world}" + (" + all-gather of colour cotangents (12 MB/rank) + NCCL allreduce of 44 MB grads" if world > 1 else "")},
             "clocks": clocks,
             "e2e": {"value": world * C_local * HEIGHT * WIDTH / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s",
                     "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

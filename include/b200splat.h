@@ -161,7 +161,12 @@ B200SPLAT_API int b200splat_sh_bwd(
  *  sh_colors_fwd : colors [C,N,3] (zeros where radii <= 0).  per_view != 0: coeffs is
  *                  [C,N,K,3], else one [N,K,3] table shared by the cameras.
  *  sh_colors_bwd : v_coeffs ([N,K,3] or [C,N,K,3]) and v_means [N,3] (may be NULL), both
- *                  fully overwritten; sums over cameras are done in registers. */
+ *                  fully overwritten; sums over cameras are done in registers.  Only cameras
+ *                  in [means_cam_begin, means_cam_end) contribute to v_means.  radii == NULL
+ *                  and colors == NULL: v_colors is pre-masked (zero for invisible Gaussians
+ *                  and clamped channels) — the form in which camera-parallel ranks exchange
+ *                  their colour cotangents instead of all-reducing the K-times larger
+ *                  coefficient gradient (splat_one_b200/distributed.py). */
 B200SPLAT_API int b200splat_camera_centers(uint32_t C, const float *viewmats, float *campos, void *stream);
 
 B200SPLAT_API int b200splat_sh_colors_fwd(
@@ -173,7 +178,8 @@ B200SPLAT_API int b200splat_sh_colors_bwd(
     uint32_t C, uint32_t N, uint32_t K, uint32_t degrees_to_use, int per_view,
     const float *means, const float *campos, const float *coeffs, const int32_t *radii,
     const float *colors, const float *v_colors,
-    float *v_coeffs, float *v_means, void *stream);
+    float *v_coeffs, float *v_means,
+    uint32_t means_cam_begin, uint32_t means_cam_end, void *stream);
 
 /* Packed (COO) variants of the fused colour stage (packed=True branch of G/rendering.py:
  * 370-392: `means[gaussian_ids] - campos[camera_ids]`, `colors[gaussian_ids]`, SH, +0.5, clamp).

@@ -249,7 +249,8 @@ __global__ void __launch_bounds__(kThreads)
 sh_colors_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, int per_view, const float *__restrict__ means,
                      const float *__restrict__ campos, const float *__restrict__ coeffs,
                      const int32_t *__restrict__ radii, const float *__restrict__ colors,
-                     const float *__restrict__ v_colors, float *__restrict__ v_coeffs, float *__restrict__ v_means) {
+                     const float *__restrict__ v_colors, float *__restrict__ v_coeffs, float *__restrict__ v_means,
+                     uint32_t means_cam_begin, uint32_t means_cam_end) {
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     const bool vec_ok = ((K * 3) % 4 == 0) && ((reinterpret_cast<uintptr_t>(v_coeffs) & 15) == 0);
@@ -273,17 +274,23 @@ sh_colors_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, int per_v
     };
     for (uint32_t c = 0; c < C; ++c) {
         const uint64_t e = (uint64_t)c * N + n;
-        if (radii[e] > 0) {
-            const float vr = colors[3 * e] > 0.f ? v_colors[3 * e] : 0.f;
-            const float vg = colors[3 * e + 1] > 0.f ? v_colors[3 * e + 1] : 0.f;
-            const float vb = colors[3 * e + 2] > 0.f ? v_colors[3 * e + 2] : 0.f;
+        // radii == NULL / colors == NULL: v_colors is PRE-MASKED (zero where the Gaussian is
+        // invisible or the colour was clamped) — the layout the camera-parallel exchange gathers
+        float vr = v_colors[3 * e], vg = v_colors[3 * e + 1], vb = v_colors[3 * e + 2];
+        if (colors != nullptr) {
+            vr = colors[3 * e] > 0.f ? vr : 0.f;
+            vg = colors[3 * e + 1] > 0.f ? vg : 0.f;
+            vb = colors[3 * e + 2] > 0.f ? vb : 0.f;
+        }
+        const bool visible = radii != nullptr ? (radii[e] > 0) : (vr != 0.f || vg != 0.f || vb != 0.f);
+        if (visible) {
             float x = 0.f, y = 0.f, z = 0.f, inorm = 0.f;
             if (NB > 1) {
                 const float dx = mx - campos[3 * c], dy = my - campos[3 * c + 1], dz = mz - campos[3 * c + 2];
                 inorm = rsqrtf(dx * dx + dy * dy + dz * dz);
                 x = dx * inorm; y = dy * inorm; z = dz * inorm;
             }
-            if (v_means != nullptr && NB > 1) {
+            if (v_means != nullptr && NB > 1 && c >= means_cam_begin && c < means_cam_end) {
                 // the row is read with 128-bit loads (12 per Gaussian at K = 16): a scalar load per
                 // coefficient touches 32 cache lines per warp instruction and is L1-wavefront bound
                 float cf[NB * 3];
@@ -489,14 +496,15 @@ extern "C" int b200splat_sh_colors_fwd(uint32_t C, uint32_t N, uint32_t K, uint3
 extern "C" int b200splat_sh_colors_bwd(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, int per_view,
                                        const float *means, const float *campos, const float *coeffs,
                                        const int32_t *radii, const float *colors, const float *v_colors,
-                                       float *v_coeffs, float *v_means, void *stream) {
+                                       float *v_coeffs, float *v_means, uint32_t means_cam_begin,
+                                       uint32_t means_cam_end, void *stream) {
     const char *where = "b200splat_sh_colors_bwd";
     B2S_REQUIRE(deg <= 4, where, "degrees_to_use must be <= 4");
     B2S_REQUIRE((deg + 1) * (deg + 1) <= K, where, "K too small for degrees_to_use");
     if (N == 0) return 0;
     const unsigned grid = div_up(N, kThreads);
     cudaStream_t st = (cudaStream_t)stream;
-#define B2S_SHC(NBV) sh_colors_bwd_kernel<NBV><<<grid, kThreads, 0, st>>>(C, N, K, deg, per_view, means, campos, coeffs, radii, colors, v_colors, v_coeffs, v_means)
+#define B2S_SHC(NBV) sh_colors_bwd_kernel<NBV><<<grid, kThreads, 0, st>>>(C, N, K, deg, per_view, means, campos, coeffs, radii, colors, v_colors, v_coeffs, v_means, means_cam_begin, means_cam_end)
     switch (deg) {
         case 0: B2S_SHC(1); break;
         case 1: B2S_SHC(4); break;

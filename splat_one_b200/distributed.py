@@ -18,6 +18,38 @@ import torch.distributed as dist
 from torch import Tensor
 
 
+class camera_parallel:
+    """Context manager for forward + backward of one camera-sharded step.
+
+    While active, the backward of the fused colour stage does not leave a per-rank SH
+    coefficient gradient to be all-reduced (3K floats per Gaussian, 81 % of the payload at
+    K = 16).  The coefficient gradient of one camera is the outer product of the SH basis at
+    that camera's view direction with the colour cotangent, so ranks ALL-GATHER their masked
+    colour cotangents (3 floats per Gaussian and camera) and camera centres, and every rank
+    sums the outer products over all cameras in one kernel: the SH gradient comes out of
+    `backward()` already global.  `reduced_ptrs` lists the parameters (by data_ptr) this
+    happened for; `GradArena.all_reduce(skip_ptrs=...)` then leaves them out."""
+
+    def __init__(self, group=None):
+        self.group = group if group is not None else dist.group.WORLD
+        self.reduced_ptrs = set()
+
+    def __enter__(self):
+        from . import wrapper
+
+        self._active = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+        if self._active:
+            wrapper._CAMERA_PARALLEL["group"] = self.group
+            wrapper._CAMERA_PARALLEL["reduced"] = self.reduced_ptrs
+        return self
+
+    def __exit__(self, *exc):
+        from . import wrapper
+
+        wrapper._CAMERA_PARALLEL.clear()
+        return False
+
+
 def shard_cameras(viewmats: Tensor, Ks: Tensor, rank: Optional[int] = None,
                   world_size: Optional[int] = None) -> Tuple[Tensor, Tensor, Tensor]:
     """Cameras owned by `rank`: indices rank, rank+W, ...  Returns (viewmats, Ks, global ids)."""
@@ -72,13 +104,32 @@ class GradArena:
             else:
                 v.copy_(g)
 
-    def all_reduce(self, group=None, average: bool = False, async_op: bool = False):
-        """SUM over ranks (optionally / world_size); a no-op outside a process group."""
+    def all_reduce(self, group=None, average: bool = False, async_op: bool = False, skip_ptrs=()):
+        """SUM over ranks (optionally / world_size); a no-op outside a process group.
+        Parameters whose data_ptr() is in `skip_ptrs` already hold a global gradient
+        (`camera_parallel`) and are left out: the arena is reduced as the maximal contiguous runs
+        of the remaining segments (one collective when the skipped parameter is the last one)."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return None
-        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        runs, start = [], None
+        for p, o in zip(self.params, self.offsets):
+            if p.data_ptr() in skip_ptrs:
+                if start is not None:
+                    runs.append((start, o))
+                    start = None
+            elif start is None:
+                start = o
+        if start is not None:
+            runs.append((start, self.flat.numel()))
+        work = None
+        for a, b in runs:
+            work = dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+            if average and not async_op:
+                self.flat[a:b].div_(dist.get_world_size(group))
         if average and not async_op:
-            self.flat.div_(dist.get_world_size(group))
+            for p, v in zip(self.params, self.views):
+                if p.data_ptr() in skip_ptrs:
+                    v.div_(dist.get_world_size(group))
         return work
 
     def scatter_to_params(self) -> None:

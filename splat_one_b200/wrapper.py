@@ -145,6 +145,11 @@ class gradient_sink:
         return False
 
 
+# camera-parallel mode (set by splat_one_b200.distributed.camera_parallel): process group + the
+# data_ptr()s of parameters whose gradient came out of the backward already summed over ranks
+_CAMERA_PARALLEL: dict = {}
+
+
 def _grad_out(like: Tensor) -> Tensor:
     """Destination for a gradient the kernel fully overwrites: the registered sink buffer of
     this parameter if there is one, else a fresh allocation."""
@@ -314,10 +319,28 @@ class _ShViewColors(torch.autograd.Function):
         per_view = int(coeffs.dim() == 4)
         v_coeffs = _grad_out(coeffs)
         v_means = torch.empty_like(means) if ctx.needs_input_grad[1] else None
-        if N:
+        v_colors = v_colors.contiguous()
+        cp = _CAMERA_PARALLEL.get("group", None) if _CAMERA_PARALLEL else None
+        if cp is not None and not per_view and N:
+            # camera-parallel exchange (splat_one_b200/distributed.py): the coefficient gradient
+            # of camera c is the outer product B(dir_c) x v_rgb_c, so ranks all-gather their masked
+            # colour cotangents (3 floats per Gaussian and camera) and every rank evaluates the
+            # sum over ALL cameras itself, instead of all-reducing 3K floats per Gaussian
+            import torch.distributed as dist
+
+            W, r = dist.get_world_size(cp), dist.get_rank(cp)
+            g_local = torch.where(colors > 0, v_colors, torch.zeros_like(v_colors))  # [C,N,3], zero where invisible
+            g_all = torch.empty((W * C, N, 3), device=means.device, dtype=torch.float32)
+            campos_all = torch.empty((W * C, 3), device=means.device, dtype=torch.float32)
+            dist.all_gather_into_tensor(g_all, g_local, group=cp)
+            dist.all_gather_into_tensor(campos_all, campos.contiguous(), group=cp)
+            native("sh_colors_bwd", lib, means.device, W * C, N, K, ctx.sh_degree, 0, _ptr(means), _ptr(campos_all),
+                   _ptr(coeffs), None, None, _ptr(g_all), _ptr(v_coeffs), _ptr(v_means), r * C, (r + 1) * C)
+            _CAMERA_PARALLEL["reduced"].add(coeffs.data_ptr())
+        elif N:
             native("sh_colors_bwd", lib, means.device, C, N, K, ctx.sh_degree, per_view, _ptr(means), _ptr(campos),
-                   _ptr(coeffs), _ptr(radii), _ptr(colors), _ptr(v_colors.contiguous()), _ptr(v_coeffs),
-                   _ptr(v_means))
+                   _ptr(coeffs), _ptr(radii), _ptr(colors), _ptr(v_colors), _ptr(v_coeffs),
+                   _ptr(v_means), 0, C)
         return None, v_means, None, (v_coeffs if ctx.needs_input_grad[3] else None), None
 
 

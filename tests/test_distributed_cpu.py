@@ -103,3 +103,55 @@ def test_grad_arena_layout_and_sparse_grads():
     assert arena.all_reduce() is None  # no process group: no-op
     arena.scatter_to_params()
     assert p[2].grad.data_ptr() == arena.views[2].data_ptr()
+
+
+def _worker_exchange(rank, world, port, out_dir):
+    """Identity behind `camera_parallel`: sum_r outer(B(dir_r), g_r) computed from all-gathered
+    colour cotangents == all-reduce of the per-rank SH coefficient gradients."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import torch_ref as O
+        from splat_one_b200.distributed import GradArena
+
+        torch.manual_seed(0)
+        Nn, K = 200, 16
+        means, table = torch.randn(Nn, 3), torch.randn(Nn, K, 3) * 0.3
+        campos = torch.randn(world, 3) * 3
+        vis = torch.rand(world, Nn) > 0.3
+        v = torch.randn(world, Nn, 3)
+
+        def colours(t, c):
+            col = O.spherical_harmonics(3, means - campos[c], t, vis[c])
+            return torch.where(vis[c][:, None], torch.clamp_min(col + 0.5, 0.0), torch.zeros_like(col))
+
+        # (a) what plain data parallelism does: local dense gradient, then all-reduce
+        t = table.clone().requires_grad_()
+        col = colours(t, rank)
+        (col * v[rank]).sum().backward()
+        other = torch.zeros(7, requires_grad=True)
+        other.grad = torch.full((7,), float(rank + 1))
+        arena = GradArena([other, t])
+        arena.gather_from_params()
+        dense = arena.views[1].clone()
+        dist.all_reduce(dense)
+        # (b) the exchange: all-gather the masked cotangents, evaluate every camera locally
+        g_local = torch.where(col.detach() > 0, v[rank], torch.zeros_like(v[rank]))
+        g_all = [torch.empty_like(g_local) for _ in range(world)]
+        dist.all_gather(g_all, g_local)
+        t2 = table.clone().requires_grad_()
+        tot = sum((O.spherical_harmonics(3, means - campos[c], t2, None) * g_all[c]).sum() for c in range(world))
+        tot.backward()
+        torch.testing.assert_close(t2.grad, dense, rtol=1e-4, atol=1e-5)
+        # the arena leaves an already-global segment alone and reduces the rest
+        arena.views[1].copy_(t2.grad)
+        arena.all_reduce(skip_ptrs={t.data_ptr()})
+        assert torch.equal(arena.views[1], t2.grad)
+        assert arena.views[0].tolist() == [float(sum(range(1, world + 1)))] * 7
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_colour_cotangent_exchange_equals_gradient_allreduce(tmp_path):
+    mp.spawn(_worker_exchange, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)

@@ -463,3 +463,37 @@ def test_sh_view_colors_fused(per_view, deg):
     g_got = torch.autograd.grad((got * v.to(DEV)).sum(), (m_g, t_g))
     torch.testing.assert_close(g_got[0].cpu(), g_ref[0], rtol=1e-3, atol=1e-4)
     torch.testing.assert_close(g_got[1].cpu(), g_ref[1], rtol=1e-4, atol=1e-4)
+
+
+def test_sh_colors_bwd_premasked_camera_exchange():
+    """The camera-parallel exchange form of the fused colour backward: pre-masked colour
+    cotangents of ALL cameras in, coefficient gradient summed over all of them out, means
+    gradient only from the local camera range (splat_one_b200/distributed.py)."""
+    from splat_one_b200 import wrapper
+    from splat_one_b200._lib import get_lib
+    from splat_one_b200.wrapper import _ptr, camera_centers, native, sh_view_colors
+
+    torch.manual_seed(0)
+    C, N, K, deg = 3, 3000, 16, 3
+    means = torch.randn(N, 3, device=DEV)
+    vm = _cams(C).to(DEV)
+    table = (torch.randn(N, K, 3) * 0.4).to(DEV)
+    radii = ((torch.rand(C, N) > 0.25).int() * 5).to(DEV)
+    v = torch.randn(C, N, 3, device=DEV)
+    # reference: the ordinary fused path over all C cameras (coefficients) and over camera 1 only (means)
+    m_all, t_all = means.clone().requires_grad_(), table.clone().requires_grad_()
+    col = sh_view_colors(deg, m_all, vm, t_all, radii)
+    g_all = torch.autograd.grad((col * v).sum(), (m_all, t_all))
+    m_1 = means.clone().requires_grad_()
+    col1 = sh_view_colors(deg, m_1, vm[1:2], table, radii[1:2])
+    g_m1 = torch.autograd.grad((col1 * v[1:2]).sum(), m_1)[0]
+    # exchange form: what rank 1 of 3 would run after the all-gather
+    g_masked = torch.where(col.detach() > 0, v, torch.zeros_like(v)).contiguous()
+    v_coeffs = torch.empty_like(table)
+    v_means = torch.empty_like(means)
+    campos = camera_centers(vm)
+    native("sh_colors_bwd", get_lib(), means.device, C, N, K, deg, 0, _ptr(means), _ptr(campos), _ptr(table), None, None,
+           _ptr(g_masked), _ptr(v_coeffs), _ptr(v_means), 1, 2)
+    torch.testing.assert_close(v_coeffs, g_all[1], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(v_means, g_m1, rtol=1e-4, atol=1e-6)
+    assert wrapper._CAMERA_PARALLEL == {}
