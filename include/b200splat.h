@@ -320,6 +320,81 @@ B200SPLAT_API int b200splat_rasterize_bwd(
     float *v_opacities,
     void *stream);
 
+/* ------------------------------------------------------------------------------------
+ * f1  rasterize_to_indices_in_range      CS/bindings.h (rasterize_to_indices_in_range_tensor),
+ *     kernel + host CS/rasterize_to_indices_in_range.cu:17-307; Python
+ *     gsplat/cuda/_wrapper.py:571-643.
+ * Lists, per pixel in (camera, row, column) order and front to back, the Gaussians of the
+ * list batches [range_start, range_end) (a batch = tile_size^2 entries of the tile's list)
+ * that pass the alpha test before the pixel's transmittance (starting from
+ * `transmittances` [C,H,W]) would drop to <= 1e-4.  Two-phase: `_count` writes per-pixel
+ * counts `chunk_cnts` [C*H*W] int32, their inclusive prefix sums `chunk_cum` [C*H*W]
+ * int64 and the total `*n_elems_out` (device); the host reads the total, allocates
+ * `gaussian_ids` / `pixel_ids` [n_elems] int64 and calls `_fill` with the same arguments.
+ * pixel_ids are global: camera * H * W + row * W + column; gaussian_ids are in [0, N).
+ * ---------------------------------------------------------------------------------- */
+B200SPLAT_API int b200splat_raster_indices_count(
+    uint32_t range_start, uint32_t range_end, uint32_t C, uint32_t N, uint64_t n_isects,
+    const float *means2d, const float *conics, const float *opacities,
+    uint32_t image_width, uint32_t image_height,
+    uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+    const int32_t *tile_offsets, const int32_t *flatten_ids, const float *transmittances,
+    int32_t *chunk_cnts, int64_t *chunk_cum, int64_t *n_elems_out,
+    void *scan_workspace, size_t scan_workspace_bytes, void *stream);
+
+B200SPLAT_API int b200splat_raster_indices_fill(
+    uint32_t range_start, uint32_t range_end, uint32_t C, uint32_t N, uint64_t n_isects,
+    const float *means2d, const float *conics, const float *opacities,
+    uint32_t image_width, uint32_t image_height,
+    uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+    const int32_t *tile_offsets, const int32_t *flatten_ids, const float *transmittances,
+    const int32_t *chunk_cnts, const int64_t *chunk_cum,
+    int64_t *gaussian_ids, int64_t *pixel_ids, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * f2  the un-fused exported operators of the projection chain (gsplat/cuda/_wrapper.py:76-200).
+ *
+ * quat_scale_to_covar_preci_fwd/bwd   CS/bindings.h (quat_scale_to_covar_preci_*_tensor),
+ *     kernels CS/quat_scale_to_covar_preci_{fwd,bwd}.cu.  quats [N,4] (wxyz, un-normalised,
+ *     16-byte aligned), scales [N,3]; covars / precis: [N,6] upper triangle if triu else
+ *     [N,3,3]; either may be NULL (not computed / no cotangent).
+ * world_to_cam_fwd/bwd                CS/world_to_cam_{fwd,bwd}.cu.  means [N,3], covars
+ *     [N,3,3], viewmats [C,4,4] -> means_c [C,N,3], covars_c [C,N,3,3].  bwd: v_means /
+ *     v_covars are fully overwritten (no zero-init needed); v_viewmats [C,4,4] is
+ *     accumulated with atomics and must be zeroed by the caller; any of the three may be
+ *     NULL, and so may either cotangent.
+ * proj_fwd/bwd                        CS/proj_{fwd,bwd}.cu.  means [C,N,3], covars [C,N,3,3],
+ *     Ks [C,3,3] -> means2d [C,N,2], covars2d [C,N,2,2] for the given camera model.
+ * ---------------------------------------------------------------------------------- */
+B200SPLAT_API int b200splat_quat_scale_to_covar_preci_fwd(
+    uint32_t N, const float *quats, const float *scales, int triu,
+    float *covars, float *precis, void *stream);
+
+B200SPLAT_API int b200splat_quat_scale_to_covar_preci_bwd(
+    uint32_t N, const float *quats, const float *scales,
+    const float *v_covars, const float *v_precis, int triu,
+    float *v_quats, float *v_scales, void *stream);
+
+B200SPLAT_API int b200splat_world_to_cam_fwd(
+    uint32_t C, uint32_t N, const float *means, const float *covars, const float *viewmats,
+    float *means_c, float *covars_c, void *stream);
+
+B200SPLAT_API int b200splat_world_to_cam_bwd(
+    uint32_t C, uint32_t N, const float *means, const float *covars, const float *viewmats,
+    const float *v_means_c, const float *v_covars_c,
+    float *v_means, float *v_covars, float *v_viewmats, void *stream);
+
+B200SPLAT_API int b200splat_proj_fwd(
+    uint32_t C, uint32_t N, const float *means, const float *covars, const float *Ks,
+    uint32_t image_width, uint32_t image_height, int camera_model,
+    float *means2d, float *covars2d, void *stream);
+
+B200SPLAT_API int b200splat_proj_bwd(
+    uint32_t C, uint32_t N, const float *means, const float *covars, const float *Ks,
+    uint32_t image_width, uint32_t image_height, int camera_model,
+    const float *v_means2d, const float *v_covars2d,
+    float *v_means, float *v_covars, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

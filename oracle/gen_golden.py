@@ -153,6 +153,109 @@ def pipeline_oracle():
         v_sh=grads[4], source="oracle/torch_ref.py::rasterization (THIS repo's oracle, regression only)")
 
 
+def unfused():
+    """quat_scale_to_covar_preci / world_to_cam / proj from the reference's _torch_impl
+    (:41-68, :276-298, :71-222) with autograd gradients for fixed cotangents."""
+    torch.manual_seed(11)
+    C, N, W, H = 2, 300, 320, 240
+    quats = torch.randn(N, 4)
+    scales = torch.rand(N, 3) * 0.2 + 0.02
+    means = torch.rand(N, 3) * 2 - 1
+    means[:, 2] += 3.0
+    viewmats = torch.eye(4).expand(C, -1, -1).contiguous().clone()
+    viewmats[1, :3, :3] = torch.tensor([[0.98, 0.0, 0.199], [0.0, 1.0, 0.0], [-0.199, 0.0, 0.98]])
+    viewmats[1, :3, 3] = torch.tensor([0.1, -0.05, 0.2])
+    Ks = torch.tensor([[300.0, 0.0, 160.0], [0.0, 280.0, 120.0], [0.0, 0.0, 1.0]]).expand(C, -1, -1).contiguous()
+    g = torch.Generator().manual_seed(5)
+    out = dict(quats=quats, scales=scales, means=means, viewmats=viewmats, Ks=Ks, width=W, height=H)
+    for triu in (False, True):
+        q, sc = quats.clone().requires_grad_(), scales.clone().requires_grad_()
+        cov, pre = R._quat_scale_to_covar_preci(q, sc, True, True, triu)
+        vc, vp = torch.randn(cov.shape, generator=g), torch.randn(pre.shape, generator=g) * 1e-3
+        gq, gs = torch.autograd.grad((cov * vc).sum() + (pre * vp).sum(), (q, sc))
+        t = "triu" if triu else "full"
+        out.update({f"ref_covars_{t}": cov, f"ref_precis_{t}": pre, f"v_covars_{t}": vc, f"v_precis_{t}": vp,
+                    f"ref_v_quats_{t}": gq, f"ref_v_scales_{t}": gs})
+    covars = R._quat_scale_to_covar_preci(quats, scales, True, False, False)[0].detach()
+    m, cv, vm = means.clone().requires_grad_(), covars.clone().requires_grad_(), viewmats.clone().requires_grad_()
+    mc, cc = R._world_to_cam(m, cv, vm)
+    v_mc, v_cc = torch.randn(mc.shape, generator=g), torch.randn(cc.shape, generator=g)
+    gm, gc, gv = torch.autograd.grad((mc * v_mc).sum() + (cc * v_cc).sum(), (m, cv, vm))
+    out.update(covars=covars, ref_means_c=mc, ref_covars_c=cc, v_means_c=v_mc, v_covars_c=v_cc, ref_w2c_v_means=gm,
+               ref_w2c_v_covars=gc, ref_w2c_v_viewmats=gv)
+    mc, cc = mc.detach(), cc.detach()
+    v_m2, v_c2 = torch.randn(C, N, 2, generator=g), torch.randn(C, N, 2, 2, generator=g)
+    out.update(v_means2d=v_m2, v_covars2d=v_c2)
+    for cm, fn in (("pinhole", R._persp_proj), ("ortho", R._ortho_proj), ("fisheye", R._fisheye_proj)):
+        a, b = mc.clone().requires_grad_(), cc.clone().requires_grad_()
+        m2, c2 = fn(a, b, Ks, W, H)
+        ga, gb = torch.autograd.grad((m2 * v_m2).sum() + (c2 * v_c2).sum(), (a, b))
+        out.update({f"ref_means2d_{cm}": m2, f"ref_covars2d_{cm}": c2, f"ref_proj_v_means_{cm}": ga,
+                    f"ref_proj_v_covars_{cm}": gb})
+    npz("unfused_ref.npz", **out,
+        source="gsplat/cuda/_torch_impl.py::_quat_scale_to_covar_preci/_world_to_cam/_persp_proj/_ortho_proj/"
+               "_fisheye_proj (reference, CPU, autograd gradients)")
+
+
+def raster_ref():
+    """rasterize_to_pixels forward + gradients from the reference's OWN pure-PyTorch
+    compositing: `_rasterize_to_pixels` (_torch_impl.py:575-670) and `accumulate` (:485-572)
+    run unmodified on the CPU.  Their two external needs are supplied by this repo's oracle:
+    `nerfacc` (third-party, not vendored) by oracle/nerfacc_stub.py, and the CUDA-only
+    `rasterize_to_indices_in_range` by oracle/torch_ref.py's restatement of
+    CS/rasterize_to_indices_in_range.cu.  The arithmetic of alpha, weights, colours, alphas,
+    background blend and all gradients (autograd) is the reference's own code."""
+    import types
+
+    from oracle import nerfacc_stub
+
+    sys.modules["nerfacc"] = nerfacc_stub
+    import gsplat.cuda._wrapper as RW
+
+    RW.rasterize_to_indices_in_range = O.rasterize_to_indices_in_range
+    torch.manual_seed(42)
+    C, N, W, H, ts = 2, 400, 56, 40, 16
+    means = torch.rand(N, 3) * 2 - 1
+    means[:, 2] = means[:, 2] * 1.5 + 3.5
+    quats = torch.randn(N, 4)
+    scales = torch.rand(N, 3) * 0.25 + 0.03
+    Ks = torch.tensor([[60.0, 0.0, 28.0], [0.0, 60.0, 20.0], [0.0, 0.0, 1.0]]).expand(C, -1, -1).contiguous()
+    viewmats = torch.eye(4).expand(C, -1, -1).contiguous().clone()
+    viewmats[1, :3, 3] = torch.tensor([0.15, -0.1, 0.3])
+    covars, _ = R._quat_scale_to_covar_preci(quats, scales, True, False)
+    radii, m2, dep, con, _ = R._fully_fused_projection(means, covars, viewmats, Ks, W, H)
+    m2, con = torch.nan_to_num(m2), torch.nan_to_num(con)
+    tw, th = math.ceil(W / ts), math.ceil(H / ts)
+    tpg, ids, fl = R._isect_tiles(m2, radii, dep, ts, tw, th, sort=False)
+    order = torch.sort(ids, stable=True).indices
+    ids, fl = ids[order], fl[order]
+    offs = R._isect_offset_encode(ids, C, tw, th)
+    g = torch.Generator().manual_seed(9)
+    opac = torch.rand(C, N, generator=g) * 0.9 + 0.05
+    for D in (3, 1):
+        colors = torch.rand(C, N, D, generator=g)
+        bg = torch.rand(C, D, generator=g)
+        P = [t.clone().requires_grad_() for t in (m2, con, colors, opac, bg)]
+        rc, ra = R._rasterize_to_pixels(P[0], P[1], P[2], P[3], W, H, ts, offs, fl, backgrounds=P[4])
+        vc, va = torch.randn(rc.shape, generator=g), torch.randn(ra.shape, generator=g)
+        grads = torch.autograd.grad((rc * vc).sum() + (ra * va).sum(), P)
+        # decision margins of the index pass (same thresholds as the fused kernel)
+        *_, margin = O.rasterize_to_indices_in_range(0, 10**9, torch.ones(C, H, W), m2, con, opac, W, H, ts, offs, fl,
+                                                      return_margin=True)
+        gi, pi, ci = O.rasterize_to_indices_in_range(0, 10**9, torch.ones(C, H, W), m2, con, opac, W, H, ts, offs, fl)
+        npz(f"raster_ref_d{D}.npz", means2d=m2, conics=con, colors=colors, opacities=opac, backgrounds=bg,
+            width=W, height=H, tile_size=ts, isect_offsets=offs, flatten_ids=fl, v_render_colors=vc,
+            v_render_alphas=va, ref_render_colors=rc, ref_render_alphas=ra, ref_v_means2d=grads[0],
+            ref_v_conics=grads[1], ref_v_colors=grads[2], ref_v_opacities=grads[3], ref_v_backgrounds=grads[4],
+            margin=margin, idx_gaussian_ids=gi, idx_pixel_ids=pi, idx_camera_ids=ci,
+            source="gsplat/cuda/_torch_impl.py::_rasterize_to_pixels + accumulate (reference, CPU) with "
+                   "oracle/nerfacc_stub.py and oracle rasterize_to_indices_in_range; idx_* from the oracle")
+        # the oracle's fused restatements must agree with the reference's compositing
+        o_c, o_a = O.rasterize_to_pixels(m2, con, colors, opac, W, H, ts, offs, fl, backgrounds=bg)
+        print(f"  D={D}: oracle vs reference max|dC|={(o_c - rc).abs().max():.2e} max|dA|={(o_a - ra).abs().max():.2e} "
+              f"M={gi.numel()} min margin={margin.min():.2e}")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     projection()
@@ -160,3 +263,5 @@ if __name__ == "__main__":
     isect()
     garden()
     pipeline_oracle()
+    unfused()
+    raster_ref()

@@ -502,6 +502,142 @@ def rasterize_to_pixels(means2d, conics, colors, opacities, image_width, image_h
 
 
 # ----------------------------------------------------------------------------------------
+# f1: rasterize_to_indices_in_range + accumulate
+# ----------------------------------------------------------------------------------------
+@torch.no_grad()
+def rasterize_to_indices_in_range(range_start, range_end, transmittances, means2d, conics, opacities,
+                                  image_width, image_height, tile_size, isect_offsets, flatten_ids,
+                                  return_margin=False):
+    """Restatement of CS/rasterize_to_indices_in_range.cu:17-177 (+ Python
+    G/cuda/_wrapper.py:571-643), vectorised per tile: batches [range_start, range_end) of
+    tile_size² list entries; a pair is listed iff sigma >= 0 and alpha >= 1/255 and no
+    earlier listed-or-stopping pair brought T·(1-alpha) to <= 1e-4 (exclusive stop); T starts
+    from `transmittances` and is multiplied sequentially in fp32 (cumprod with the start
+    value prepended has the kernel's multiplication order).  Output grouped by pixel in
+    (camera, row, column) order.  `return_margin`: also per pixel the smallest relative
+    distance of any decision to its threshold (pixels below ~1e-3 may legitimately differ
+    between two fp32 implementations)."""
+    C, N = means2d.shape[:2]
+    th, tw = isect_offsets.shape[1:3]
+    n_isects = flatten_ids.numel()
+    H, W = image_height, image_width
+    m2, cn, op = means2d.reshape(-1, 2), conics.reshape(-1, 3), opacities.reshape(-1)
+    offs = torch.cat([isect_offsets.flatten().long(), torch.tensor([n_isects])])
+    bs = tile_size * tile_size
+    per_pixel = [[None] * (H * W) for _ in range(C)]
+    margin = torch.full((C, H, W), float("inf"))
+    for c in range(C):
+        for ty in range(th):
+            for tx in range(tw):
+                t_lin = (c * th + ty) * tw + tx
+                s, e = int(offs[t_lin]), int(offs[t_lin + 1])
+                nb = (e - s + bs - 1) // bs
+                if range_start >= nb:
+                    continue
+                lo, hi = s + bs * range_start, min(e, s + bs * min(range_end, nb))
+                y0, x0 = ty * tile_size, tx * tile_size
+                y1, x1 = min(y0 + tile_size, H), min(x0 + tile_size, W)
+                if y1 <= y0 or x1 <= x0 or hi <= lo:
+                    continue
+                ys = torch.arange(y0, y1, dtype=m2.dtype) + 0.5
+                xs = torch.arange(x0, x1, dtype=m2.dtype) + 0.5
+                py, px = torch.meshgrid(ys, xs, indexing="ij")
+                py, px = py.reshape(-1, 1), px.reshape(-1, 1)
+                g = flatten_ids[lo:hi].long()
+                dx = m2[g, 0][None, :] - px
+                dy = m2[g, 1][None, :] - py
+                ca, cb, cc = cn[g, 0][None, :], cn[g, 1][None, :], cn[g, 2][None, :]
+                sigma = 0.5 * (ca * dx * dx + cc * dy * dy) + cb * dx * dy
+                raw = op[g][None, :] * torch.exp(-sigma)
+                alpha = torch.clamp(raw, max=ALPHA_MAX)
+                valid = (sigma >= 0) & (alpha >= ALPHA_MIN)
+                one_m = torch.where(valid, 1.0 - alpha, torch.ones_like(alpha))
+                T0 = transmittances[c, y0:y1, x0:x1].reshape(-1, 1).to(m2.dtype)
+                T_incl = torch.cumprod(torch.cat([T0, one_m], dim=1), dim=1)[:, 1:]
+                stop = valid & (T_incl <= T_EPS)
+                alive = torch.cumsum(stop.int(), dim=1) == 0
+                listed = valid & alive
+                if return_margin:
+                    seen = torch.cat([torch.ones_like(alive[:, :1]), alive[:, :-1]], dim=1)  # evaluated at all
+                    big = torch.full_like(sigma, float("inf"))
+                    m_a = torch.where(seen & (sigma >= 0), (raw - ALPHA_MIN).abs() / ALPHA_MIN, big)
+                    m_t = torch.where(seen & valid, (T_incl - T_EPS).abs() / T_EPS, big)
+                    mg = torch.minimum(m_a, m_t).min(dim=1).values
+                    margin[c, y0:y1, x0:x1] = mg.reshape(y1 - y0, x1 - x0)
+                gn = (g % N)
+                k = 0
+                for yy in range(y0, y1):
+                    for xx in range(x0, x1):
+                        per_pixel[c][yy * W + xx] = gn[listed[k]]
+                        k += 1
+    gs, ps, cs = [], [], []
+    for c in range(C):
+        for p, lst in enumerate(per_pixel[c]):
+            if lst is not None and lst.numel():
+                gs.append(lst)
+                ps.append(torch.full_like(lst, p))
+                cs.append(torch.full_like(lst, c))
+    cat = lambda xs: torch.cat(xs) if xs else torch.zeros((0,), dtype=torch.int64)
+    out = (cat(gs), cat(ps), cat(cs))
+    return out + (margin,) if return_margin else out
+
+
+def accumulate(means2d, conics, opacities, colors, gaussian_ids, pixel_ids, camera_ids, image_width,
+               image_height):
+    """Restatement of G/cuda/_torch_impl.py:485-572 with the two nerfacc calls written out
+    (oracle/nerfacc_stub.py).  Differentiable."""
+    from . import nerfacc_stub as NA
+
+    C = means2d.shape[0]
+    channels = colors.shape[-1]
+    pc = torch.stack([pixel_ids % image_width, pixel_ids // image_width], dim=-1) + 0.5
+    deltas = pc - means2d[camera_ids, gaussian_ids]
+    c = conics[camera_ids, gaussian_ids]
+    sigmas = 0.5 * (c[:, 0] * deltas[:, 0] ** 2 + c[:, 2] * deltas[:, 1] ** 2) + c[:, 1] * deltas[:, 0] * deltas[:, 1]
+    alphas = torch.clamp_max(opacities[camera_ids, gaussian_ids] * torch.exp(-sigmas), 0.999)
+    indices = camera_ids * image_height * image_width + pixel_ids
+    total = C * image_height * image_width
+    weights, _ = NA.render_weight_from_alpha(alphas, ray_indices=indices, n_rays=total)
+    renders = NA.accumulate_along_rays(weights, colors[camera_ids, gaussian_ids], ray_indices=indices, n_rays=total)
+    accs = NA.accumulate_along_rays(weights, None, ray_indices=indices, n_rays=total)
+    return renders.reshape(C, image_height, image_width, channels), accs.reshape(C, image_height, image_width, 1)
+
+
+# ----------------------------------------------------------------------------------------
+# f2: un-fused projection chain
+# ----------------------------------------------------------------------------------------
+_TRIU = ([0, 0, 0, 1, 1, 2], [0, 1, 2, 1, 2, 2])
+
+
+def quat_scale_to_covar_preci(quats, scales, compute_covar=True, compute_preci=True, triu=False):
+    """CS/utils.cuh:66-97 (G/cuda/_torch_impl.py::_quat_scale_to_covar_preci)."""
+    R = quat_to_rotmat(quats)
+    covars = precis = None
+    if compute_covar:
+        M = R * scales[..., None, :]
+        covars = M @ M.transpose(-1, -2)
+        if triu:
+            covars = covars[..., _TRIU[0], _TRIU[1]]
+    if compute_preci:
+        P = R * (1.0 / scales[..., None, :])
+        precis = P @ P.transpose(-1, -2)
+        if triu:
+            precis = precis[..., _TRIU[0], _TRIU[1]]
+    return covars, precis
+
+
+def proj(means_c, covars_c, Ks, width, height, camera_model="pinhole"):
+    """CS/proj_fwd.cu:18-83: camera-space means/covariances -> (means2d, covars2d)."""
+    if camera_model == "pinhole":
+        return persp_proj(means_c, covars_c, Ks, width, height)
+    if camera_model == "ortho":
+        return ortho_proj(means_c, covars_c, Ks, width, height)
+    if camera_model == "fisheye":
+        return fisheye_proj(means_c, covars_c, Ks, width, height)
+    return spherical_proj(means_c, covars_c, width, height)
+
+
+# ----------------------------------------------------------------------------------------
 # a1: the whole pipeline (G/rendering.py:28-582), CPU
 # ----------------------------------------------------------------------------------------
 def rasterization(means, quats, scales, opacities, colors, viewmats, Ks, width, height,

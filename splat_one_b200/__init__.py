@@ -10,10 +10,16 @@ there is no CPU / PyTorch fallback.
 """
 from .rendering import rasterization
 from .wrapper import (
+    accumulate,
     fully_fused_projection,
     isect_offset_encode,
     isect_tiles,
+    persp_proj,
+    proj,
+    quat_scale_to_covar_preci,
+    rasterize_to_indices_in_range,
     rasterize_to_pixels,
+    world_to_cam,
     spherical_harmonics,
     spherical_harmonics_table,
 )
@@ -26,6 +32,12 @@ __all__ = [
     "isect_tiles",
     "isect_offset_encode",
     "rasterize_to_pixels",
+    "rasterize_to_indices_in_range",
+    "accumulate",
+    "quat_scale_to_covar_preci",
+    "proj",
+    "persp_proj",
+    "world_to_cam",
     "spherical_harmonics",
     "spherical_harmonics_table",
 ]

@@ -17,7 +17,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("B200SPLAT_LIB", _PKG / "libb200splat.so"))
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 _P = c_void_p
 _U32 = c_uint32
@@ -64,6 +64,17 @@ SIGNATURES = {
     "b200splat_rasterize_bwd": (
         _I, [_U32, _U32, _U64, _U32, _P, _P, _P, _P, _P, _P, _U32, _U32, _U32, _U32, _U32, _P, _P, _P,
              _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "b200splat_raster_indices_count": (
+        _I, [_U32, _U32, _U32, _U32, _U64, _P, _P, _P, _U32, _U32, _U32, _U32, _U32, _P, _P, _P, _P, _P, _P, _P,
+             c_size_t, _P]),
+    "b200splat_raster_indices_fill": (
+        _I, [_U32, _U32, _U32, _U32, _U64, _P, _P, _P, _U32, _U32, _U32, _U32, _U32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "b200splat_quat_scale_to_covar_preci_fwd": (_I, [_U32, _P, _P, _I, _P, _P, _P]),
+    "b200splat_quat_scale_to_covar_preci_bwd": (_I, [_U32, _P, _P, _P, _P, _I, _P, _P, _P]),
+    "b200splat_world_to_cam_fwd": (_I, [_U32, _U32, _P, _P, _P, _P, _P, _P]),
+    "b200splat_world_to_cam_bwd": (_I, [_U32, _U32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "b200splat_proj_fwd": (_I, [_U32, _U32, _P, _P, _P, _U32, _U32, _I, _P, _P, _P]),
+    "b200splat_proj_bwd": (_I, [_U32, _U32, _P, _P, _P, _U32, _U32, _I, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -332,7 +332,7 @@ __device__ __forceinline__ bool bwd_quad(float2 &T2, float2 &ntb2, const float2 
     return ok0 || ok1;
 }
 
-template <int CDIM, bool ABS, int NQ, int MINB>
+template <int CDIM, bool ABS, int NQ, int MINB, int JOINT>
 __global__ void __launch_bounds__(32 * (4 / NQ), MINB)
 raster_bwd_quad_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channels, const float4 *__restrict__ rec,
                        const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks, uint32_t W,
@@ -462,21 +462,31 @@ raster_bwd_quad_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t chann
             acc[0].nW0 = acc[0].nW1 = acc[0].nW2 = acc[1].nW0 = acc[1].nW1 = acc[1].nW2 = make_float2(0.f, 0.f);
             float2 abs2x = make_float2(0.f, 0.f), abs2y = abs2x;
             bool hit = false;
+#define B2S_BQ(SIGN_, q_)                                                                                            \
+    hit |= bwd_quad<CDIM, ABS, SIGN_>(T2[q_], ntb2[q_], v_c2[q_], binf[q_], nvacc2, acc[(q_) & 1], abs2x, abs2y,        \
+                                      dy2[(q_) >> 1], ndy2[(q_) >> 1], ((q_) & 1) ? dxb : dxa, hA, cb,                 \
+                                      ((q_) & 1) ? nAb : nAa, ((q_) & 1) ? Bb : Ba, hC, nopac, ncol, idx)
             if (m & kNonPD) {
 #pragma unroll
                 for (int q = 0; q < NQ; ++q)
-                    if (m >> q & 1)  // warp-uniform
-                        hit |= bwd_quad<CDIM, ABS, true>(T2[q], ntb2[q], v_c2[q], binf[q], nvacc2, acc[q & 1], abs2x, abs2y,
-                                                         dy2[q >> 1], ndy2[q >> 1], (q & 1) ? dxb : dxa, hA, cb,
-                                                         (q & 1) ? nAb : nAa, (q & 1) ? Bb : Ba, hC, nopac, ncol, idx);
-            } else {
+                    if (m >> q & 1) B2S_BQ(true, q);  // warp-uniform
+            } else if (JOINT == 0) {
 #pragma unroll
                 for (int q = 0; q < NQ; ++q)
-                    if (m >> q & 1)  // warp-uniform
-                        hit |= bwd_quad<CDIM, ABS, false>(T2[q], ntb2[q], v_c2[q], binf[q], nvacc2, acc[q & 1], abs2x, abs2y,
-                                                          dy2[q >> 1], ndy2[q >> 1], (q & 1) ? dxb : dxa, hA, cb,
-                                                          (q & 1) ? nAb : nAa, (q & 1) ? Bb : Ba, hC, nopac, ncol, idx);
+                    if (m >> q & 1) B2S_BQ(false, q);  // warp-uniform
+            } else if (JOINT == 2 && NQ == 4 && (m & 0xFu) == 0xFu) {
+                B2S_BQ(false, 0); B2S_BQ(false, 1); B2S_BQ(false, 2); B2S_BQ(false, 3);
+            } else {
+                // both quads of a quad row in one basic block when both are reached (ILP 2)
+#pragma unroll
+                for (int h = 0; h < NQY; ++h) {
+                    const uint32_t mm = (m >> (2 * h)) & 3u;
+                    if (mm == 3u) { B2S_BQ(false, 2 * h); B2S_BQ(false, 2 * h + 1); }
+                    else if (mm == 1u) B2S_BQ(false, 2 * h);
+                    else if (mm == 2u) B2S_BQ(false, 2 * h + 1);
+                }
             }
+#undef B2S_BQ
             if (!__any_sync(0xffffffffu, hit)) continue;
             // negated moments -> gradients (conic entries in the record are scaled by log2 e)
             float v[NV];
@@ -510,16 +520,20 @@ static void launch_bwd_quad(uint32_t C, uint64_t n_isects, uint32_t channels, co
                             const float *v_render_colors, const float *v_render_alphas, float *v_means2d_abs,
                             float *v_means2d, float *v_conics, float *v_colors, float *v_opacities, cudaStream_t st) {
     const uint32_t total = C * tile_width * tile_height;
-#define B2S_BWDQ(NQ_, MINB_)                                                                                         \
-    raster_bwd_quad_kernel<CDIM, ABS, NQ_, MINB_><<<total, 32 * (4 / NQ_), 0, st>>>(                                  \
+#define B2S_BWDQ(NQ_, MINB_, J_)                                                                                     \
+    raster_bwd_quad_kernel<CDIM, ABS, NQ_, MINB_, J_><<<total, 32 * (4 / NQ_), 0, st>>>(                              \
         total, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, \
         render_alphas, last_ids, v_render_colors, v_render_alphas, v_means2d_abs, v_means2d, v_conics, v_colors,     \
         v_opacities)
     switch (tuning_variant()) {
-        case 1: B2S_BWDQ(4, 20); break;
-        case 2: B2S_BWDQ(2, 16); break;
-        case 3: B2S_BWDQ(2, 10); break;
-        default: B2S_BWDQ(4, 16); break;
+        case 1: B2S_BWDQ(4, 20, 0); break;
+        case 2: B2S_BWDQ(2, 16, 0); break;
+        case 3: B2S_BWDQ(2, 10, 0); break;
+        case 4: B2S_BWDQ(4, 16, 1); break;
+        case 5: B2S_BWDQ(4, 16, 2); break;
+        case 6: B2S_BWDQ(4, 12, 1); break;
+        case 7: B2S_BWDQ(4, 12, 2); break;
+        default: B2S_BWDQ(4, 16, 0); break;
     }
 #undef B2S_BWDQ
 }

@@ -179,7 +179,7 @@ __device__ __forceinline__ void fwd_quad(float2 &T2, float2 (&pix2)[CDIM], int32
     T2.y = st1 ? fminf(T2.y, -T2.y) : next_T2.y;
 }
 
-template <int CDIM, int NQ, int MINB>
+template <int CDIM, int NQ, int MINB, int JOINT>
 __global__ void __launch_bounds__(32 * (4 / NQ), MINB)
 raster_fwd_quad_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channels, const float4 *__restrict__ rec,
                        const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks, uint32_t W,
@@ -288,19 +288,32 @@ raster_fwd_quad_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t chann
                 ndy2[qy] = __fadd2_rn(pyc2[qy], bc2(c4.z));   // p_y - g_y
                 dy2[qy] = __fadd2_rn(npyc2[qy], bc2(a.y));    // g_y - p_y
             }
+#define B2S_FQ(SIGN_, q_)                                                                                            \
+    fwd_quad<CDIM, SIGN_>(T2[q_], pix2[q_], cur[q_], dy2[(q_) >> 1], ndy2[(q_) >> 1], ((q_) & 1) ? nAb : nAa,          \
+                          ((q_) & 1) ? Bb : Ba, hC, nopac, ncol, idx)
             if (m & kNonPD) {
 #pragma unroll
                 for (int q = 0; q < NQ; ++q)
-                    if (m >> q & 1)  // warp-uniform
-                        fwd_quad<CDIM, true>(T2[q], pix2[q], cur[q], dy2[q >> 1], ndy2[q >> 1], (q & 1) ? nAb : nAa,
-                                             (q & 1) ? Bb : Ba, hC, nopac, ncol, idx);
-            } else {
+                    if (m >> q & 1) B2S_FQ(true, q);  // warp-uniform
+            } else if (JOINT == 0) {
 #pragma unroll
                 for (int q = 0; q < NQ; ++q)
-                    if (m >> q & 1)  // warp-uniform
-                        fwd_quad<CDIM, false>(T2[q], pix2[q], cur[q], dy2[q >> 1], ndy2[q >> 1], (q & 1) ? nAb : nAa,
-                                              (q & 1) ? Bb : Ba, hC, nopac, ncol, idx);
+                    if (m >> q & 1) B2S_FQ(false, q);  // warp-uniform
+            } else if (JOINT == 2 && NQ == 4 && (m & 0xFu) == 0xFu) {
+                // all four quads: one basic block, four independent dependency chains
+                B2S_FQ(false, 0); B2S_FQ(false, 1); B2S_FQ(false, 2); B2S_FQ(false, 3);
+            } else {
+                // the two quads of a quad row in ONE basic block when both are reached, so the
+                // scheduler interleaves their (independent) chains: ILP 2 instead of 1
+#pragma unroll
+                for (int h = 0; h < NQY; ++h) {
+                    const uint32_t mm = (m >> (2 * h)) & 3u;
+                    if (mm == 3u) { B2S_FQ(false, 2 * h); B2S_FQ(false, 2 * h + 1); }
+                    else if (mm == 1u) B2S_FQ(false, 2 * h);
+                    else if (mm == 2u) B2S_FQ(false, 2 * h + 1);
+                }
             }
+#undef B2S_FQ
         }
         // quads whose pixels have all stopped are skipped from now on
         uint32_t nl = 0;
@@ -337,15 +350,19 @@ static void launch_fwd_quad(uint32_t C, uint64_t n_isects, uint32_t channels, co
                             const int32_t *flatten_ids, float *render_colors, float *render_alphas, int32_t *last_ids,
                             cudaStream_t st) {
     const uint32_t total = C * tile_width * tile_height;
-#define B2S_FWDQ(NQ_, MINB_)                                                                                        \
-    raster_fwd_quad_kernel<CDIM, NQ_, MINB_><<<total, 32 * (4 / NQ_), 0, st>>>(                                      \
+#define B2S_FWDQ(NQ_, MINB_, J_)                                                                                    \
+    raster_fwd_quad_kernel<CDIM, NQ_, MINB_, J_><<<total, 32 * (4 / NQ_), 0, st>>>(                                  \
         total, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, \
         render_colors, render_alphas, last_ids)
     switch (tuning_variant()) {
-        case 1: B2S_FWDQ(4, 16); break;
-        case 2: B2S_FWDQ(2, 16); break;
-        case 3: B2S_FWDQ(2, 10); break;
-        default: B2S_FWDQ(4, 20); break;
+        case 1: B2S_FWDQ(4, 16, 0); break;
+        case 2: B2S_FWDQ(2, 16, 0); break;
+        case 3: B2S_FWDQ(2, 10, 0); break;
+        case 4: B2S_FWDQ(4, 20, 1); break;
+        case 5: B2S_FWDQ(4, 20, 2); break;
+        case 6: B2S_FWDQ(4, 16, 1); break;
+        case 7: B2S_FWDQ(4, 16, 2); break;
+        default: B2S_FWDQ(4, 20, 0); break;
     }
 #undef B2S_FWDQ
 }

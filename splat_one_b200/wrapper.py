@@ -9,6 +9,8 @@ types as the reference (G = /root/reference/submodules/gsplat/gsplat):
     isect_tiles              G/cuda/_wrapper.py:342-413
     isect_offset_encode      G/cuda/_wrapper.py:416-433
     rasterize_to_pixels      G/cuda/_wrapper.py:436-568   (+ _RasterizeToPixels :901-1028)
+    rasterize_to_indices_in_range  G/cuda/_wrapper.py:571-643;  accumulate  G/cuda/_torch_impl.py:485-572
+    quat_scale_to_covar_preci, proj, persp_proj, world_to_cam   G/cuda/_wrapper.py:76-200, 646-772
 
 Every tensor (outputs, gradients, scan/sort workspaces) is allocated here with torch so
 memory stays under the caching allocator and the current stream; the native library
@@ -48,6 +50,8 @@ class _Profiler:
         "projection_packed_bwd": 1, "sh_fwd": 1, "sh_bwd": 1, "camera_centers": 1, "sh_colors_fwd": 1,
         "sh_colors_bwd": 1, "sh_colors_packed_fwd": 1, "sh_colors_packed_bwd": 1, "isect_count": 2, "isect_fill": 1,
         "isect_sort": 0, "isect_sorted": 5, "isect_offset_encode": 1, "rasterize_pack": 1, "rasterize_fwd": 1, "rasterize_bwd": 1,
+        "raster_indices_count": 2, "raster_indices_fill": 1, "quat_scale_to_covar_preci_fwd": 1,
+        "quat_scale_to_covar_preci_bwd": 1, "world_to_cam_fwd": 1, "world_to_cam_bwd": 1, "proj_fwd": 1, "proj_bwd": 1,
     }
 
     def __init__(self):
@@ -935,3 +939,294 @@ class _RasterizeToPixels(torch.autograd.Function):
             v_backgrounds = (v_render_colors * (1.0 - render_alphas).float()).sum(dim=(1, 2))
         return (v_means2d, v_conics, v_colors, v_opacities, v_backgrounds,
                 None, None, None, None, None, None, None)
+
+
+# ----------------------------------------------------------------------------------------
+# rasterize_to_indices_in_range + accumulate
+# ----------------------------------------------------------------------------------------
+@torch.no_grad()
+def rasterize_to_indices_in_range(
+    range_start: int,
+    range_end: int,
+    transmittances: Tensor,  # [C, image_height, image_width]
+    means2d: Tensor,  # [C, N, 2]
+    conics: Tensor,  # [C, N, 3]
+    opacities: Tensor,  # [C, N]
+    image_width: int,
+    image_height: int,
+    tile_size: int,
+    isect_offsets: Tensor,  # [C, tile_height, tile_width]
+    flatten_ids: Tensor,  # [n_isects]
+) -> Tuple[Tensor, Tensor, Tensor]:
+    """Rasterizes a batch of Gaussians to images but only returns the indices
+    (G/cuda/_wrapper.py:571-643; kernel CS/rasterize_to_indices_in_range.cu).
+
+    `[range_start, range_end)` counts batches of tile_size² list entries per tile, front to
+    back.  Returns (gaussian_ids, pixel_ids, camera_ids), int64 [M], grouped by pixel in
+    (camera, row, column) order and front to back inside a pixel."""
+    C, N, _ = means2d.shape
+    assert conics.shape == (C, N, 3), conics.shape
+    assert opacities.shape == (C, N), opacities.shape
+    assert isect_offsets.shape[0] == C, isect_offsets.shape
+    tile_height, tile_width = isect_offsets.shape[1:3]
+    assert (
+        tile_height * tile_size >= image_height
+    ), f"Assert Failed: {tile_height} * {tile_size} >= {image_height}"
+    assert (
+        tile_width * tile_size >= image_width
+    ), f"Assert Failed: {tile_width} * {tile_size} >= {image_width}"
+    assert transmittances.shape == (C, image_height, image_width), transmittances.shape
+    transmittances = transmittances.contiguous()
+    means2d, conics, opacities = means2d.contiguous(), conics.contiguous(), opacities.contiguous()
+    isect_offsets, flatten_ids = isect_offsets.contiguous(), flatten_ids.contiguous()
+    _check_cuda(transmittances, means2d, conics, opacities, isect_offsets, flatten_ids)
+    for t in (transmittances, means2d, conics, opacities):
+        _f32(t)
+    if isect_offsets.dtype != torch.int32 or flatten_ids.dtype != torch.int32:
+        raise RuntimeError("b200splat: isect_offsets and flatten_ids must be int32")
+    lib = get_lib()
+    dev = means2d.device
+    n_pix = C * image_height * image_width
+    n_isects = flatten_ids.numel()
+    # clamp the Python ints (callers pass e.g. 1e10 for "to the end") into uint32
+    rs = int(min(max(range_start, 0), 0xFFFFFFFF))
+    re_ = int(min(max(range_end, 0), 0xFFFFFFFF))
+    n_elems = 0
+    if n_pix and n_isects and N:
+        cnts = torch.empty((n_pix,), device=dev, dtype=torch.int32)
+        cum = torch.empty((n_pix,), device=dev, dtype=torch.int64)
+        total = torch.empty((1,), device=dev, dtype=torch.int64)
+        ws_bytes = lib.b200splat_scan_workspace_bytes(n_pix)
+        ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
+        common = (rs, re_, C, N, n_isects, _ptr(means2d), _ptr(conics), _ptr(opacities), image_width, image_height,
+                  tile_size, tile_width, tile_height, _ptr(isect_offsets), _ptr(flatten_ids), _ptr(transmittances))
+        native("raster_indices_count", lib, dev, *common, _ptr(cnts), _ptr(cum), _ptr(total), _ptr(ws), ws_bytes)
+        n_elems = int(total.item())  # the one host sync (CS/rasterize_to_indices_in_range.cu:263)
+    gaussian_ids = torch.empty((n_elems,), device=dev, dtype=torch.int64)
+    out_indices = torch.empty((n_elems,), device=dev, dtype=torch.int64)
+    if n_elems:
+        native("raster_indices_fill", lib, dev, *common, _ptr(cnts), _ptr(cum), _ptr(gaussian_ids), _ptr(out_indices))
+    out_pixel_ids = out_indices % (image_width * image_height)
+    out_camera_ids = out_indices // (image_width * image_height)
+    return gaussian_ids, out_pixel_ids, out_camera_ids
+
+
+def accumulate(
+    means2d: Tensor,  # [C, N, 2]
+    conics: Tensor,  # [C, N, 3]
+    opacities: Tensor,  # [C, N]
+    colors: Tensor,  # [C, N, channels]
+    gaussian_ids: Tensor,  # [M]
+    pixel_ids: Tensor,  # [M]
+    camera_ids: Tensor,  # [M]
+    image_width: int,
+    image_height: int,
+) -> Tuple[Tensor, Tensor]:
+    """Alpha compositing of the listed (Gaussian, pixel, camera) intersections in plain
+    PyTorch, differentiable by autograd (G/cuda/_torch_impl.py:485-572).
+
+    The reference delegates the two segment operations to the third-party `nerfacc` package
+    (`render_weight_from_alpha`, `accumulate_along_rays`; un-pinned git dependency, not
+    vendored); here they are torch ops: transmittance = segmented exclusive product of
+    (1 - alpha) over the entries of a pixel (float64 log-space prefix sums, so cancellation
+    across millions of entries stays below fp32 resolution), accumulation = `index_add`.
+    Like nerfacc, entries of one pixel must be contiguous and front to back — the order
+    `rasterize_to_indices_in_range` returns.
+
+    Returns (renders [C,H,W,channels], alphas [C,H,W,1])."""
+    C, N = means2d.shape[:2]
+    channels = colors.shape[-1]
+    pixel_ids_x = pixel_ids % image_width
+    pixel_ids_y = pixel_ids // image_width
+    pixel_coords = torch.stack([pixel_ids_x, pixel_ids_y], dim=-1) + 0.5  # [M, 2]
+    deltas = pixel_coords - means2d[camera_ids, gaussian_ids]  # [M, 2]
+    c = conics[camera_ids, gaussian_ids]  # [M, 3]
+    sigmas = 0.5 * (c[:, 0] * deltas[:, 0] ** 2 + c[:, 2] * deltas[:, 1] ** 2) + c[:, 1] * deltas[:, 0] * deltas[:, 1]
+    alphas = torch.clamp_max(opacities[camera_ids, gaussian_ids] * torch.exp(-sigmas), 0.999)
+
+    indices = camera_ids * image_height * image_width + pixel_ids
+    total_pixels = C * image_height * image_width
+    M = indices.numel()
+    if M:
+        log1m = torch.log1p(-alphas.double())
+        incl = torch.cumsum(log1m, dim=0)
+        excl = incl - log1m
+        first = torch.ones_like(indices, dtype=torch.bool)
+        first[1:] = indices[1:] != indices[:-1]
+        # prefix sum just before the first entry of each pixel's segment, broadcast to the segment
+        seg = torch.cumsum(first.long(), dim=0) - 1
+        base = excl[first][seg]
+        trans = torch.exp(excl - base).to(alphas.dtype)
+        weights = alphas * trans
+    else:
+        weights = alphas
+    renders = torch.zeros((total_pixels, channels), device=means2d.device, dtype=colors.dtype)
+    renders = renders.index_add(0, indices, weights[:, None] * colors[camera_ids, gaussian_ids])
+    accs = torch.zeros((total_pixels,), device=means2d.device, dtype=colors.dtype).index_add(0, indices, weights)
+    return (renders.reshape(C, image_height, image_width, channels),
+            accs.reshape(C, image_height, image_width, 1))
+
+
+# ----------------------------------------------------------------------------------------
+# un-fused projection chain (SURVEY §8 f2)
+# ----------------------------------------------------------------------------------------
+def quat_scale_to_covar_preci(
+    quats: Tensor,  # [N, 4],
+    scales: Tensor,  # [N, 3],
+    compute_covar: bool = True,
+    compute_preci: bool = True,
+    triu: bool = False,
+) -> Tuple[Optional[Tensor], Optional[Tensor]]:
+    """Converts quaternions and scales to covariance and precision matrices
+    (G/cuda/_wrapper.py:76-107).  [N,6] upper triangles if `triu`, else [N,3,3]."""
+    assert quats.dim() == 2 and quats.size(1) == 4, quats.size()
+    assert scales.dim() == 2 and scales.size(1) == 3, scales.size()
+    quats = quats.contiguous()
+    scales = scales.contiguous()
+    covars, precis = _QuatScaleToCovarPreci.apply(quats, scales, compute_covar, compute_preci, triu)
+    return covars if compute_covar else None, precis if compute_preci else None
+
+
+class _QuatScaleToCovarPreci(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, quats, scales, compute_covar=True, compute_preci=True, triu=False):
+        _check_cuda(quats, scales)
+        _f32(quats), _f32(scales)
+        lib = get_lib()
+        quats = _aligned16(quats)
+        N = quats.shape[0]
+        shape = (N, 6) if triu else (N, 3, 3)
+        # a skipped output is an empty tensor, like the reference's (CS/quat_scale_to_covar_preci_fwd.cu)
+        covars = torch.empty(shape if compute_covar else (0,), device=quats.device, dtype=torch.float32)
+        precis = torch.empty(shape if compute_preci else (0,), device=quats.device, dtype=torch.float32)
+        if N:
+            native("quat_scale_to_covar_preci_fwd", lib, quats.device, N, _ptr(quats), _ptr(scales), int(triu),
+                   _ptr(covars) if compute_covar else None, _ptr(precis) if compute_preci else None)
+        ctx.save_for_backward(quats, scales)
+        ctx.compute_covar, ctx.compute_preci, ctx.triu = compute_covar, compute_preci, triu
+        return covars, precis
+
+    @staticmethod
+    def backward(ctx, v_covars, v_precis):
+        quats, scales = ctx.saved_tensors
+        lib = get_lib()
+        N = quats.shape[0]
+        if ctx.compute_covar and v_covars.is_sparse:
+            v_covars = v_covars.to_dense()
+        if ctx.compute_preci and v_precis.is_sparse:
+            v_precis = v_precis.to_dense()
+        v_covars = v_covars.contiguous() if ctx.compute_covar else None
+        v_precis = v_precis.contiguous() if ctx.compute_preci else None
+        v_quats = torch.empty_like(quats)
+        v_scales = torch.empty_like(scales)
+        if N:
+            native("quat_scale_to_covar_preci_bwd", lib, quats.device, N, _ptr(quats), _ptr(scales), _ptr(v_covars),
+                   _ptr(v_precis), int(ctx.triu), _ptr(v_quats), _ptr(v_scales))
+        return v_quats, v_scales, None, None, None
+
+
+def persp_proj(means: Tensor, covars: Tensor, Ks: Tensor, width: int, height: int) -> Tuple[Tensor, Tensor]:
+    """DEPRECATED alias of `proj(..., camera_model="pinhole")` (G/cuda/_wrapper.py:110-139)."""
+    import warnings
+
+    warnings.warn("persp_proj is deprecated and will be removed in a future release. "
+                  "Use proj with ortho=False instead.", DeprecationWarning)
+    return proj(means, covars, Ks, width, height, "pinhole")
+
+
+def proj(
+    means: Tensor,  # [C, N, 3]
+    covars: Tensor,  # [C, N, 3, 3]
+    Ks: Tensor,  # [C, 3, 3]
+    width: int,
+    height: int,
+    camera_model: Literal["pinhole", "ortho", "fisheye", "spherical"] = "pinhole",
+) -> Tuple[Tensor, Tensor]:
+    """Projection of camera-space Gaussians (G/cuda/_wrapper.py:142-172):
+    returns (means2d [C,N,2], covars2d [C,N,2,2])."""
+    C, N, _ = means.shape
+    assert means.shape == (C, N, 3), means.size()
+    assert covars.shape == (C, N, 3, 3), covars.size()
+    assert Ks.shape == (C, 3, 3), Ks.size()
+    if camera_model not in CAMERA_MODELS:
+        raise AttributeError(f"CameraModelType has no member {camera_model.upper()!r}")
+    return _Proj.apply(means.contiguous(), covars.contiguous(), Ks.contiguous(), width, height, camera_model)
+
+
+class _Proj(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means, covars, Ks, width, height, camera_model="pinhole"):
+        _check_cuda(means, covars, Ks)
+        _f32(means), _f32(covars), _f32(Ks)
+        lib = get_lib()
+        C, N = means.shape[:2]
+        means2d = torch.empty((C, N, 2), device=means.device, dtype=torch.float32)
+        covars2d = torch.empty((C, N, 2, 2), device=means.device, dtype=torch.float32)
+        if C * N:
+            native("proj_fwd", lib, means.device, C, N, _ptr(means), _ptr(covars), _ptr(Ks), width, height,
+                   CAMERA_MODELS[camera_model], _ptr(means2d), _ptr(covars2d))
+        ctx.save_for_backward(means, covars, Ks)
+        ctx.width, ctx.height, ctx.camera_model = width, height, CAMERA_MODELS[camera_model]
+        return means2d, covars2d
+
+    @staticmethod
+    def backward(ctx, v_means2d, v_covars2d):
+        means, covars, Ks = ctx.saved_tensors
+        lib = get_lib()
+        C, N = means.shape[:2]
+        v_means = torch.empty_like(means)
+        v_covars = torch.empty_like(covars)
+        if C * N:
+            native("proj_bwd", lib, means.device, C, N, _ptr(means), _ptr(covars), _ptr(Ks), ctx.width, ctx.height,
+                   ctx.camera_model, _ptr(_aligned16(v_means2d.contiguous())), _ptr(_aligned16(v_covars2d.contiguous())),
+                   _ptr(v_means), _ptr(v_covars))
+        return v_means, v_covars, None, None, None, None
+
+
+def world_to_cam(
+    means: Tensor,  # [N, 3]
+    covars: Tensor,  # [N, 3, 3]
+    viewmats: Tensor,  # [C, 4, 4]
+) -> Tuple[Tensor, Tensor]:
+    """Transforms Gaussians from world to camera coordinates (G/cuda/_wrapper.py:175-200):
+    returns (means_c [C,N,3], covars_c [C,N,3,3])."""
+    C = viewmats.size(0)
+    N = means.size(0)
+    assert means.size() == (N, 3), means.size()
+    assert covars.size() == (N, 3, 3), covars.size()
+    assert viewmats.size() == (C, 4, 4), viewmats.size()
+    return _WorldToCam.apply(means.contiguous(), covars.contiguous(), viewmats.contiguous())
+
+
+class _WorldToCam(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means, covars, viewmats):
+        _check_cuda(means, covars, viewmats)
+        _f32(means), _f32(covars), _f32(viewmats)
+        lib = get_lib()
+        C, N = viewmats.shape[0], means.shape[0]
+        means_c = torch.empty((C, N, 3), device=means.device, dtype=torch.float32)
+        covars_c = torch.empty((C, N, 3, 3), device=means.device, dtype=torch.float32)
+        if C * N:
+            native("world_to_cam_fwd", lib, means.device, C, N, _ptr(means), _ptr(covars), _ptr(viewmats),
+                   _ptr(means_c), _ptr(covars_c))
+        ctx.save_for_backward(means, covars, viewmats)
+        return means_c, covars_c
+
+    @staticmethod
+    def backward(ctx, v_means_c, v_covars_c):
+        means, covars, viewmats = ctx.saved_tensors
+        lib = get_lib()
+        C, N = viewmats.shape[0], means.shape[0]
+        need = ctx.needs_input_grad
+        v_means = torch.empty_like(means) if need[0] else None
+        v_covars = torch.empty_like(covars) if need[1] else None
+        v_viewmats = torch.zeros_like(viewmats) if need[2] else None
+        if C * N:
+            native("world_to_cam_bwd", lib, means.device, C, N, _ptr(means), _ptr(covars), _ptr(viewmats),
+                   _ptr(v_means_c.contiguous()), _ptr(v_covars_c.contiguous()), _ptr(v_means), _ptr(v_covars),
+                   _ptr(v_viewmats))
+        elif N:
+            v_means = torch.zeros_like(means) if need[0] else None
+            v_covars = torch.zeros_like(covars) if need[1] else None
+        return v_means, v_covars, v_viewmats
