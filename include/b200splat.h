@@ -395,6 +395,25 @@ B200SPLAT_API int b200splat_proj_bwd(
     const float *v_means2d, const float *v_covars2d,
     float *v_means, float *v_covars, void *stream);
 
+/* ------------------------------------------------------------------------------------
+ * f3  optimizer / densifier-side kernels fed by the path's outputs.
+ *
+ * selective_adam_update   CS/adam.cu:16-82 (gsplat/cuda/_wrapper.py:19-34): Adam moments
+ *     and step for the M elements of every Gaussian whose `visible` byte (bool) is set;
+ *     no bias correction, exactly as the reference.  param/exp_avg/exp_avg_sq [N*M] are
+ *     updated in place.
+ * compute_relocation      CS/compute_relocation.cu:6-70 (gsplat/relocation.py:10-55):
+ *     ratios int32 [N] already clamped to [1, n_max]; binoms fp32 [n_max, n_max], n_max <= 64.
+ * ---------------------------------------------------------------------------------- */
+B200SPLAT_API int b200splat_selective_adam_update(
+    float *param, const float *param_grad, float *exp_avg, float *exp_avg_sq,
+    const uint8_t *visible, float lr, float b1, float b2, float eps,
+    uint32_t N, uint32_t M, void *stream);
+
+B200SPLAT_API int b200splat_compute_relocation(
+    uint32_t N, const float *opacities, const float *scales, const int32_t *ratios,
+    const float *binoms, int n_max, float *new_opacities, float *new_scales, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

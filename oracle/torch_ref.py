@@ -638,6 +638,36 @@ def proj(means_c, covars_c, Ks, width, height, camera_model="pinhole"):
 
 
 # ----------------------------------------------------------------------------------------
+# f3: optimizer / densifier-side kernels
+# ----------------------------------------------------------------------------------------
+def selective_adam_update(param, grad, exp_avg, exp_avg_sq, visible, lr, b1, b2, eps):
+    """CS/adam.cu:16-44, out of place: returns (param, exp_avg, exp_avg_sq).  No bias
+    correction; Gaussians with visible == False keep all three tensors."""
+    N = visible.numel()
+    vis = visible.reshape((N,) + (1,) * (param.dim() - 1)).expand_as(param)
+    m = b1 * exp_avg + (1.0 - b1) * grad
+    v = b2 * exp_avg_sq + (1.0 - b2) * grad * grad
+    step = -lr * m / (torch.sqrt(v) + eps)
+    return (torch.where(vis, param + step, param), torch.where(vis, m, exp_avg), torch.where(vis, v, exp_avg_sq))
+
+
+def compute_relocation(opacities, scales, ratios, binoms):
+    """CS/compute_relocation.cu:6-39 (+ the clamp of G/relocation.py:48-49), float32, same
+    (i outer, k inner) summation order."""
+    n_max = binoms.shape[0]
+    n = ratios.clamp(min=1, max=n_max).int()
+    new_op = 1.0 - torch.pow(1.0 - opacities, 1.0 / n.to(opacities.dtype))
+    denom = torch.zeros_like(opacities)
+    for i in range(1, n_max + 1):
+        active = n >= i
+        for k in range(i):
+            term = ((-1.0) ** k / math.sqrt(k + 1)) * torch.pow(new_op, k + 1)
+            denom = denom + torch.where(active, binoms[i - 1, k] * term, torch.zeros_like(term))
+    coeff = opacities / denom
+    return new_op, coeff[:, None] * scales
+
+
+# ----------------------------------------------------------------------------------------
 # a1: the whole pipeline (G/rendering.py:28-582), CPU
 # ----------------------------------------------------------------------------------------
 def rasterization(means, quats, scales, opacities, colors, viewmats, Ks, width, height,

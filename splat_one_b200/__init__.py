@@ -8,9 +8,11 @@ that inuex35/splat_one calls (`gsplat.rasterization` and the five operators unde
 The compute lives in libb200splat.so (hand-written CUDA, C ABI in include/b200splat.h);
 there is no CPU / PyTorch fallback.
 """
+from .optimizers import SelectiveAdam
 from .rendering import rasterization
 from .wrapper import (
     accumulate,
+    compute_relocation,
     fully_fused_projection,
     isect_offset_encode,
     isect_tiles,
@@ -19,6 +21,7 @@ from .wrapper import (
     quat_scale_to_covar_preci,
     rasterize_to_indices_in_range,
     rasterize_to_pixels,
+    selective_adam_update,
     world_to_cam,
     spherical_harmonics,
     spherical_harmonics_table,
@@ -38,6 +41,9 @@ __all__ = [
     "proj",
     "persp_proj",
     "world_to_cam",
+    "selective_adam_update",
+    "compute_relocation",
+    "SelectiveAdam",
     "spherical_harmonics",
     "spherical_harmonics_table",
 ]

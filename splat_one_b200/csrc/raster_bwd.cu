@@ -529,11 +529,9 @@ static void launch_bwd_quad(uint32_t C, uint64_t n_isects, uint32_t channels, co
         case 1: B2S_BWDQ(4, 20, 0); break;
         case 2: B2S_BWDQ(2, 16, 0); break;
         case 3: B2S_BWDQ(2, 10, 0); break;
-        case 4: B2S_BWDQ(4, 16, 1); break;
+        case 4: B2S_BWDQ(4, 16, 0); break;
         case 5: B2S_BWDQ(4, 16, 2); break;
-        case 6: B2S_BWDQ(4, 12, 1); break;
-        case 7: B2S_BWDQ(4, 12, 2); break;
-        default: B2S_BWDQ(4, 16, 0); break;
+        default: B2S_BWDQ(4, 16, 1); break;  // measured on config B: 0.615 ms vs 0.652 (JOINT 0), 0.617 (JOINT 2)
     }
 #undef B2S_BWDQ
 }

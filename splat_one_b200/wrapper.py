@@ -52,6 +52,7 @@ class _Profiler:
         "isect_sort": 0, "isect_sorted": 5, "isect_offset_encode": 1, "rasterize_pack": 1, "rasterize_fwd": 1, "rasterize_bwd": 1,
         "raster_indices_count": 2, "raster_indices_fill": 1, "quat_scale_to_covar_preci_fwd": 1,
         "quat_scale_to_covar_preci_bwd": 1, "world_to_cam_fwd": 1, "world_to_cam_bwd": 1, "proj_fwd": 1, "proj_bwd": 1,
+        "selective_adam_update": 1, "compute_relocation": 1,
     }
 
     def __init__(self):
@@ -1230,3 +1231,61 @@ class _WorldToCam(torch.autograd.Function):
             v_means = torch.zeros_like(means) if need[0] else None
             v_covars = torch.zeros_like(covars) if need[1] else None
         return v_means, v_covars, v_viewmats
+
+
+# ----------------------------------------------------------------------------------------
+# optimizer / densifier-side operators
+# ----------------------------------------------------------------------------------------
+def selective_adam_update(
+    param: Tensor,
+    param_grad: Tensor,
+    exp_avg: Tensor,
+    exp_avg_sq: Tensor,
+    tiles_touched: Tensor,
+    lr: float,
+    b1: float,
+    b2: float,
+    eps: float,
+    N: int,
+    M: int,
+) -> None:
+    """In-place Adam update of the Gaussians flagged in `tiles_touched` [N] (bool)
+    (G/cuda/_wrapper.py:19-34, kernel CS/adam.cu:16-44)."""
+    _check_cuda(param, param_grad, exp_avg, exp_avg_sq, tiles_touched)
+    for t in (param, param_grad, exp_avg, exp_avg_sq):
+        _f32(t)
+    if tiles_touched.dtype != torch.bool:
+        raise RuntimeError(f"b200splat: tiles_touched must be bool, got {tiles_touched.dtype}")
+    assert param.numel() == N * M and param_grad.numel() == N * M, (param.shape, N, M)
+    assert exp_avg.numel() == N * M and exp_avg_sq.numel() == N * M and tiles_touched.numel() == N
+    if N * M:
+        native("selective_adam_update", get_lib(), param.device, _ptr(param), _ptr(param_grad), _ptr(exp_avg),
+               _ptr(exp_avg_sq), _ptr(tiles_touched), float(lr), float(b1), float(b2), float(eps), N, M)
+
+
+def compute_relocation(
+    opacities: Tensor,  # [N]
+    scales: Tensor,  # [N, 3]
+    ratios: Tensor,  # [N]
+    binoms: Tensor,  # [n_max, n_max]
+) -> Tuple[Tensor, Tensor]:
+    """New opacities / scales of relocated Gaussians, Eq. (9) of "3D Gaussian Splatting as
+    Markov Chain Monte Carlo" (G/relocation.py:10-55, kernel CS/compute_relocation.cu:6-39).
+    Like the reference, clamps `ratios` to [1, n_max] IN PLACE before converting to int."""
+    N = opacities.shape[0]
+    n_max, _ = binoms.shape
+    assert scales.shape == (N, 3), scales.shape
+    assert ratios.shape == (N,), ratios.shape
+    opacities = opacities.contiguous()
+    scales = scales.contiguous()
+    ratios.clamp_(min=1, max=n_max)
+    ratios = ratios.int().contiguous()
+    binoms = binoms.contiguous()
+    _check_cuda(opacities, scales, ratios, binoms)
+    _f32(opacities), _f32(scales), _f32(binoms)
+    new_opacities = torch.empty_like(opacities)
+    new_scales = torch.empty_like(scales)
+    if N:
+        native("compute_relocation", get_lib(), opacities.device, N, _ptr(opacities), _ptr(scales), _ptr(ratios),
+               _ptr(binoms), int(n_max), _ptr(new_opacities), _ptr(new_scales))
+    return new_opacities, new_scales

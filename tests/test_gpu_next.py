@@ -238,3 +238,68 @@ def test_unfused_chain_equals_fused_projection():
     assert e[0].shape == (0, 3, 3) and e[1].shape == (0, 3, 3)
     e = S.world_to_cam(torch.zeros(0, 3, device=DEV), torch.zeros(0, 3, 3, device=DEV), _g(vm))
     assert e[0].shape == (C, 0, 3) and e[1].shape == (C, 0, 3, 3)
+
+
+# ------------------------------------------------------------------------------------
+# f3: selective_adam_update / SelectiveAdam / compute_relocation
+# ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(1000, 3), (777, 15, 3), (512,), (64, 4)])
+def test_selective_adam_matches_oracle(shape):
+    g = torch.Generator().manual_seed(len(shape))
+    N = shape[0]
+    param, grad = torch.randn(shape, generator=g), torch.randn(shape, generator=g)
+    m, v = torch.randn(shape, generator=g) * 0.1, torch.rand(shape, generator=g) * 0.1
+    vis = torch.rand(N, generator=g) > 0.4
+    lr, b1, b2, eps = 1e-2, 0.9, 0.999, 1e-8
+    rp, rm, rv = O.selective_adam_update(param, grad, m, v, vis, lr, b1, b2, eps)
+    gp, gm, gv = _g(param).clone(), _g(m).clone(), _g(v).clone()
+    S.selective_adam_update(gp, _g(grad), gm, gv, _g(vis), lr, b1, b2, eps, N, param.numel() // N)
+    torch.testing.assert_close(gp.cpu(), rp, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(gm.cpu(), rm, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(gv.cpu(), rv, rtol=1e-6, atol=1e-7)
+    # invisible rows are bit-identical to the input
+    assert torch.equal(gp.cpu()[~vis], param[~vis]) and torch.equal(gm.cpu()[~vis], m[~vis])
+
+
+def test_selective_adam_optimizer_class():
+    g = torch.Generator().manual_seed(0)
+    p0 = torch.randn(100, 3, generator=g)
+    p = torch.nn.Parameter(_g(p0).clone())
+    opt = S.SelectiveAdam([{"params": [p], "lr": 0.05}], eps=1e-8, betas=(0.9, 0.999))
+    vis = _g(torch.cat([torch.ones(50), torch.zeros(50)]).bool())
+    ref_p, ref_m, ref_v = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    for _ in range(3):
+        opt.zero_grad()
+        (p ** 2).sum().backward()
+        opt.step(visibility=vis)
+        ref_p, ref_m, ref_v = O.selective_adam_update(ref_p, 2 * ref_p, ref_m, ref_v, vis.cpu(), 0.05, 0.9, 0.999, 1e-8)
+    torch.testing.assert_close(p.detach().cpu(), ref_p, rtol=1e-5, atol=1e-6)
+    assert torch.equal(p.detach().cpu()[50:], p0[50:])
+    with pytest.raises(RuntimeError):
+        S.selective_adam_update(p0, p0, p0, p0, vis.cpu(), 0.1, 0.9, 0.99, 1e-8, 100, 3)
+
+
+def test_compute_relocation_matches_oracle():
+    g = torch.Generator().manual_seed(2)
+    N, n_max = 4000, 51
+    binoms = torch.zeros(n_max, n_max)
+    for n in range(n_max):
+        for k in range(n + 1):
+            binoms[n, k] = math.comb(n, k)
+    op = torch.rand(N, generator=g) * 0.98 + 0.01
+    sc = torch.rand(N, 3, generator=g)
+    ratios = torch.randint(0, 12, (N,), generator=g)  # 0 is clamped to 1; modest n keeps fp32 well conditioned
+    r_op, r_sc = O.compute_relocation(op, sc, ratios.clone(), binoms)
+    rt = _g(ratios).clone()
+    g_op, g_sc = S.compute_relocation(_g(op), _g(sc), rt, _g(binoms))
+    assert int(rt.min()) == 1  # clamped in place like the reference (G/relocation.py:48)
+    torch.testing.assert_close(g_op.cpu(), r_op, rtol=2e-4, atol=1e-6)
+    torch.testing.assert_close(g_sc.cpu(), r_sc, rtol=2e-3, atol=1e-6)
+    # n = 1 is the identity
+    one = torch.ones(N, dtype=torch.int64)
+    i_op, i_sc = S.compute_relocation(_g(op), _g(sc), _g(one), _g(binoms))
+    torch.testing.assert_close(i_op.cpu(), op, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(i_sc.cpu(), sc, rtol=1e-4, atol=1e-6)
+    e = S.compute_relocation(torch.zeros(0, device=DEV), torch.zeros(0, 3, device=DEV),
+                             torch.zeros(0, device=DEV, dtype=torch.int64), _g(binoms))
+    assert e[0].shape == (0,) and e[1].shape == (0, 3)

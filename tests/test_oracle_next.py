@@ -105,3 +105,31 @@ def test_unfused_oracle_matches_reference_torch_impl(golden):
         ga, gb = torch.autograd.grad((m2 * d["v_means2d"]).sum() + (c2 * d["v_covars2d"]).sum(), (a, b))
         assert_grad_close(ga, d[f"ref_proj_v_means_{cm}"], rtol=1e-3, what=f"proj v_means {cm}")
         assert_grad_close(gb, d[f"ref_proj_v_covars_{cm}"], rtol=1e-3, what=f"proj v_covars {cm}")
+
+
+def test_relocation_and_adam_oracle_known_answers():
+    """n = 1 relocation is the identity; n = 2 has the closed form of Eq. (9); selective Adam
+    equals torch.optim.Adam's first step without bias correction on the visible rows."""
+    import math
+
+    n_max = 51
+    binoms = torch.zeros(n_max, n_max)
+    for n in range(n_max):
+        for k in range(n + 1):
+            binoms[n, k] = math.comb(n, k)
+    op = torch.tensor([0.3, 0.7, 0.95])
+    sc = torch.tensor([[1.0, 2.0, 3.0]] * 3)
+    no, ns = O.compute_relocation(op, sc, torch.tensor([1, 1, 1]), binoms)
+    torch.testing.assert_close(no, op)
+    torch.testing.assert_close(ns, sc)
+    no, ns = O.compute_relocation(op, sc, torch.tensor([2, 2, 2]), binoms)
+    exp_no = 1 - torch.sqrt(1 - op)
+    denom = exp_no + (exp_no - exp_no ** 2 / math.sqrt(2))
+    torch.testing.assert_close(no, exp_no)
+    torch.testing.assert_close(ns, (op / denom)[:, None] * sc)
+    p, g = torch.tensor([[1.0, 2.0], [3.0, 4.0]]), torch.tensor([[0.5, -0.5], [1.0, 1.0]])
+    z = torch.zeros_like(p)
+    np_, nm, nv = O.selective_adam_update(p, g, z, z, torch.tensor([True, False]), 0.1, 0.9, 0.999, 1e-8)
+    assert torch.equal(np_[1], p[1]) and torch.equal(nm[1], z[1])
+    m, v = 0.1 * g[0], 0.001 * g[0] ** 2
+    torch.testing.assert_close(np_[0], p[0] - 0.1 * m / (v.sqrt() + 1e-8))
