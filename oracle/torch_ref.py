@@ -645,8 +645,14 @@ def selective_adam_update(param, grad, exp_avg, exp_avg_sq, visible, lr, b1, b2,
     correction; Gaussians with visible == False keep all three tensors."""
     N = visible.numel()
     vis = visible.reshape((N,) + (1,) * (param.dim() - 1)).expand_as(param)
-    m = b1 * exp_avg + (1.0 - b1) * grad
-    v = b2 * exp_avg_sq + (1.0 - b2) * grad * grad
+    # the kernel forms 1 - beta in float32 (`1.0f - b1`, CS/adam.cu:34-35), which differs from
+    # the double-precision 1 - beta by up to ~1e-5 relative
+    f32 = np.float32
+    b1, b2 = f32(b1), f32(b2)
+    omb1, omb2 = float(f32(1.0) - b1), float(f32(1.0) - b2)
+    b1, b2 = float(b1), float(b2)
+    m = b1 * exp_avg + omb1 * grad
+    v = b2 * exp_avg_sq + omb2 * grad * grad
     step = -lr * m / (torch.sqrt(v) + eps)
     return (torch.where(vis, param + step, param), torch.where(vis, m, exp_avg), torch.where(vis, v, exp_avg_sq))
 

@@ -256,7 +256,7 @@ def test_selective_adam_matches_oracle(shape):
     S.selective_adam_update(gp, _g(grad), gm, gv, _g(vis), lr, b1, b2, eps, N, param.numel() // N)
     torch.testing.assert_close(gp.cpu(), rp, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(gm.cpu(), rm, rtol=1e-6, atol=1e-7)
-    torch.testing.assert_close(gv.cpu(), rv, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(gv.cpu(), rv, rtol=2e-6, atol=2e-7)
     # invisible rows are bit-identical to the input
     assert torch.equal(gp.cpu()[~vis], param[~vis]) and torch.equal(gm.cpu()[~vis], m[~vis])
 
