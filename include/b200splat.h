@@ -414,6 +414,65 @@ B200SPLAT_API int b200splat_compute_relocation(
     uint32_t N, const float *opacities, const float *scales, const int32_t *ratios,
     const float *binoms, int n_max, float *new_opacities, float *new_scales, void *stream);
 
+/* ------------------------------------------------------------------------------------
+ * f4  the training step either side of rasterization()
+ *     (R/utils/gsplat_utils/gsplat_trainer.py; R = splat_one checkout).
+ *
+ * sh_colors_staged_fwd/bwd   the fused colour stage of rasterization() (rendering.py:368-392,
+ *     as b200splat_sh_colors_fwd/bwd with per_view = 0) for ONE shared coefficient table
+ *     given either whole (`sh0 == NULL`, `rest` = coeffs [N,K,3]) or as the two tensors
+ *     splat_one optimises (`sh0` [N,1,3], `rest` = shN [N,K-1,3]) — which removes the
+ *     `torch.cat([sh0, shN], 1)` of gsplat_trainer.py:474 and its split backward.  Coefficient
+ *     rows move through shared memory (coalesced 128-bit global accesses); dynamic shared
+ *     memory per block = b200splat_sh_colors_staged_smem_bytes(K, split).  bwd conventions
+ *     (radii / colors == NULL: pre-masked cotangents; means camera window) as sh_colors_bwd;
+ *     v_sh0 [N,1,3] / v_rest are fully overwritten.
+ * splat_activations_fwd/bwd  scales = exp(scales_raw) [N,3], opacities = sigmoid(opacities_raw)
+ *     [N] (gsplat_trainer.py:458-459) and their VJPs (either v_*_raw may be NULL).
+ * l1_ssim_fwd/bwd            loss = l1_loss(img, target) (1 - lambda) + (1 - ssim) lambda with
+ *     ssim = fused_ssim(img, target, padding="valid") (gsplat_trainer.py:624-628; fused_ssim is
+ *     an un-vendored third-party dependency: standard SSIM, 11x11 Gaussian window sigma 1.5,
+ *     C1 = 0.01^2, C2 = 0.03^2, zero-padded statistics, mean over interior pixels).  img /
+ *     target / v_img / d_* are [C,H,W,3] fp32 (the layout rasterization() returns; no NCHW
+ *     copy).  fwd writes out3 = {loss, l1 mean, ssim mean} (device) and, when d_mu != NULL,
+ *     the three derivative maps the backward convolves; v_loss: device scalar or NULL (= 1).
+ *     workspace: b200splat_l1_ssim_workspace_bytes(C, H, W) bytes.
+ * ---------------------------------------------------------------------------------- */
+B200SPLAT_API size_t b200splat_sh_colors_staged_smem_bytes(uint32_t K, int split);
+
+B200SPLAT_API int b200splat_sh_colors_staged_fwd(
+    uint32_t C, uint32_t N, uint32_t K, uint32_t degrees_to_use,
+    const float *means, const float *campos, const float *sh0, const float *rest,
+    const int32_t *radii, float *colors, void *stream);
+
+B200SPLAT_API int b200splat_sh_colors_staged_bwd(
+    uint32_t C, uint32_t N, uint32_t K, uint32_t degrees_to_use,
+    const float *means, const float *campos, const float *sh0, const float *rest,
+    const int32_t *radii, const float *colors, const float *v_colors,
+    float *v_sh0, float *v_rest, float *v_means,
+    uint32_t means_cam_begin, uint32_t means_cam_end, void *stream);
+
+B200SPLAT_API int b200splat_splat_activations_fwd(
+    uint32_t N, const float *scales_raw, const float *opacities_raw,
+    float *scales, float *opacities, void *stream);
+
+B200SPLAT_API int b200splat_splat_activations_bwd(
+    uint32_t N, const float *scales, const float *opacities,
+    const float *v_scales, const float *v_opacities,
+    float *v_scales_raw, float *v_opacities_raw, void *stream);
+
+B200SPLAT_API size_t b200splat_l1_ssim_workspace_bytes(uint32_t C, uint32_t H, uint32_t W);
+
+B200SPLAT_API int b200splat_l1_ssim_fwd(
+    uint32_t C, uint32_t H, uint32_t W, const float *img, const float *target, float ssim_lambda,
+    float *d_mu, float *d_xx, float *d_xy, float *out3,
+    void *workspace, size_t workspace_bytes, void *stream);
+
+B200SPLAT_API int b200splat_l1_ssim_bwd(
+    uint32_t C, uint32_t H, uint32_t W, const float *img, const float *target, float ssim_lambda,
+    const float *d_mu, const float *d_xx, const float *d_xy, const float *v_loss,
+    float *v_img, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,7 @@ there is no CPU / PyTorch fallback.
 """
 from .optimizers import SelectiveAdam
 from .rendering import rasterization
+from .step import l1_ssim_loss, rasterize_splats, splat_activations
 from .wrapper import (
     accumulate,
     compute_relocation,
@@ -46,4 +47,7 @@ __all__ = [
     "SelectiveAdam",
     "spherical_harmonics",
     "spherical_harmonics_table",
+    "rasterize_splats",
+    "splat_activations",
+    "l1_ssim_loss",
 ]

@@ -17,7 +17,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("B200SPLAT_LIB", _PKG / "libb200splat.so"))
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 _P = c_void_p
 _U32 = c_uint32
@@ -77,6 +77,15 @@ SIGNATURES = {
     "b200splat_proj_bwd": (_I, [_U32, _U32, _P, _P, _P, _U32, _U32, _I, _P, _P, _P, _P, _P]),
     "b200splat_selective_adam_update": (_I, [_P, _P, _P, _P, _P, _F, _F, _F, _F, _U32, _U32, _P]),
     "b200splat_compute_relocation": (_I, [_U32, _P, _P, _P, _P, _I, _P, _P, _P]),
+    "b200splat_sh_colors_staged_smem_bytes": (c_size_t, [_U32, _I]),
+    "b200splat_sh_colors_staged_fwd": (_I, [_U32, _U32, _U32, _U32, _P, _P, _P, _P, _P, _P, _P]),
+    "b200splat_sh_colors_staged_bwd": (_I, [_U32, _U32, _U32, _U32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _U32, _U32,
+                                            _P]),
+    "b200splat_splat_activations_fwd": (_I, [_U32, _P, _P, _P, _P, _P]),
+    "b200splat_splat_activations_bwd": (_I, [_U32, _P, _P, _P, _P, _P, _P, _P]),
+    "b200splat_l1_ssim_workspace_bytes": (c_size_t, [_U32, _U32, _U32]),
+    "b200splat_l1_ssim_fwd": (_I, [_U32, _U32, _U32, _P, _P, _F, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "b200splat_l1_ssim_bwd": (_I, [_U32, _U32, _U32, _P, _P, _F, _P, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

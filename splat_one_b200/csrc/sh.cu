@@ -419,6 +419,240 @@ sh_colors_packed_bwd_kernel(uint32_t nnz, uint32_t N, uint32_t K, uint32_t deg, 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Staged ("split-capable") colour stage.  Same maths as sh_colors_fwd/bwd_kernel for ONE shared
+// coefficient table, but (1) the table may arrive as the two tensors splat_one optimises,
+// sh0 [N,1,3] and shN [N,K-1,3] (R/utils/gsplat_utils/gsplat_trainer.py:474 concatenates them
+// into [N,K,3] on every step: a 2 x 12K-byte-per-Gaussian copy forward and its split
+// backward), and (2) coefficient rows move through shared memory: a warp owns 32 consecutive
+// Gaussians, whose rows are one contiguous, 16-byte aligned span of global memory, so the span
+// is loaded / stored with fully coalesced 128-bit accesses and each lane picks its own row out
+// of shared memory (row stride chosen odd in units of the access width: conflict-free).
+// The thread-per-row kernels above touch 32 different cache lines per load instruction.
+//   sh0 != NULL: `rest` = shN, rows of R = 3 (K-1) floats, basis k >= 1 at column 3 (k-1)
+//   sh0 == NULL: `rest` = the whole table, rows of R = 3 K floats, basis k at column 3 k
+// ---------------------------------------------------------------------------------------
+constexpr int kStageWarps = 4;
+
+__host__ __device__ __forceinline__ uint32_t stage_row_stride(uint32_t R) {
+    return (R % 4 == 0) ? 4u * ((R / 4) | 1u) : (R | 1u);
+}
+
+// global span [g, g + cnt*R) -> smem rows of stride RS
+__device__ __forceinline__ void stage_rows_in(const float *__restrict__ g, uint32_t cnt, uint32_t R, uint32_t RS,
+                                              float *s, unsigned lane, bool aligned) {
+    const uint32_t total = cnt * R;
+    if (aligned && R % 4 == 0) {
+        const float4 *g4 = reinterpret_cast<const float4 *>(g);
+        float4 *s4 = reinterpret_cast<float4 *>(s);
+        const uint32_t R4 = R / 4, RS4 = RS / 4;
+        for (uint32_t i = lane; i < total / 4; i += 32) {
+            const uint32_t r = i / R4;
+            s4[r * RS4 + (i - r * R4)] = __ldg(g4 + i);
+        }
+    } else if (aligned && RS == R) {
+        const float4 *g4 = reinterpret_cast<const float4 *>(g);
+        float4 *s4 = reinterpret_cast<float4 *>(s);
+        const uint32_t nv = total / 4;
+        for (uint32_t i = lane; i < nv; i += 32) s4[i] = __ldg(g4 + i);
+        for (uint32_t i = 4 * nv + lane; i < total; i += 32) s[i] = __ldg(g + i);
+    } else {
+        for (uint32_t i = lane; i < total; i += 32) {
+            const uint32_t r = i / R;
+            s[r * RS + (i - r * R)] = __ldg(g + i);
+        }
+    }
+}
+
+// smem rows -> global span (streaming stores: the gradient is read once, by the optimizer)
+__device__ __forceinline__ void stage_rows_out(float *__restrict__ g, uint32_t cnt, uint32_t R, uint32_t RS,
+                                               const float *s, unsigned lane, bool aligned) {
+    const uint32_t total = cnt * R;
+    if (aligned && R % 4 == 0) {
+        float4 *g4 = reinterpret_cast<float4 *>(g);
+        const float4 *s4 = reinterpret_cast<const float4 *>(s);
+        const uint32_t R4 = R / 4, RS4 = RS / 4;
+        for (uint32_t i = lane; i < total / 4; i += 32) {
+            const uint32_t r = i / R4;
+            __stcs(g4 + i, s4[r * RS4 + (i - r * R4)]);
+        }
+    } else if (aligned && RS == R) {
+        float4 *g4 = reinterpret_cast<float4 *>(g);
+        const float4 *s4 = reinterpret_cast<const float4 *>(s);
+        const uint32_t nv = total / 4;
+        for (uint32_t i = lane; i < nv; i += 32) __stcs(g4 + i, s4[i]);
+        for (uint32_t i = 4 * nv + lane; i < total; i += 32) g[i] = s[i];
+    } else {
+        for (uint32_t i = lane; i < total; i += 32) {
+            const uint32_t r = i / R;
+            g[i] = s[r * RS + (i - r * R)];
+        }
+    }
+}
+
+// this lane's row: NF floats starting at column 0, smem -> registers
+template <int NF>
+__device__ __forceinline__ void row_to_regs(const float *srow, float (&c)[NF], bool vec) {
+    if (vec && NF % 4 == 0) {
+        const float4 *p = reinterpret_cast<const float4 *>(srow);
+#pragma unroll
+        for (int k = 0; k < NF / 4; k++) {
+            const float4 q = p[k];
+            c[4 * k] = q.x; c[4 * k + 1] = q.y; c[4 * k + 2] = q.z; c[4 * k + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < NF; k++) c[k] = srow[k];
+    }
+}
+
+// registers -> this lane's row: NF values, then zeros up to R
+template <int NF>
+__device__ __forceinline__ void regs_to_row(float *srow, const float (&c)[NF], uint32_t R, bool vec) {
+    if (vec && NF % 4 == 0) {
+        float4 *p = reinterpret_cast<float4 *>(srow);
+#pragma unroll
+        for (int k = 0; k < NF / 4; k++) p[k] = make_float4(c[4 * k], c[4 * k + 1], c[4 * k + 2], c[4 * k + 3]);
+        for (uint32_t k = NF / 4; k < R / 4; k++) p[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+#pragma unroll
+        for (int k = 0; k < NF; k++) srow[k] = c[k];
+        for (uint32_t k = NF; k < R; k++) srow[k] = 0.f;
+    }
+}
+
+// SPLIT: sh0/shN layout.  NF = floats of a staged row that the active bases use.
+template <int NB, bool SPLIT>
+__global__ void __launch_bounds__(32 * kStageWarps)
+sh_colors_staged_fwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, const float *__restrict__ means,
+                            const float *__restrict__ campos, const float *__restrict__ sh0,
+                            const float *__restrict__ rest, const int32_t *__restrict__ radii,
+                            float *__restrict__ colors) {
+    constexpr int K0 = SPLIT ? 1 : 0;
+    constexpr int NF = (NB - K0) * 3;
+    extern __shared__ float4 stage_smem4[];
+    const uint32_t R = (K - K0) * 3, RS = stage_row_stride(R);
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *s = reinterpret_cast<float *>(stage_smem4) + (size_t)warp * 32 * RS;
+    const uint32_t n0 = (blockIdx.x * kStageWarps + warp) * 32;
+    if (n0 >= N) return;  // warp-uniform
+    const uint32_t cnt = min(32u, N - n0), n = n0 + lane, c = blockIdx.y;
+    const uint64_t e = (uint64_t)c * N + n;
+    const bool act = lane < cnt && radii[e] > 0;
+    const bool aligned = (reinterpret_cast<uintptr_t>(rest) & 15) == 0;
+    float cf[NF > 0 ? NF : 1];
+    if (NF > 0) {
+        if (__any_sync(0xffffffffu, act)) stage_rows_in(rest + (size_t)n0 * R, cnt, R, RS, s, lane, aligned);
+        __syncwarp();
+        if (act) row_to_regs<(NF > 0 ? NF : 1)>(s + (size_t)lane * RS, cf, R % 4 == 0);
+    }
+    if (lane >= cnt) return;
+    float r = 0.f, g = 0.f, b = 0.f;
+    if (act) {
+        float dc[3] = {0.f, 0.f, 0.f};
+        if (SPLIT) { dc[0] = __ldg(sh0 + 3 * (size_t)n); dc[1] = __ldg(sh0 + 3 * (size_t)n + 1); dc[2] = __ldg(sh0 + 3 * (size_t)n + 2); }
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (NB > 1) {
+            const float dx = __ldg(means + 3 * (size_t)n) - campos[3 * c], dy = __ldg(means + 3 * (size_t)n + 1) - campos[3 * c + 1],
+                        dz = __ldg(means + 3 * (size_t)n + 2) - campos[3 * c + 2];
+            const float inorm = rsqrtf(dx * dx + dy * dy + dz * dz);
+            x = dx * inorm; y = dy * inorm; z = dz * inorm;
+        }
+        sh_for_each_basis<false>(deg, x, y, z, [&](int k, float B, float, float, float) {
+            if (SPLIT && k == 0) { r += B * dc[0]; g += B * dc[1]; b += B * dc[2]; }
+            else { r += B * cf[3 * (k - K0)]; g += B * cf[3 * (k - K0) + 1]; b += B * cf[3 * (k - K0) + 2]; }
+        });
+        r = fmaxf(r + 0.5f, 0.f); g = fmaxf(g + 0.5f, 0.f); b = fmaxf(b + 0.5f, 0.f);
+    }
+    colors[3 * e] = r; colors[3 * e + 1] = g; colors[3 * e + 2] = b;
+}
+
+// One lane per Gaussian, loop over cameras (like sh_colors_bwd_kernel: same conventions for
+// radii / colors == NULL and the means camera window); gradient rows leave through smem.
+template <int NB, bool SPLIT>
+__global__ void __launch_bounds__(32 * kStageWarps)
+sh_colors_staged_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, const float *__restrict__ means,
+                            const float *__restrict__ campos, const float *__restrict__ sh0,
+                            const float *__restrict__ rest, const int32_t *__restrict__ radii,
+                            const float *__restrict__ colors, const float *__restrict__ v_colors,
+                            float *__restrict__ v_sh0, float *__restrict__ v_rest, float *__restrict__ v_means,
+                            uint32_t means_cam_begin, uint32_t means_cam_end) {
+    constexpr int K0 = SPLIT ? 1 : 0;
+    constexpr int NF = (NB - K0) * 3;
+    constexpr int NFA = NF > 0 ? NF : 1;
+    extern __shared__ float4 stage_smem4[];
+    const uint32_t R = (K - K0) * 3, RS = stage_row_stride(R);
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *s = reinterpret_cast<float *>(stage_smem4) + (size_t)warp * 32 * RS;
+    const uint32_t n0 = (blockIdx.x * kStageWarps + warp) * 32;
+    if (n0 >= N) return;  // warp-uniform
+    const uint32_t cnt = min(32u, N - n0);
+    const bool mine = lane < cnt;
+    const uint32_t n = mine ? n0 + lane : n0;
+    const bool vec = R % 4 == 0;
+    const bool want_means = v_means != nullptr && NB > 1 && means_cam_begin < means_cam_end;
+    // the DC basis has no direction derivative: sh0 itself is never read here
+    float cf[NFA];
+    if (want_means && NF > 0) {
+        stage_rows_in(rest + (size_t)n0 * R, cnt, R, RS, s, lane, (reinterpret_cast<uintptr_t>(rest) & 15) == 0);
+        __syncwarp();
+        row_to_regs<NFA>(s + (size_t)lane * RS, cf, vec);
+        __syncwarp();  // the buffer is reused for the gradient rows below
+    }
+    float vc[NFA], vdc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < NFA; k++) vc[k] = 0.f;
+    float vmx = 0.f, vmy = 0.f, vmz = 0.f;
+    const float mx = __ldg(means + 3 * (size_t)n), my = __ldg(means + 3 * (size_t)n + 1), mz = __ldg(means + 3 * (size_t)n + 2);
+    for (uint32_t c = 0; c < C && mine; ++c) {
+        const uint64_t e = (uint64_t)c * N + n;
+        float vr = v_colors[3 * e], vg = v_colors[3 * e + 1], vb = v_colors[3 * e + 2];
+        if (colors != nullptr) {
+            vr = colors[3 * e] > 0.f ? vr : 0.f;
+            vg = colors[3 * e + 1] > 0.f ? vg : 0.f;
+            vb = colors[3 * e + 2] > 0.f ? vb : 0.f;
+        }
+        const bool visible = radii != nullptr ? (radii[e] > 0) : (vr != 0.f || vg != 0.f || vb != 0.f);
+        if (!visible) continue;
+        float x = 0.f, y = 0.f, z = 0.f, inorm = 0.f;
+        if (NB > 1) {
+            const float dx = mx - campos[3 * c], dy = my - campos[3 * c + 1], dz = mz - campos[3 * c + 2];
+            inorm = rsqrtf(dx * dx + dy * dy + dz * dz);
+            x = dx * inorm; y = dy * inorm; z = dz * inorm;
+        }
+        if (want_means && c >= means_cam_begin && c < means_cam_end) {
+            float vx = 0.f, vy = 0.f, vz = 0.f;
+            sh_for_each_basis<true>(deg, x, y, z, [&](int k, float B, float Bx, float By, float Bz) {
+                if (SPLIT && k == 0) { vdc[0] += B * vr; vdc[1] += B * vg; vdc[2] += B * vb; return; }  // dB0 = 0
+                const int j = 3 * (k - K0);
+                vc[j] += B * vr; vc[j + 1] += B * vg; vc[j + 2] += B * vb;
+                const float w = cf[j] * vr + cf[j + 1] * vg + cf[j + 2] * vb;
+                vx += Bx * w; vy += By * w; vz += Bz * w;
+            });
+            const float d = vx * x + vy * y + vz * z;
+            vmx += (vx - d * x) * inorm; vmy += (vy - d * y) * inorm; vmz += (vz - d * z) * inorm;
+        } else {
+            sh_for_each_basis<false>(deg, x, y, z, [&](int k, float B, float, float, float) {
+                if (SPLIT && k == 0) { vdc[0] += B * vr; vdc[1] += B * vg; vdc[2] += B * vb; return; }
+                const int j = 3 * (k - K0);
+                vc[j] += B * vr; vc[j + 1] += B * vg; vc[j + 2] += B * vb;
+            });
+        }
+    }
+    if (R > 0) {
+        if (mine) {
+            if constexpr (NF > 0) regs_to_row<NF>(s + (size_t)lane * RS, vc, R, vec);
+            else for (uint32_t k = 0; k < R; k++) s[(size_t)lane * RS + k] = 0.f;
+        }
+        __syncwarp();
+        stage_rows_out(v_rest + (size_t)n0 * R, cnt, R, RS, s, lane, (reinterpret_cast<uintptr_t>(v_rest) & 15) == 0);
+    }
+    if (!mine) return;
+    if (SPLIT) { v_sh0[3 * (size_t)n] = vdc[0]; v_sh0[3 * (size_t)n + 1] = vdc[1]; v_sh0[3 * (size_t)n + 2] = vdc[2]; }
+    if (v_means != nullptr) { v_means[3 * (size_t)n] = vmx; v_means[3 * (size_t)n + 1] = vmy; v_means[3 * (size_t)n + 2] = vmz; }
+}
+
 }  // namespace b2s
 
 using namespace b2s;
@@ -562,6 +796,98 @@ extern "C" int b200splat_sh_colors_packed_bwd(uint32_t nnz, uint32_t C, uint32_t
         default: B2S_SHP(25); break;
     }
 #undef B2S_SHP
+    B2S_CHECK_LAUNCH(where);
+    return 0;
+}
+
+// ---- staged colour stage (shared table, optionally split into sh0 / shN) ------------------
+extern "C" size_t b200splat_sh_colors_staged_smem_bytes(uint32_t K, int split) {
+    const uint32_t R = (K - (split ? 1 : 0)) * 3;
+    return (size_t)kStageWarps * 32 * stage_row_stride(R) * sizeof(float);
+}
+
+template <bool SPLIT>
+static int launch_staged_fwd(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, const float *means, const float *campos,
+                             const float *sh0, const float *rest, const int32_t *radii, float *colors, size_t smem,
+                             cudaStream_t st) {
+    const dim3 grid(div_up(N, 32 * kStageWarps), C);
+#define B2S_SHS(NBV)                                                                                                 \
+    do {                                                                                                             \
+        auto kern = sh_colors_staged_fwd_kernel<NBV, SPLIT>;                                                         \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+        kern<<<grid, 32 * kStageWarps, smem, st>>>(C, N, K, deg, means, campos, sh0, rest, radii, colors);           \
+    } while (0)
+    switch (deg) {
+        case 0: B2S_SHS(1); break;
+        case 1: B2S_SHS(4); break;
+        case 2: B2S_SHS(9); break;
+        case 3: B2S_SHS(16); break;
+        default: B2S_SHS(25); break;
+    }
+#undef B2S_SHS
+    return 0;
+}
+
+template <bool SPLIT>
+static int launch_staged_bwd(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, const float *means, const float *campos,
+                             const float *sh0, const float *rest, const int32_t *radii, const float *colors,
+                             const float *v_colors, float *v_sh0, float *v_rest, float *v_means, uint32_t cb,
+                             uint32_t ce, size_t smem, cudaStream_t st) {
+    const unsigned grid = div_up(N, 32 * kStageWarps);
+#define B2S_SHS(NBV)                                                                                                 \
+    do {                                                                                                             \
+        auto kern = sh_colors_staged_bwd_kernel<NBV, SPLIT>;                                                         \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+        kern<<<grid, 32 * kStageWarps, smem, st>>>(C, N, K, deg, means, campos, sh0, rest, radii, colors, v_colors,  \
+                                                   v_sh0, v_rest, v_means, cb, ce);                                  \
+    } while (0)
+    switch (deg) {
+        case 0: B2S_SHS(1); break;
+        case 1: B2S_SHS(4); break;
+        case 2: B2S_SHS(9); break;
+        case 3: B2S_SHS(16); break;
+        default: B2S_SHS(25); break;
+    }
+#undef B2S_SHS
+    return 0;
+}
+
+extern "C" int b200splat_sh_colors_staged_fwd(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, const float *means,
+                                              const float *campos, const float *sh0, const float *rest,
+                                              const int32_t *radii, float *colors, void *stream) {
+    const char *where = "b200splat_sh_colors_staged_fwd";
+    B2S_REQUIRE(deg <= 4, where, "degrees_to_use must be <= 4");
+    B2S_REQUIRE((deg + 1) * (deg + 1) <= K, where, "K too small for degrees_to_use");
+    if ((uint64_t)C * N == 0) return 0;
+    B2S_REQUIRE(C <= 65535, where, "more than 65535 cameras");
+    const size_t smem = b200splat_sh_colors_staged_smem_bytes(K, sh0 != nullptr);
+    B2S_REQUIRE(smem <= 200 * 1024, where, "K too large for the staged colour kernels");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (sh0 != nullptr) launch_staged_fwd<true>(C, N, K, deg, means, campos, sh0, rest, radii, colors, smem, st);
+    else launch_staged_fwd<false>(C, N, K, deg, means, campos, sh0, rest, radii, colors, smem, st);
+    B2S_CHECK_LAUNCH(where);
+    return 0;
+}
+
+extern "C" int b200splat_sh_colors_staged_bwd(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, const float *means,
+                                              const float *campos, const float *sh0, const float *rest,
+                                              const int32_t *radii, const float *colors, const float *v_colors,
+                                              float *v_sh0, float *v_rest, float *v_means, uint32_t means_cam_begin,
+                                              uint32_t means_cam_end, void *stream) {
+    const char *where = "b200splat_sh_colors_staged_bwd";
+    B2S_REQUIRE(deg <= 4, where, "degrees_to_use must be <= 4");
+    B2S_REQUIRE((deg + 1) * (deg + 1) <= K, where, "K too small for degrees_to_use");
+    if (N == 0) return 0;
+    B2S_REQUIRE((sh0 != nullptr) == (v_sh0 != nullptr), where, "sh0 and v_sh0 go together");
+    const size_t smem = b200splat_sh_colors_staged_smem_bytes(K, sh0 != nullptr);
+    B2S_REQUIRE(smem <= 200 * 1024, where, "K too large for the staged colour kernels");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (sh0 != nullptr)
+        launch_staged_bwd<true>(C, N, K, deg, means, campos, sh0, rest, radii, colors, v_colors, v_sh0, v_rest, v_means,
+                                means_cam_begin, means_cam_end, smem, st);
+    else
+        launch_staged_bwd<false>(C, N, K, deg, means, campos, sh0, rest, radii, colors, v_colors, v_sh0, v_rest,
+                                 v_means, means_cam_begin, means_cam_end, smem, st);
     B2S_CHECK_LAUNCH(where);
     return 0;
 }

@@ -27,7 +27,9 @@ from .wrapper import (
     isect_tiles_and_offsets,
     rasterize_to_pixels,
     sh_view_colors,
+    sh_view_colors_split,
     spherical_harmonics,
+    staged_colors_supported,
 )
 
 
@@ -70,6 +72,22 @@ def rasterization(
     """
     meta: Dict = {}
 
+    # extension (splat_one_b200/step.py): `colors=(sh0, shN)` is the SH table of
+    # gsplat_trainer.py:474 before its `torch.cat`; the un-packed colour stage reads the two
+    # tensors in place, every other configuration concatenates as the caller would have
+    sh_split = None
+    if isinstance(colors, (tuple, list)):
+        sh0, shN = colors
+        assert sh_degree is not None, "a split (sh0, shN) table needs sh_degree"
+        assert sh0.dim() == 3 and sh0.shape[1:] == (1, 3) and shN.dim() == 3 and shN.shape[2] == 3, (sh0.shape, shN.shape)
+        assert sh0.shape[0] == shN.shape[0], (sh0.shape, shN.shape)
+        if (not packed and not viewmats.requires_grad and sh0.is_cuda
+                and staged_colors_supported(1 + shN.shape[1], True)):
+            sh_split = (sh0, shN)
+            colors = sh0  # placeholder for the shape asserts below
+        else:
+            colors = torch.cat([sh0, shN], 1)
+
     N = means.shape[0]
     C = viewmats.shape[0]
     assert means.shape == (N, 3), means.shape
@@ -95,7 +113,7 @@ def rasterization(
         assert (colors.dim() == 3 and colors.shape[0] == N and colors.shape[2] == 3) or (
             colors.dim() == 4 and colors.shape[:2] == (C, N) and colors.shape[3] == 3
         ), colors.shape
-        assert (sh_degree + 1) ** 2 <= colors.shape[-2], colors.shape
+        assert (sh_degree + 1) ** 2 <= (colors.shape[-2] if sh_split is None else 1 + sh_split[1].shape[1]), colors.shape
 
     if absgrad:
         assert not distributed, "AbsGrad is not supported in distributed mode."
@@ -141,7 +159,9 @@ def rasterization(
         else:
             colors = colors.expand(C, -1, -1) if colors.dim() == 2 else colors
     else:
-        if packed and not viewmats.requires_grad:
+        if sh_split is not None:
+            colors = sh_view_colors_split(sh_degree, means, viewmats, sh_split[0], sh_split[1], radii)  # [C, N, 3]
+        elif packed and not viewmats.requires_grad:
             # same maths, one fused kernel per direction over the COO rows
             colors = sh_view_colors_packed(sh_degree, means, viewmats, colors, camera_ids, gaussian_ids)  # [nnz, 3]
         elif viewmats.requires_grad:

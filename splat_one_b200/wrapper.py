@@ -52,7 +52,8 @@ class _Profiler:
         "isect_sort": 0, "isect_sorted": 5, "isect_offset_encode": 1, "rasterize_pack": 1, "rasterize_fwd": 1, "rasterize_bwd": 1,
         "raster_indices_count": 2, "raster_indices_fill": 1, "quat_scale_to_covar_preci_fwd": 1,
         "quat_scale_to_covar_preci_bwd": 1, "world_to_cam_fwd": 1, "world_to_cam_bwd": 1, "proj_fwd": 1, "proj_bwd": 1,
-        "selective_adam_update": 1, "compute_relocation": 1,
+        "selective_adam_update": 1, "compute_relocation": 1, "sh_colors_staged_fwd": 1, "sh_colors_staged_bwd": 1,
+        "splat_activations_fwd": 1, "splat_activations_bwd": 1, "l1_ssim_fwd": 2, "l1_ssim_bwd": 1,
     }
 
     def __init__(self):
@@ -347,6 +348,80 @@ class _ShViewColors(torch.autograd.Function):
                    _ptr(coeffs), _ptr(radii), _ptr(colors), _ptr(v_colors), _ptr(v_coeffs),
                    _ptr(v_means), 0, C)
         return None, v_means, None, (v_coeffs if ctx.needs_input_grad[3] else None), None
+
+
+def sh_view_colors_split(sh_degree: int, means: Tensor, viewmats: Tensor, sh0: Optional[Tensor], rest: Tensor,
+                         radii: Tensor) -> Tensor:
+    """`sh_view_colors` for ONE shared table given as the two tensors splat_one optimises,
+    `sh0 [N,1,3]` and `rest = shN [N,K-1,3]` — i.e. `sh_view_colors(deg, means, viewmats,
+    torch.cat([sh0, shN], 1), radii)` (R/utils/gsplat_utils/gsplat_trainer.py:474) without the
+    concatenation and its split backward.  With `sh0=None`, `rest` is the whole [N,K,3] table.
+    Coefficient rows are staged through shared memory (csrc/sh.cu, staged kernels)."""
+    C, N = radii.shape
+    assert means.shape == (N, 3), means.shape
+    K = rest.shape[1] + (0 if sh0 is None else 1)
+    assert rest.dim() == 3 and rest.shape[0] == N and rest.shape[2] == 3, rest.shape
+    assert sh0 is None or sh0.shape == (N, 1, 3), sh0.shape
+    assert (sh_degree + 1) ** 2 <= K, (sh_degree, K)
+    campos = camera_centers(viewmats)
+    return _ShViewColorsStaged.apply(sh_degree, means.contiguous(), campos,
+                                     None if sh0 is None else sh0.contiguous(), rest.contiguous(), radii.contiguous())
+
+
+def staged_colors_supported(K: int, split: bool) -> bool:
+    """The staged kernels keep 128 coefficient rows per block in shared memory."""
+    return get_lib().b200splat_sh_colors_staged_smem_bytes(K, int(split)) <= 200 * 1024
+
+
+class _ShViewColorsStaged(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sh_degree, means, campos, sh0, rest, radii):
+        _check_cuda(means, campos, sh0, rest, radii)
+        _f32(means), _f32(sh0), _f32(rest)
+        lib = get_lib()
+        C, N = radii.shape
+        K = rest.shape[1] + (0 if sh0 is None else 1)
+        colors = torch.empty((C, N, 3), device=means.device, dtype=torch.float32)
+        if C * N:
+            native("sh_colors_staged_fwd", lib, means.device, C, N, K, sh_degree, _ptr(means), _ptr(campos), _ptr(sh0),
+                   _ptr(rest), _ptr(radii), _ptr(colors))
+        ctx.save_for_backward(means, campos, sh0, rest, radii, colors)
+        ctx.sh_degree = sh_degree
+        return colors
+
+    @staticmethod
+    def backward(ctx, v_colors):
+        means, campos, sh0, rest, radii, colors = ctx.saved_tensors
+        lib = get_lib()
+        C, N = radii.shape
+        K = rest.shape[1] + (0 if sh0 is None else 1)
+        v_sh0 = _grad_out(sh0) if sh0 is not None else None
+        v_rest = _grad_out(rest)
+        v_means = torch.empty_like(means) if ctx.needs_input_grad[1] else None
+        v_colors = v_colors.contiguous()
+        cp = _CAMERA_PARALLEL.get("group", None) if _CAMERA_PARALLEL else None
+        if cp is not None and N:
+            # camera-parallel exchange, as in _ShViewColors.backward
+            import torch.distributed as dist
+
+            W, r = dist.get_world_size(cp), dist.get_rank(cp)
+            g_local = torch.where(colors > 0, v_colors, torch.zeros_like(v_colors))
+            g_all = torch.empty((W * C, N, 3), device=means.device, dtype=torch.float32)
+            campos_all = torch.empty((W * C, 3), device=means.device, dtype=torch.float32)
+            dist.all_gather_into_tensor(g_all, g_local, group=cp)
+            dist.all_gather_into_tensor(campos_all, campos.contiguous(), group=cp)
+            native("sh_colors_staged_bwd", lib, means.device, W * C, N, K, ctx.sh_degree, _ptr(means),
+                   _ptr(campos_all), _ptr(sh0), _ptr(rest), None, None, _ptr(g_all), _ptr(v_sh0), _ptr(v_rest),
+                   _ptr(v_means), r * C, (r + 1) * C)
+            _CAMERA_PARALLEL["reduced"].add(rest.data_ptr())
+            if sh0 is not None:
+                _CAMERA_PARALLEL["reduced"].add(sh0.data_ptr())
+        elif N:
+            native("sh_colors_staged_bwd", lib, means.device, C, N, K, ctx.sh_degree, _ptr(means), _ptr(campos),
+                   _ptr(sh0), _ptr(rest), _ptr(radii), _ptr(colors), _ptr(v_colors), _ptr(v_sh0), _ptr(v_rest),
+                   _ptr(v_means), 0, C)
+        return (None, v_means, None, (v_sh0 if sh0 is not None and ctx.needs_input_grad[3] else None),
+                (v_rest if ctx.needs_input_grad[4] else None), None)
 
 
 def sh_view_colors_packed(sh_degree: int, means: Tensor, viewmats: Tensor, coeffs: Tensor, camera_ids: Tensor,
