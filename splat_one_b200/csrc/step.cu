@@ -61,97 +61,160 @@ static Window make_window() {
     return w;
 }
 
-// stage the (kHalo x kHalo x 3) apron tile of one [H,W,3] image, zero outside the image
-__device__ __forceinline__ void stage_tile(const float *__restrict__ img, uint32_t H, uint32_t W, int x0, int y0,
-                                           float *s) {
-    for (int i = threadIdx.x; i < kHalo * kRowF; i += blockDim.x) {
-        const int r = i / kRowF, f = i - r * kRowF;
-        const int px3 = f / 3, y = y0 - kHalf + r, x = x0 - kHalf + px3;
-        float v = 0.f;
-        if (y >= 0 && y < (int)H && x >= 0 && x < (int)W) v = __ldg(img + ((size_t)y * W + x) * 3 + (f - 3 * px3));
-        s[i] = v;
+// Shared-memory geometry.  A staged apron row holds kHalo pixels x 3 channels; rows are padded
+// to an odd number of elements so that lanes walking DOWN the rows (the horizontal pass) hit
+// distinct banks, and the horizontal pass writes its results transposed ([column][row], odd
+// row count) so that the vertical pass, whose lanes walk ACROSS the columns, does too.
+constexpr int kRowS = kRowF + 1;             // 127 elements per staged row
+constexpr int kColS = kHalo + 1;             // 43 rows per transposed column
+constexpr int kRun = 6;                      // consecutive outputs per thread, horizontal pass
+constexpr int kRunsPerRow = 6;               // 6 runs of 6 cover the 32 columns (starts 0,6,11,16,21,26: the
+                                             // overlapping columns are computed twice with identical results)
+constexpr int kRowsPerThread = 4;            // consecutive outputs per thread, vertical pass
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ int run_start(int i) { return i < 2 ? 6 * i : 5 * i + 1; }
+
+// Stage the apron tile of up to three [H,W,3] images (zero outside the image): elements of
+// images A and B interleaved as float2, image C (optional) as float.
+template <bool WITH_C>
+__device__ __forceinline__ void stage_tiles(const float *__restrict__ A, const float *__restrict__ B,
+                                            const float *__restrict__ Cc, uint32_t H, uint32_t W, int x0, int y0,
+                                            float2 *s_ab, float *s_c) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int off[4];   // element offset inside an image row, or -1 when the column is outside the image
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int f = lane + 32 * i, px3 = f / 3, x = x0 - kHalf + px3;
+        off[i] = (f < kRowF && x >= 0 && x < (int)W) ? x * 3 + (f - 3 * px3) : -1;
+    }
+    for (int r = warp; r < kHalo; r += 8) {
+        const int y = y0 - kHalf + r;
+        const bool row_ok = y >= 0 && y < (int)H;
+        const size_t base = (size_t)(row_ok ? y : 0) * W * 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int f = lane + 32 * i;
+            if (f >= kRowF) continue;
+            float a = 0.f, b = 0.f, c = 0.f;
+            if (row_ok && off[i] >= 0) {
+                a = __ldg(A + base + off[i]);
+                b = __ldg(B + base + off[i]);
+                if (WITH_C) c = __ldg(Cc + base + off[i]);
+            }
+            s_ab[r * kRowS + f] = f2(a, b);
+            if (WITH_C) s_c[r * kRowS + f] = c;
+        }
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 l1_ssim_fwd_kernel(uint32_t H, uint32_t W, const float *__restrict__ img, const float *__restrict__ tgt,
                    const Window win, float *__restrict__ d_mu, float *__restrict__ d_xx, float *__restrict__ d_xy,
                    float *__restrict__ partials) {
-    extern __shared__ float smem[];
-    float *s_x = smem;                          // [kHalo][kRowF]
-    float *s_y = s_x + kHalo * kRowF;
-    float *s_h = s_y + kHalo * kRowF;           // [5][kHalo][kTile]
+    extern __shared__ float2 smem2[];
+    float2 *s_ab = smem2;                        // [kHalo][kRowS]   {img, tgt}
+    float2 *s_m = s_ab + kHalo * kRowS;          // [kTile][kColS]   {sum g a, sum g b}
+    float2 *s_q = s_m + kTile * kColS;           // [kTile][kColS]   {sum g a², sum g b²}
+    float *s_p = reinterpret_cast<float *>(s_q + kTile * kColS);  // [kTile][kColS]  sum g a b
     const uint32_t cam = blockIdx.z;
     const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
     const size_t img_off = (size_t)cam * H * W * 3;
-    stage_tile(img + img_off, H, W, x0, y0, s_x);
-    stage_tile(tgt + img_off, H, W, x0, y0, s_y);
+    stage_tiles<false>(img + img_off, tgt + img_off, nullptr, H, W, x0, y0, s_ab, nullptr);
     __syncthreads();
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int px = x0 + tx;
     float l1 = 0.f, ss = 0.f;
-    float o_mu[4][3], o_xx[4][3], o_xy[4][3];
+    float o_mu[kRowsPerThread][3], o_xx[kRowsPerThread][3], o_xy[kRowsPerThread][3];
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
-        // horizontal pass: 5 running statistics per (row, column)
-        for (int i = threadIdx.x; i < kHalo * kTile; i += blockDim.x) {
-            const int r = i >> 5, x = i & 31;
-            float hx = 0.f, hy = 0.f, hxx = 0.f, hyy = 0.f, hxy = 0.f;
+        // horizontal pass: thread = (apron row r, run of kRun output columns); packed fp32x2
+        // accumulation of the {a, b} and {a², b²} pairs (FFMA2), scalar a·b
+        if (threadIdx.x < kHalo * kRunsPerRow) {
+            const int r = threadIdx.x % kHalo, xr = run_start(threadIdx.x / kHalo);
+            float2 hm[kRun], hq[kRun];
+            float hp[kRun];
 #pragma unroll
-            for (int k = 0; k < kWin; ++k) {
-                const float a = s_x[r * kRowF + (x + k) * 3 + ch], b = s_y[r * kRowF + (x + k) * 3 + ch];
-                const float g = win.g[k], ga = g * a, gb = g * b;
-                hx += ga; hy += gb; hxx = fmaf(ga, a, hxx); hyy = fmaf(gb, b, hyy); hxy = fmaf(ga, b, hxy);
+            for (int j = 0; j < kRun; ++j) { hm[j] = f2(0.f, 0.f); hq[j] = f2(0.f, 0.f); hp[j] = 0.f; }
+#pragma unroll
+            for (int e = 0; e < kRun + kWin - 1; ++e) {
+                const float2 ab = s_ab[r * kRowS + (xr + e) * 3 + ch];
+                const float2 sq = __fmul2_rn(ab, ab);
+                const float pr = ab.x * ab.y;
+#pragma unroll
+                for (int j = 0; j < kRun; ++j) {
+                    const int k = e - j;   // tap index of element e for output j
+                    if (k >= 0 && k < kWin) {
+                        const float g = win.g[k];
+                        hm[j] = __ffma2_rn(f2(g, g), ab, hm[j]);
+                        hq[j] = __ffma2_rn(f2(g, g), sq, hq[j]);
+                        hp[j] = fmaf(g, pr, hp[j]);
+                    }
+                }
             }
-            s_h[(0 * kHalo + r) * kTile + x] = hx;
-            s_h[(1 * kHalo + r) * kTile + x] = hy;
-            s_h[(2 * kHalo + r) * kTile + x] = hxx;
-            s_h[(3 * kHalo + r) * kTile + x] = hyy;
-            s_h[(4 * kHalo + r) * kTile + x] = hxy;
+#pragma unroll
+            for (int j = 0; j < kRun; ++j) {
+                s_m[(xr + j) * kColS + r] = hm[j];
+                s_q[(xr + j) * kColS + r] = hq[j];
+                s_p[(xr + j) * kColS + r] = hp[j];
+            }
         }
         __syncthreads();
+        // vertical pass: thread = (column tx, kRowsPerThread consecutive rows)
+        {
+            const int ly0 = ty * kRowsPerThread;
+            float2 vm[kRowsPerThread], vq[kRowsPerThread];
+            float vp[kRowsPerThread];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int ly = ty + 8 * j, py = y0 + ly;
-            float mu1 = 0.f, mu2 = 0.f, exx = 0.f, eyy = 0.f, exy = 0.f;
+            for (int j = 0; j < kRowsPerThread; ++j) { vm[j] = f2(0.f, 0.f); vq[j] = f2(0.f, 0.f); vp[j] = 0.f; }
 #pragma unroll
-            for (int k = 0; k < kWin; ++k) {
-                const float g = win.g[k];
-                mu1 = fmaf(g, s_h[(0 * kHalo + ly + k) * kTile + tx], mu1);
-                mu2 = fmaf(g, s_h[(1 * kHalo + ly + k) * kTile + tx], mu2);
-                exx = fmaf(g, s_h[(2 * kHalo + ly + k) * kTile + tx], exx);
-                eyy = fmaf(g, s_h[(3 * kHalo + ly + k) * kTile + tx], eyy);
-                exy = fmaf(g, s_h[(4 * kHalo + ly + k) * kTile + tx], exy);
+            for (int e = 0; e < kRowsPerThread + kWin - 1; ++e) {
+                const float2 m = s_m[tx * kColS + ly0 + e], q = s_q[tx * kColS + ly0 + e];
+                const float p = s_p[tx * kColS + ly0 + e];
+#pragma unroll
+                for (int j = 0; j < kRowsPerThread; ++j) {
+                    const int k = e - j;
+                    if (k >= 0 && k < kWin) {
+                        const float g = win.g[k];
+                        vm[j] = __ffma2_rn(f2(g, g), m, vm[j]);
+                        vq[j] = __ffma2_rn(f2(g, g), q, vq[j]);
+                        vp[j] = fmaf(g, p, vp[j]);
+                    }
+                }
             }
-            const bool inside = px < (int)W && py < (int)H;
-            const bool valid = inside && px >= kHalf && py >= kHalf && px + kHalf < (int)W && py + kHalf < (int)H;
-            float dmu = 0.f, dxx = 0.f, dxy = 0.f;
-            if (valid) {
-                const float A = mu1 * mu1 + mu2 * mu2 + kC1;
-                const float B = (exx - mu1 * mu1) + (eyy - mu2 * mu2) + kC2;
-                const float Cn = 2.f * mu1 * mu2 + kC1;
-                const float Dn = 2.f * (exy - mu1 * mu2) + kC2;
-                const float iA = 1.f / A, iB = 1.f / B, iAB = iA * iB;
-                const float val = Cn * Dn * iAB;
-                ss += val;
-                // derivatives of val w.r.t. (mu1, E[x²], E[xy]) as independent variables
-                dxx = -val * iB;
-                dxy = 2.f * Cn * iAB;
-                dmu = 2.f * (mu2 * (Dn - Cn) * iAB + mu1 * val * (iB - iA));
+#pragma unroll
+            for (int j = 0; j < kRowsPerThread; ++j) {
+                const int ly = ly0 + j, py = y0 + ly;
+                const float mu1 = vm[j].x, mu2 = vm[j].y, exx = vq[j].x, eyy = vq[j].y, exy = vp[j];
+                const bool inside = px < (int)W && py < (int)H;
+                const bool valid = inside && px >= kHalf && py >= kHalf && px + kHalf < (int)W && py + kHalf < (int)H;
+                float dmu = 0.f, dxx = 0.f, dxy = 0.f;
+                if (valid) {
+                    const float A = mu1 * mu1 + mu2 * mu2 + kC1;
+                    const float B = (exx - mu1 * mu1) + (eyy - mu2 * mu2) + kC2;
+                    const float Cn = 2.f * mu1 * mu2 + kC1;
+                    const float Dn = 2.f * (exy - mu1 * mu2) + kC2;
+                    const float iA = 1.f / A, iB = 1.f / B, iAB = iA * iB;
+                    const float val = Cn * Dn * iAB;
+                    ss += val;
+                    // derivatives of val w.r.t. (mu1, E[x²], E[xy]) as independent variables
+                    dxx = -val * iB;
+                    dxy = 2.f * Cn * iAB;
+                    dmu = 2.f * (mu2 * (Dn - Cn) * iAB + mu1 * val * (iB - iA));
+                }
+                if (inside) {
+                    const float2 ab = s_ab[(ly + kHalf) * kRowS + (tx + kHalf) * 3 + ch];
+                    l1 += fabsf(ab.x - ab.y);
+                }
+                o_mu[j][ch] = dmu; o_xx[j][ch] = dxx; o_xy[j][ch] = dxy;
             }
-            if (inside) {
-                const float a = s_x[(ly + kHalf) * kRowF + (tx + kHalf) * 3 + ch];
-                const float b = s_y[(ly + kHalf) * kRowF + (tx + kHalf) * 3 + ch];
-                l1 += fabsf(a - b);
-            }
-            o_mu[j][ch] = dmu; o_xx[j][ch] = dxx; o_xy[j][ch] = dxy;
         }
         __syncthreads();
     }
     if (d_mu != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int py = y0 + ty + 8 * j;
+        for (int j = 0; j < kRowsPerThread; ++j) {
+            const int py = y0 + ty * kRowsPerThread + j;
             if (px < (int)W && py < (int)H) {
                 const size_t o = img_off + ((size_t)py * W + px) * 3;
 #pragma unroll
@@ -199,67 +262,93 @@ l1_ssim_finalize_kernel(uint32_t n_blocks, const float *__restrict__ partials, d
 
 // v_img = v_loss * [ (1-lambda)/n_l1 * sign(img - tgt)
 //                    - lambda/n_ssim * (G*d_mu + 2 img (G*d_xx) + tgt (G*d_xy)) ]      (G* = zero-padded window)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 l1_ssim_bwd_kernel(uint32_t H, uint32_t W, const float *__restrict__ img, const float *__restrict__ tgt,
                    const Window win, const float *__restrict__ d_mu, const float *__restrict__ d_xx,
                    const float *__restrict__ d_xy, const float *__restrict__ v_loss, float s_l1, float s_ssim,
                    float *__restrict__ v_img) {
-    extern __shared__ float smem[];
-    float *s_m[3] = {smem, smem + kHalo * kRowF, smem + 2 * kHalo * kRowF};
-    float *s_h = smem + 3 * kHalo * kRowF;      // [3][kHalo][kTile]
+    extern __shared__ float2 smem2[];
+    float2 *s_ab = smem2;                        // [kHalo][kRowS]  {d_mu, d_xx}
+    float2 *s_m = s_ab + kHalo * kRowS;          // [kTile][kColS]  horizontal sums of the pair
+    float *s_c = reinterpret_cast<float *>(s_m + kTile * kColS);   // [kHalo][kRowS]  d_xy
+    float *s_p = s_c + kHalo * kRowS;            // [kTile][kColS]
     const uint32_t cam = blockIdx.z;
     const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
     const size_t img_off = (size_t)cam * H * W * 3;
-    stage_tile(d_mu + img_off, H, W, x0, y0, s_m[0]);
-    stage_tile(d_xx + img_off, H, W, x0, y0, s_m[1]);
-    stage_tile(d_xy + img_off, H, W, x0, y0, s_m[2]);
+    stage_tiles<true>(d_mu + img_off, d_xx + img_off, d_xy + img_off, H, W, x0, y0, s_ab, s_c);
     __syncthreads();
     const float gl = v_loss != nullptr ? __ldg(v_loss) : 1.f;
     const float k_l1 = gl * s_l1, k_ss = gl * s_ssim;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int px = x0 + tx;
-    float out[4][3];
+    float out[kRowsPerThread][3];
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
-        for (int i = threadIdx.x; i < kHalo * kTile; i += blockDim.x) {
-            const int r = i >> 5, x = i & 31;
-            float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+        if (threadIdx.x < kHalo * kRunsPerRow) {
+            const int r = threadIdx.x % kHalo, xr = run_start(threadIdx.x / kHalo);
+            float2 hm[kRun];
+            float hp[kRun];
 #pragma unroll
-            for (int k = 0; k < kWin; ++k) {
-                const float g = win.g[k];
-                const int o = r * kRowF + (x + k) * 3 + ch;
-                h0 = fmaf(g, s_m[0][o], h0); h1 = fmaf(g, s_m[1][o], h1); h2 = fmaf(g, s_m[2][o], h2);
+            for (int j = 0; j < kRun; ++j) { hm[j] = f2(0.f, 0.f); hp[j] = 0.f; }
+#pragma unroll
+            for (int e = 0; e < kRun + kWin - 1; ++e) {
+                const float2 ab = s_ab[r * kRowS + (xr + e) * 3 + ch];
+                const float c = s_c[r * kRowS + (xr + e) * 3 + ch];
+#pragma unroll
+                for (int j = 0; j < kRun; ++j) {
+                    const int k = e - j;
+                    if (k >= 0 && k < kWin) {
+                        const float g = win.g[k];
+                        hm[j] = __ffma2_rn(f2(g, g), ab, hm[j]);
+                        hp[j] = fmaf(g, c, hp[j]);
+                    }
+                }
             }
-            s_h[(0 * kHalo + r) * kTile + x] = h0;
-            s_h[(1 * kHalo + r) * kTile + x] = h1;
-            s_h[(2 * kHalo + r) * kTile + x] = h2;
+#pragma unroll
+            for (int j = 0; j < kRun; ++j) {
+                s_m[(xr + j) * kColS + r] = hm[j];
+                s_p[(xr + j) * kColS + r] = hp[j];
+            }
         }
         __syncthreads();
+        {
+            const int ly0 = ty * kRowsPerThread;
+            float2 vm[kRowsPerThread];
+            float vp[kRowsPerThread];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int ly = ty + 8 * j, py = y0 + ly;
-            float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+            for (int j = 0; j < kRowsPerThread; ++j) { vm[j] = f2(0.f, 0.f); vp[j] = 0.f; }
 #pragma unroll
-            for (int k = 0; k < kWin; ++k) {
-                const float g = win.g[k];
-                c0 = fmaf(g, s_h[(0 * kHalo + ly + k) * kTile + tx], c0);
-                c1 = fmaf(g, s_h[(1 * kHalo + ly + k) * kTile + tx], c1);
-                c2 = fmaf(g, s_h[(2 * kHalo + ly + k) * kTile + tx], c2);
+            for (int e = 0; e < kRowsPerThread + kWin - 1; ++e) {
+                const float2 m = s_m[tx * kColS + ly0 + e];
+                const float p = s_p[tx * kColS + ly0 + e];
+#pragma unroll
+                for (int j = 0; j < kRowsPerThread; ++j) {
+                    const int k = e - j;
+                    if (k >= 0 && k < kWin) {
+                        const float g = win.g[k];
+                        vm[j] = __ffma2_rn(f2(g, g), m, vm[j]);
+                        vp[j] = fmaf(g, p, vp[j]);
+                    }
+                }
             }
-            float v = 0.f;
-            if (px < (int)W && py < (int)H) {
-                const size_t o = img_off + ((size_t)py * W + px) * 3 + ch;
-                const float a = __ldg(img + o), b = __ldg(tgt + o);
-                const float sgn = a > b ? 1.f : (a < b ? -1.f : 0.f);
-                v = k_l1 * sgn + k_ss * (c0 + 2.f * a * c1 + b * c2);
+#pragma unroll
+            for (int j = 0; j < kRowsPerThread; ++j) {
+                const int py = y0 + ly0 + j;
+                float v = 0.f;
+                if (px < (int)W && py < (int)H) {
+                    const size_t o = img_off + ((size_t)py * W + px) * 3 + ch;
+                    const float a = __ldg(img + o), b = __ldg(tgt + o);
+                    const float sgn = a > b ? 1.f : (a < b ? -1.f : 0.f);
+                    v = k_l1 * sgn + k_ss * (vm[j].x + 2.f * a * vm[j].y + b * vp[j]);
+                }
+                out[j][ch] = v;
             }
-            out[j][ch] = v;
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int py = y0 + ty + 8 * j;
+    for (int j = 0; j < kRowsPerThread; ++j) {
+        const int py = y0 + ty * kRowsPerThread + j;
         if (px < (int)W && py < (int)H) {
             const size_t o = img_off + ((size_t)py * W + px) * 3;
 #pragma unroll
@@ -314,7 +403,7 @@ extern "C" int b200splat_l1_ssim_fwd(uint32_t C, uint32_t H, uint32_t W, const f
     static const Window win = make_window();
     cudaStream_t st = (cudaStream_t)stream;
     const dim3 grid(div_up(W, kTile), div_up(H, kTile), C);
-    const size_t smem = (size_t)(2 * kHalo * kRowF + 5 * kHalo * kTile) * sizeof(float);
+    const size_t smem = (size_t)(kHalo * kRowS * 2 + kTile * kColS * 5) * sizeof(float);
     cudaFuncSetAttribute(l1_ssim_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     float *partials = reinterpret_cast<float *>(workspace);
     l1_ssim_fwd_kernel<<<grid, 256, smem, st>>>(H, W, img, target, win, d_mu, d_xx, d_xy, partials);
@@ -334,7 +423,7 @@ extern "C" int b200splat_l1_ssim_bwd(uint32_t C, uint32_t H, uint32_t W, const f
     static const Window win = make_window();
     cudaStream_t st = (cudaStream_t)stream;
     const dim3 grid(div_up(W, kTile), div_up(H, kTile), C);
-    const size_t smem = (size_t)(3 * kHalo * kRowF + 3 * kHalo * kTile) * sizeof(float);
+    const size_t smem = (size_t)(kHalo * kRowS * 3 + kTile * kColS * 3) * sizeof(float);
     cudaFuncSetAttribute(l1_ssim_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const double n_l1 = (double)C * H * W * 3, n_ssim = (double)C * (H - 2 * kHalf) * (W - 2 * kHalf) * 3;
     l1_ssim_bwd_kernel<<<grid, 256, smem, st>>>(H, W, img, target, win, d_mu, d_xx, d_xy, v_loss,
