@@ -367,6 +367,8 @@ def run_gpu(args):
             "sh_colors_fwd": 216 * V + 4 * C * N,
             "sh_colors_bwd": 228 * V + 192 * N + 4 * C * N,
             "isect_sorted": 16 * V + 8 * C * N + 12 * I + 24 * I,
+            "isect_depth_order": 16 * C * N + 12 * C * N,   # depth keys + order out, counts gathered + scanned
+            "isect_tile_order": 16 * V + 12 * I + 24 * I,   # expand reads, ids + flatten_ids out, one pair sort
             "grad_gather": 2 * 236 * N,
             "grad_allreduce": 236 * N,
             "rasterize_pack": 36 * C * N + 48 * C * N,

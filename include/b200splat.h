@@ -263,6 +263,28 @@ B200SPLAT_API int b200splat_isect_sorted(
     void *workspace, size_t workspace_bytes,
     void *stream);
 
+/* The two phases of b200splat_isect_sorted as separate calls.  Phase 1 (depth order of the
+ * (camera, Gaussian) pairs + scan of their tile counts in that order) needs only n_elems, so
+ * a host binding launches it BEFORE it reads n_isects back from b200splat_isect_count and the
+ * round trip of that one host sync (CS/isect_tiles.cu:201) is hidden behind device work.
+ * `selector_out` (host) says which half of the ping-pong buffers holds the order; pass it and
+ * the same workspace to phase 2 as `depth_workspace` / `depth_selector`. */
+B200SPLAT_API size_t b200splat_isect_depth_order_workspace_bytes(uint64_t n_elems);
+
+B200SPLAT_API int b200splat_isect_depth_order(
+    uint64_t n_elems, const float *depths, const int32_t *tiles_per_gauss,
+    void *workspace, size_t workspace_bytes, int *selector_out, void *stream);
+
+B200SPLAT_API size_t b200splat_isect_tile_order_workspace_bytes(uint64_t n_isects);
+
+B200SPLAT_API int b200splat_isect_tile_order(
+    int packed, uint32_t C, uint32_t N, uint32_t nnz, const int64_t *camera_ids,
+    const float *means2d, const int32_t *radii, const float *depths,
+    const void *depth_workspace, int depth_selector, uint64_t n_isects,
+    uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+    int64_t *isect_ids, int32_t *flatten_ids, int32_t *offsets,
+    void *workspace, size_t workspace_bytes, void *stream);
+
 /* a7  isect_offset_encode                 CS/bindings.h:162-167, kernel
  *     CS/isect_tiles.cu:309-355.  offsets [C*n_tiles] int32 fully written
  *     (all zeros when n_isects == 0). */
@@ -451,6 +473,10 @@ B200SPLAT_API int b200splat_sh_colors_staged_bwd(
     const int32_t *radii, const float *colors, const float *v_colors,
     float *v_sh0, float *v_rest, float *v_means,
     uint32_t means_cam_begin, uint32_t means_cam_end, void *stream);
+
+/* viewmats = inverse(camtoworlds) [C,4,4] (gsplat_trainer.py:483), adjugate in double, no
+ * host synchronisation (torch.linalg.inv syncs to report singular inputs). */
+B200SPLAT_API int b200splat_invert_4x4(uint32_t C, const float *mats, float *out, void *stream);
 
 B200SPLAT_API int b200splat_splat_activations_fwd(
     uint32_t N, const float *scales_raw, const float *opacities_raw,

@@ -17,7 +17,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("B200SPLAT_LIB", _PKG / "libb200splat.so"))
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 _P = c_void_p
 _U32 = c_uint32
@@ -51,6 +51,11 @@ SIGNATURES = {
     "b200splat_isect_sorted_workspace_bytes": (c_size_t, [_U64, _U64]),
     "b200splat_isect_sorted": (_I, [_I, _U32, _U32, _U32, _P, _P, _P, _P, _P, _U64, _U32, _U32, _U32, _P, _P, _P, _P,
                                     c_size_t, _P]),
+    "b200splat_isect_depth_order_workspace_bytes": (c_size_t, [_U64]),
+    "b200splat_isect_depth_order": (_I, [_U64, _P, _P, _P, c_size_t, ctypes.POINTER(c_int), _P]),
+    "b200splat_isect_tile_order_workspace_bytes": (c_size_t, [_U64]),
+    "b200splat_isect_tile_order": (_I, [_I, _U32, _U32, _U32, _P, _P, _P, _P, _P, _I, _U64, _U32, _U32, _U32, _P, _P,
+                                        _P, _P, c_size_t, _P]),
     "b200splat_scan_workspace_bytes": (c_size_t, [_U64]),
     "b200splat_isect_fill": (_I, [_I, _U32, _U32, _U32, _P, _P, _P, _P, _P, _U32, _U32, _U32, _P, _P, _P]),
     "b200splat_sort_workspace_bytes": (c_size_t, [_U64]),
@@ -81,6 +86,7 @@ SIGNATURES = {
     "b200splat_sh_colors_staged_fwd": (_I, [_U32, _U32, _U32, _U32, _P, _P, _P, _P, _P, _P, _P]),
     "b200splat_sh_colors_staged_bwd": (_I, [_U32, _U32, _U32, _U32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _U32, _U32,
                                             _P]),
+    "b200splat_invert_4x4": (_I, [_U32, _P, _P, _P]),
     "b200splat_splat_activations_fwd": (_I, [_U32, _P, _P, _P, _P, _P]),
     "b200splat_splat_activations_bwd": (_I, [_U32, _P, _P, _P, _P, _P, _P, _P]),
     "b200splat_l1_ssim_workspace_bytes": (c_size_t, [_U32, _U32, _U32]),

@@ -151,13 +151,16 @@ assemble_kernel(uint64_t n_isects, const uint32_t *__restrict__ tile_keys, const
 
 static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
-struct SortedLayout {
-    size_t gkeys_a, gkeys_b, gvals_a, gvals_b, counts, cum, total, scan_ws, scan_ws_bytes;
+// workspace of phase 1 (depth order; depends on n_elems only) and of phase 2 (tile order)
+struct DepthLayout {
+    size_t gkeys_a, gkeys_b, gvals_a, gvals_b, counts, cum, total, scan_ws, scan_ws_bytes, cub, cub_bytes, end;
+};
+struct TileLayout {
     size_t tkeys_a, tkeys_b, tvals_a, tvals_b, cub, cub_bytes, end;
 };
 
-static SortedLayout sorted_layout(uint64_t n_elems, uint64_t n_isects) {
-    SortedLayout L;
+static DepthLayout depth_layout(uint64_t n_elems) {
+    DepthLayout L;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes); return r; };
     L.gkeys_a = take(4 * n_elems); L.gkeys_b = take(4 * n_elems);
@@ -167,15 +170,25 @@ static SortedLayout sorted_layout(uint64_t n_elems, uint64_t n_isects) {
     L.total = take(8);
     L.scan_ws_bytes = scan_workspace_bytes(n_elems);
     L.scan_ws = take(L.scan_ws_bytes);
+    size_t b1 = 0;
+    cub::DoubleBuffer<uint32_t> k(nullptr, nullptr), v(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, b1, k, v, (int64_t)(n_elems ? n_elems : 1), 0, 32, (cudaStream_t)0);
+    L.cub_bytes = b1 + 256;
+    L.cub = take(L.cub_bytes);
+    L.end = o;
+    return L;
+}
+
+static TileLayout tile_layout(uint64_t n_isects) {
+    TileLayout L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes); return r; };
     L.tkeys_a = take(4 * n_isects); L.tkeys_b = take(4 * n_isects);
     L.tvals_a = take(4 * n_isects); L.tvals_b = take(4 * n_isects);
-    size_t b1 = 0, b2 = 0;
-    {
-        cub::DoubleBuffer<uint32_t> k(nullptr, nullptr), v(nullptr, nullptr);
-        cub::DeviceRadixSort::SortPairs(nullptr, b1, k, v, (int64_t)(n_elems ? n_elems : 1), 0, 32, (cudaStream_t)0);
-        cub::DeviceRadixSort::SortPairs(nullptr, b2, k, v, (int64_t)(n_isects ? n_isects : 1), 0, 32, (cudaStream_t)0);
-    }
-    L.cub_bytes = (b1 > b2 ? b1 : b2) + 256;
+    size_t b2 = 0;
+    cub::DoubleBuffer<uint32_t> k(nullptr, nullptr), v(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, b2, k, v, (int64_t)(n_isects ? n_isects : 1), 0, 32, (cudaStream_t)0);
+    L.cub_bytes = b2 + 256;
     L.cub = take(L.cub_bytes);
     L.end = o;
     return L;
@@ -214,17 +227,59 @@ extern "C" int b200splat_isect_sort(uint64_t n_isects, uint32_t end_bit, int64_t
     return 0;
 }
 
-extern "C" size_t b200splat_isect_sorted_workspace_bytes(uint64_t n_elems, uint64_t n_isects) {
-    return sorted_layout(n_elems, n_isects).end;
+// ---- depth-first ordering, phase 1: everything that does not need n_isects -----------------
+// (launched by the wrapper BEFORE it reads n_isects back, so the host round trip of that one
+// sync is hidden behind ~0.1 ms of useful device work)
+extern "C" size_t b200splat_isect_depth_order_workspace_bytes(uint64_t n_elems) {
+    return depth_layout(n_elems).end;
 }
 
-extern "C" int b200splat_isect_sorted(int packed, uint32_t C, uint32_t N, uint32_t nnz, const int64_t *camera_ids,
-                                      const float *means2d, const int32_t *radii, const float *depths,
-                                      const int32_t *tiles_per_gauss, uint64_t n_isects, uint32_t tile_size,
-                                      uint32_t tile_width, uint32_t tile_height, int64_t *isect_ids,
-                                      int32_t *flatten_ids, int32_t *offsets, void *workspace, size_t workspace_bytes,
-                                      void *stream) {
-    const char *where = "b200splat_isect_sorted";
+extern "C" int b200splat_isect_depth_order(uint64_t n_elems, const float *depths, const int32_t *tiles_per_gauss,
+                                           void *workspace, size_t workspace_bytes, int *selector_out, void *stream) {
+    const char *where = "b200splat_isect_depth_order";
+    cudaStream_t st = (cudaStream_t)stream;
+    B2S_REQUIRE(n_elems <= 0xffffffffull, where, "more than 2^32 (camera, Gaussian) pairs");
+    B2S_REQUIRE(selector_out != nullptr, where, "selector_out is required");
+    *selector_out = 0;
+    if (n_elems == 0) return 0;
+    const DepthLayout L = depth_layout(n_elems);
+    B2S_REQUIRE(workspace != nullptr && workspace_bytes >= L.end, where,
+                "workspace too small (see b200splat_isect_depth_order_workspace_bytes)");
+    char *ws = reinterpret_cast<char *>(workspace);
+    auto u32 = [&](size_t off) { return reinterpret_cast<uint32_t *>(ws + off); };
+    // 1. Gaussians by depth
+    depth_keys_kernel<<<div_up(n_elems, kThreads), kThreads, 0, st>>>(n_elems, tiles_per_gauss, depths, u32(L.gkeys_a),
+                                                                      u32(L.gvals_a));
+    B2S_CHECK_LAUNCH(where);
+    cub::DoubleBuffer<uint32_t> gk(u32(L.gkeys_a), u32(L.gkeys_b)), gv(u32(L.gvals_a), u32(L.gvals_b));
+    size_t cb = L.cub_bytes;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(ws + L.cub, cb, gk, gv, (int64_t)n_elems, 0, 32, st);
+    if (e != cudaSuccess) return fail_cuda(where, e);
+    *selector_out = gv.selector;
+    const uint32_t *order = gv.Current();
+    // 2. offsets in depth order
+    int32_t *counts = reinterpret_cast<int32_t *>(ws + L.counts);
+    int64_t *cum = reinterpret_cast<int64_t *>(ws + L.cum);
+    gather_counts_kernel<<<div_up(n_elems, kThreads), kThreads, 0, st>>>(n_elems, order, tiles_per_gauss, counts);
+    B2S_CHECK_LAUNCH(where);
+    if (lookback_scan_i32_to_i64(counts, cum, n_elems, reinterpret_cast<int64_t *>(ws + L.total), ws + L.scan_ws,
+                                 L.scan_ws_bytes, st))
+        return fail(where, "scan failed");
+    return 0;
+}
+
+// ---- phase 2: expand, stable tile sort, assemble (+ offsets) ---------------------------------
+extern "C" size_t b200splat_isect_tile_order_workspace_bytes(uint64_t n_isects) {
+    return tile_layout(n_isects).end;
+}
+
+extern "C" int b200splat_isect_tile_order(int packed, uint32_t C, uint32_t N, uint32_t nnz, const int64_t *camera_ids,
+                                          const float *means2d, const int32_t *radii, const float *depths,
+                                          const void *depth_workspace, int depth_selector, uint64_t n_isects,
+                                          uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+                                          int64_t *isect_ids, int32_t *flatten_ids, int32_t *offsets, void *workspace,
+                                          size_t workspace_bytes, void *stream) {
+    const char *where = "b200splat_isect_tile_order";
     cudaStream_t st = (cudaStream_t)stream;
     const uint64_t n_elems = packed ? (uint64_t)nnz : (uint64_t)C * N;
     B2S_REQUIRE(!packed || camera_ids != nullptr, where, "camera_ids required when packed");
@@ -235,29 +290,16 @@ extern "C" int b200splat_isect_sorted(int packed, uint32_t C, uint32_t N, uint32
     for (uint32_t v = C; v; v >>= 1) ++cam_n_bits;
     B2S_REQUIRE(tile_n_bits + cam_n_bits <= 32, where, "camera and tile ids do not fit in 32 bits");
     if (n_isects == 0 || n_elems == 0) return 0;
-    const SortedLayout L = sorted_layout(n_elems, n_isects);
+    const DepthLayout D = depth_layout(n_elems);
+    const TileLayout L = tile_layout(n_isects);
+    B2S_REQUIRE(depth_workspace != nullptr, where, "depth_workspace (from b200splat_isect_depth_order) is required");
     B2S_REQUIRE(workspace != nullptr && workspace_bytes >= L.end, where,
-                "workspace too small (see b200splat_isect_sorted_workspace_bytes)");
+                "workspace too small (see b200splat_isect_tile_order_workspace_bytes)");
+    const char *dws = reinterpret_cast<const char *>(depth_workspace);
     char *ws = reinterpret_cast<char *>(workspace);
     auto u32 = [&](size_t off) { return reinterpret_cast<uint32_t *>(ws + off); };
-
-    // 1. Gaussians by depth
-    depth_keys_kernel<<<div_up(n_elems, kThreads), kThreads, 0, st>>>(n_elems, tiles_per_gauss, depths, u32(L.gkeys_a),
-                                                                      u32(L.gvals_a));
-    B2S_CHECK_LAUNCH(where);
-    cub::DoubleBuffer<uint32_t> gk(u32(L.gkeys_a), u32(L.gkeys_b)), gv(u32(L.gvals_a), u32(L.gvals_b));
-    size_t cb = L.cub_bytes;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(ws + L.cub, cb, gk, gv, (int64_t)n_elems, 0, 32, st);
-    if (e != cudaSuccess) return fail_cuda(where, e);
-    const uint32_t *order = gv.Current();
-    // 2. offsets in depth order
-    int32_t *counts = reinterpret_cast<int32_t *>(ws + L.counts);
-    int64_t *cum = reinterpret_cast<int64_t *>(ws + L.cum);
-    gather_counts_kernel<<<div_up(n_elems, kThreads), kThreads, 0, st>>>(n_elems, order, tiles_per_gauss, counts);
-    B2S_CHECK_LAUNCH(where);
-    if (lookback_scan_i32_to_i64(counts, cum, n_elems, reinterpret_cast<int64_t *>(ws + L.total), ws + L.scan_ws,
-                                 L.scan_ws_bytes, st))
-        return fail(where, "scan failed");
+    const uint32_t *order = reinterpret_cast<const uint32_t *>(dws + (depth_selector ? D.gvals_b : D.gvals_a));
+    const int64_t *cum = reinterpret_cast<const int64_t *>(dws + D.cum);
     // 3. expand
     expand_kernel<<<div_up(n_elems, kThreads), kThreads, 0, st>>>(packed, N, n_elems, order, cum, camera_ids, means2d,
                                                                   radii, (float)tile_size, tile_width, tile_height,
@@ -265,8 +307,9 @@ extern "C" int b200splat_isect_sorted(int packed, uint32_t C, uint32_t N, uint32
     B2S_CHECK_LAUNCH(where);
     // 4. stable sort by cam|tile
     cub::DoubleBuffer<uint32_t> tk(u32(L.tkeys_a), u32(L.tkeys_b)), tv(u32(L.tvals_a), u32(L.tvals_b));
-    cb = L.cub_bytes;
-    e = cub::DeviceRadixSort::SortPairs(ws + L.cub, cb, tk, tv, (int64_t)n_isects, 0, (int)(tile_n_bits + cam_n_bits), st);
+    size_t cb = L.cub_bytes;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(ws + L.cub, cb, tk, tv, (int64_t)n_isects, 0,
+                                                    (int)(tile_n_bits + cam_n_bits), st);
     if (e != cudaSuccess) return fail_cuda(where, e);
     // 5. assemble
     assemble_kernel<<<div_up(n_isects, kThreads), kThreads, 0, st>>>(n_isects, tk.Current(), tv.Current(), depths,
@@ -274,4 +317,31 @@ extern "C" int b200splat_isect_sorted(int packed, uint32_t C, uint32_t N, uint32
                                                                      tile_n_bits, offsets);
     B2S_CHECK_LAUNCH(where);
     return 0;
+}
+
+// both phases in one call (workspace = phase-1 layout followed by phase-2 layout)
+extern "C" size_t b200splat_isect_sorted_workspace_bytes(uint64_t n_elems, uint64_t n_isects) {
+    return depth_layout(n_elems).end + tile_layout(n_isects).end;
+}
+
+extern "C" int b200splat_isect_sorted(int packed, uint32_t C, uint32_t N, uint32_t nnz, const int64_t *camera_ids,
+                                      const float *means2d, const int32_t *radii, const float *depths,
+                                      const int32_t *tiles_per_gauss, uint64_t n_isects, uint32_t tile_size,
+                                      uint32_t tile_width, uint32_t tile_height, int64_t *isect_ids,
+                                      int32_t *flatten_ids, int32_t *offsets, void *workspace, size_t workspace_bytes,
+                                      void *stream) {
+    const char *where = "b200splat_isect_sorted";
+    const uint64_t n_elems = packed ? (uint64_t)nnz : (uint64_t)C * N;
+    B2S_REQUIRE(n_elems <= 0xffffffffull, where, "more than 2^32 (camera, Gaussian) pairs");
+    if (n_isects == 0 || n_elems == 0) return 0;
+    const size_t d_bytes = depth_layout(n_elems).end, t_bytes = tile_layout(n_isects).end;
+    B2S_REQUIRE(workspace != nullptr && workspace_bytes >= d_bytes + t_bytes, where,
+                "workspace too small (see b200splat_isect_sorted_workspace_bytes)");
+    char *ws = reinterpret_cast<char *>(workspace);
+    int sel = 0;
+    int rc = b200splat_isect_depth_order(n_elems, depths, tiles_per_gauss, ws, d_bytes, &sel, stream);
+    if (rc) return rc;
+    return b200splat_isect_tile_order(packed, C, N, nnz, camera_ids, means2d, radii, depths, ws, sel, n_isects,
+                                      tile_size, tile_width, tile_height, isect_ids, flatten_ids, offsets, ws + d_bytes,
+                                      t_bytes, stream);
 }

@@ -43,6 +43,38 @@ splat_activations_bwd_kernel(uint32_t N, const float *__restrict__ scales, const
 }
 
 // ---------------------------------------------------------------------------------------
+// viewmats = inverse(camtoworlds)  (gsplat_trainer.py:483 `torch.linalg.inv`): general 4x4
+// inverse by the adjugate, evaluated in double.  torch.linalg.inv synchronises the host to
+// check for singular inputs, which drains the launch queue once per step; this kernel does
+// not (a singular matrix yields inf/nan, like 1/0).
+// ---------------------------------------------------------------------------------------
+__global__ void invert_4x4_kernel(uint32_t C, const float *__restrict__ mats, float *__restrict__ out) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double m[16], inv[16];
+    for (int i = 0; i < 16; i++) m[i] = (double)mats[16 * c + i];
+    inv[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+    inv[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+    inv[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+    inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+    inv[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+    inv[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+    inv[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+    inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+    inv[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+    inv[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+    inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+    inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+    inv[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+    inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+    inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+    inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+    const double det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
+    const double idet = 1.0 / det;
+    for (int i = 0; i < 16; i++) out[16 * c + i] = (float)(inv[i] * idet);
+}
+
+// ---------------------------------------------------------------------------------------
 // L1 + SSIM
 // ---------------------------------------------------------------------------------------
 constexpr int kWin = 11, kHalf = 5;
@@ -379,6 +411,13 @@ extern "C" int b200splat_splat_activations_bwd(uint32_t N, const float *scales, 
     splat_activations_bwd_kernel<<<div_up(3 * (uint64_t)N, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
         N, scales, opacities, v_scales, v_opacities, v_scales_raw, v_opacities_raw);
     B2S_CHECK_LAUNCH("b200splat_splat_activations_bwd");
+    return 0;
+}
+
+extern "C" int b200splat_invert_4x4(uint32_t C, const float *mats, float *out, void *stream) {
+    if (C == 0) return 0;
+    invert_4x4_kernel<<<div_up(C, 64), 64, 0, (cudaStream_t)stream>>>(C, mats, out);
+    B2S_CHECK_LAUNCH("b200splat_invert_4x4");
     return 0;
 }
 

@@ -65,6 +65,22 @@ def splat_activations(scales_raw: Tensor, opacities_raw: Tensor) -> Tuple[Tensor
     return _SplatActivations.apply(scales_raw.contiguous(), opacities_raw.contiguous())
 
 
+def invert_poses(camtoworlds: Tensor) -> Tensor:
+    """`torch.linalg.inv(camtoworlds)` [C,4,4] (gsplat_trainer.py:483) without the host
+    synchronisation torch performs to report singular inputs.  Poses that require a gradient
+    (pose optimisation) go through torch."""
+    if camtoworlds.requires_grad:
+        return torch.linalg.inv(camtoworlds)
+    m = camtoworlds.contiguous()
+    _check_cuda(m)
+    _f32(m)
+    assert m.shape[-2:] == (4, 4), m.shape
+    out = torch.empty_like(m)
+    if m.numel():
+        native("invert_4x4", get_lib(), m.device, m.numel() // 16, _ptr(m), _ptr(out))
+    return out
+
+
 # ----------------------------------------------------------------------------------------
 # rasterize_splats (gsplat_trainer.py:446-497)
 # ----------------------------------------------------------------------------------------
@@ -93,7 +109,7 @@ def rasterize_splats(
         scales=scales,
         opacities=opacities,
         colors=(splats["sh0"], splats["shN"]),  # == torch.cat([sh0, shN], 1), never materialised
-        viewmats=torch.linalg.inv(camtoworlds),
+        viewmats=invert_poses(camtoworlds),
         Ks=Ks,
         width=width,
         height=height,

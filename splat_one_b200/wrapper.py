@@ -20,6 +20,7 @@ reference's TORCH_CHECK (CS/bindings.h:10-16).
 from __future__ import annotations
 
 import ctypes
+import threading
 import os
 from typing import Optional, Tuple
 
@@ -49,7 +50,7 @@ class _Profiler:
         "projection_fwd": 1, "projection_bwd": 1, "projection_packed_count": 3, "projection_packed_fill": 1,
         "projection_packed_bwd": 1, "sh_fwd": 1, "sh_bwd": 1, "camera_centers": 1, "sh_colors_fwd": 1,
         "sh_colors_bwd": 1, "sh_colors_packed_fwd": 1, "sh_colors_packed_bwd": 1, "isect_count": 2, "isect_fill": 1,
-        "isect_sort": 0, "isect_sorted": 5, "isect_offset_encode": 1, "rasterize_pack": 1, "rasterize_fwd": 1, "rasterize_bwd": 1,
+        "isect_sort": 0, "isect_sorted": 5, "isect_depth_order": 3, "isect_tile_order": 2, "invert_4x4": 1, "isect_offset_encode": 1, "rasterize_pack": 1, "rasterize_fwd": 1, "rasterize_bwd": 1,
         "raster_indices_count": 2, "raster_indices_fill": 1, "quat_scale_to_covar_preci_fwd": 1,
         "quat_scale_to_covar_preci_bwd": 1, "world_to_cam_fwd": 1, "world_to_cam_bwd": 1, "proj_fwd": 1, "proj_bwd": 1,
         "selective_adam_update": 1, "compute_relocation": 1, "sh_colors_staged_fwd": 1, "sh_colors_staged_bwd": 1,
@@ -101,6 +102,35 @@ def _ptr(t: Optional[Tensor]):
 
 def _stream(device: torch.device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+_PINNED = threading.local()
+
+
+def _read_back(t: Tensor, ready: Optional["torch.cuda.Event"] = None):
+    """Values of a tiny device tensor on the host: one copy into a per-thread pinned buffer.
+    With `ready` (an event recorded when `t` was produced) the copy runs on a side stream, so
+    kernels queued on the current stream AFTER the event keep running while the host waits."""
+    buf = getattr(_PINNED, "buf", None)
+    if buf is None or buf.dtype != t.dtype or buf.numel() < t.numel():
+        buf = torch.empty((max(t.numel(), 8),), dtype=t.dtype, pin_memory=True)
+        _PINNED.buf = buf
+    view = buf[: t.numel()]
+    if ready is None:
+        view.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(t.device).synchronize()
+        return view.tolist()
+    side = getattr(_PINNED, "streams", None)
+    if side is None:
+        side = _PINNED.streams = {}
+    st = side.get(t.device)
+    if st is None:
+        st = side[t.device] = torch.cuda.Stream(device=t.device)
+    st.wait_event(ready)
+    with torch.cuda.stream(st):
+        view.copy_(t, non_blocking=True)
+    st.synchronize()
+    return view.tolist()
 
 
 def _check_cuda(*tensors: Optional[Tensor]) -> None:
@@ -773,6 +803,8 @@ def _isect_tiles_impl(
 
     tiles_per_gauss = torch.empty(radii.shape, device=dev, dtype=torch.int32)
     n_isects, neg_depth = 0, False
+    depth_first = sort and not _FORCE_GENERIC_SORT
+    depth_ws, depth_sel = None, ctypes.c_int(0)
     if n_elems:
         cum_tiles = torch.empty((n_elems,), device=dev, dtype=torch.int64)
         n_isects_dev = torch.empty((2,), device=dev, dtype=torch.int64)
@@ -780,20 +812,30 @@ def _isect_tiles_impl(
         ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
         native("isect_count", lib, dev, int(packed), C, N, nnz, _ptr(means2d), _ptr(radii), _ptr(depths), tile_size,
                tile_width, tile_height, _ptr(tiles_per_gauss), _ptr(cum_tiles), _ptr(n_isects_dev), _ptr(ws), ws_bytes)
-        n_isects, neg = n_isects_dev.tolist()  # the one host sync (CS/isect_tiles.cu:201)
+        ready = None
+        if depth_first:
+            # phase 1 of the depth-first ordering needs only n_elems: it is queued BEFORE the host
+            # reads n_isects back (on a side stream), so that round trip overlaps ~0.1 ms of device work
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(dev))
+            dws_bytes = lib.b200splat_isect_depth_order_workspace_bytes(n_elems)
+            depth_ws = torch.empty((dws_bytes,), device=dev, dtype=torch.uint8)
+            native("isect_depth_order", lib, dev, n_elems, _ptr(depths), _ptr(tiles_per_gauss), _ptr(depth_ws),
+                   dws_bytes, ctypes.byref(depth_sel))
+        n_isects, neg = _read_back(n_isects_dev, ready)  # the one host sync (CS/isect_tiles.cu:201)
         neg_depth = bool(neg)
 
     isect_ids = torch.empty((n_isects,), device=dev, dtype=torch.int64)
     flatten_ids = torch.empty((n_isects,), device=dev, dtype=torch.int32)
     if n_isects:
-        if sort and not neg_depth and not _FORCE_GENERIC_SORT:
+        if depth_first and not neg_depth:
             # depth-first ordering (csrc/sort.cu): bit-identical to fill + full-key sort
-            ws_bytes = lib.b200splat_isect_sorted_workspace_bytes(n_elems, n_isects)
+            ws_bytes = lib.b200splat_isect_tile_order_workspace_bytes(n_isects)
             ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
             offsets = (torch.empty((C, tile_height, tile_width), device=dev, dtype=torch.int32)
                        if want_offsets else None)
-            native("isect_sorted", lib, dev, int(packed), C, N, nnz, _ptr(camera_ids), _ptr(means2d), _ptr(radii),
-                   _ptr(depths), _ptr(tiles_per_gauss), n_isects, tile_size, tile_width, tile_height,
+            native("isect_tile_order", lib, dev, int(packed), C, N, nnz, _ptr(camera_ids), _ptr(means2d), _ptr(radii),
+                   _ptr(depths), _ptr(depth_ws), depth_sel.value, n_isects, tile_size, tile_width, tile_height,
                    _ptr(isect_ids), _ptr(flatten_ids), _ptr(offsets), _ptr(ws), ws_bytes)
             return tiles_per_gauss, isect_ids, flatten_ids, offsets
         native("isect_fill", lib, dev, int(packed), C, N, nnz, _ptr(camera_ids), _ptr(means2d), _ptr(radii),
