@@ -109,6 +109,71 @@ struct GradSink {
     }
 };
 
+// Shared-memory variant of the commit.  The butterfly above is a chain of 5 dependent SHFL
+// stages per pair (ncu: ~10 % of the kernel's stall samples are FADDs waiting on a shuffle).
+// Here every lane parks its NV partial values in shared memory (row (slot, k), 32 lanes wide,
+// rows padded to 36 floats so that the 128-bit row reads below are conflict-free); once
+// SLOTS = 32 / NV pairs are parked, lane l sums row l with eight LDS.128 and issues ONE RED:
+// no shuffles, ~26 instead of ~46 warp instructions per pair, and the sums of a flush are
+// independent of the compositing chain of the following pairs.
+template <int NV>
+struct SmemSink {
+    static constexpr int SLOTS = 32 / NV;
+    static constexpr int ROW = 36;
+    static constexpr int FLOATS = SLOTS * NV * ROW;
+    float *base;       // destination array of this lane's value index (lane % NV); nullptr: none
+    uint32_t stride;
+    float *buf;        // [SLOTS * NV][ROW]
+    int *gid;          // [SLOTS] Gaussian row of each parked pair
+    int cnt;
+    int my_slot;
+
+    template <int CDIM>
+    __device__ __forceinline__ void init(unsigned lane, uint32_t channels, float *v_colors, float *v_conics,
+                                         float *v_means2d, float *v_opacities, float *v_means2d_abs, float *smem_buf,
+                                         int *smem_gid) {
+        buf = smem_buf; gid = smem_gid; cnt = 0;
+        my_slot = (int)lane / NV;
+        const int k = (int)lane - my_slot * NV;
+        base = nullptr; stride = 0;
+        if (my_slot >= SLOTS) return;
+        if (k < CDIM) {
+            if (k < (int)channels) { base = v_colors + k; stride = channels; }
+        } else if (k < CDIM + 3) { base = v_conics + (k - CDIM); stride = 3; }
+        else if (k < CDIM + 5) { base = v_means2d + (k - CDIM - 3); stride = 2; }
+        else if (k == CDIM + 5) { base = v_opacities; stride = 1; }
+        else { base = v_means2d_abs + (k - CDIM - 6); stride = 2; }
+    }
+
+    __device__ __forceinline__ void flush(unsigned lane) {
+        __syncwarp();
+        if ((int)lane < cnt * NV) {
+            const float4 *r = reinterpret_cast<const float4 *>(buf + lane * ROW);
+            const float4 a = r[0], b = r[1], c = r[2], d = r[3], e = r[4], f = r[5], g4 = r[6], h = r[7];
+            const float s0 = (a.x + a.y) + (a.z + a.w) + ((b.x + b.y) + (b.z + b.w));
+            const float s1 = (c.x + c.y) + (c.z + c.w) + ((d.x + d.y) + (d.z + d.w));
+            const float s2 = (e.x + e.y) + (e.z + e.w) + ((f.x + f.y) + (f.z + f.w));
+            const float s3 = (g4.x + g4.y) + (g4.z + g4.w) + ((h.x + h.y) + (h.z + h.w));
+            const int g = gid[my_slot];
+            if (base != nullptr) atomicAdd(base + (size_t)g * stride, (s0 + s1) + (s2 + s3));
+        }
+        __syncwarp();
+        cnt = 0;
+    }
+
+    __device__ __forceinline__ void commit(const float (&v)[NV], unsigned lane, int32_t g) {
+        float *row = buf + (cnt * NV) * ROW + lane;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) row[k * ROW] = v[k];
+        if (lane == 0) gid[cnt] = g;
+        if (++cnt == SLOTS) flush(lane);
+    }
+
+    __device__ __forceinline__ void finish(unsigned lane) {
+        if (cnt > 0) flush(lane);
+    }
+};
+
 template <int CDIM, bool ABS, int MAXT>
 __global__ void __launch_bounds__(MAXT)
 raster_bwd_kernel(uint32_t C, uint64_t n_isects, uint32_t channels, const float2 *__restrict__ means2d,
@@ -332,7 +397,7 @@ __device__ __forceinline__ bool bwd_quad(float2 &T2, float2 &ntb2, const float2 
     return ok0 || ok1;
 }
 
-template <int CDIM, bool ABS, int NQ, int MINB, int JOINT>
+template <int CDIM, bool ABS, int NQ, int MINB, int JOINT, int SINK, int ASYNC>
 __global__ void __launch_bounds__(32 * (4 / NQ), MINB)
 raster_bwd_quad_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channels, const float4 *__restrict__ rec,
                        const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks, uint32_t W,
@@ -347,9 +412,15 @@ raster_bwd_quad_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t chann
     constexpr int NQY = NQ / 2;   // quad rows per warp
     __shared__ float4 s_rec_all[NW][32 * 3];
     __shared__ int4 s_im_all[NW][32];  // {sorted index, quad mask, Gaussian row, -}
+    using SSink = SmemSink<NV>;
+    __shared__ __align__(16) float s_red_all[SINK ? NW : 1][SINK ? SSink::FLOATS : 4];
+    __shared__ int s_gid_all[SINK ? NW : 1][SINK ? SSink::SLOTS : 1];
+    __shared__ float4 s_pre_all[ASYNC ? NW : 1][ASYNC ? 32 * 3 : 1];  // records of the batch in flight
     const unsigned lane = threadIdx.x & 31, sub = threadIdx.x >> 5;
     float4 *s_rec = s_rec_all[sub];
     int4 *s_im = s_im_all[sub];
+    const float4 *s_pre = s_pre_all[ASYNC ? sub : 0] + (ASYNC ? 3 * lane : 0);
+    const uint32_t pre_addr = (uint32_t)__cvta_generic_to_shared(s_pre);
     const uint32_t tile_lin = blockIdx.x;
     if (masks != nullptr && !masks[tile_lin]) return;
     const int32_t range_start = tile_offsets[tile_lin];
@@ -406,14 +477,20 @@ raster_bwd_quad_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t chann
     const float pxa = tc.px, pxb = tc.px + 8.f;
 
     GradSink<NV> sink;
-    sink.template init<CDIM>(lane, channels, v_colors, v_conics, v_means2d, v_opacities, v_means2d_abs);
+    SSink ssink;
+    if (SINK) ssink.template init<CDIM>(lane, channels, v_colors, v_conics, v_means2d, v_opacities, v_means2d_abs,
+                                        s_red_all[SINK ? sub : 0], s_gid_all[SINK ? sub : 0]);
+    else sink.template init<CDIM>(lane, channels, v_colors, v_conics, v_means2d, v_opacities, v_means2d_abs);
 
+    // record prefetch one batch ahead (ASYNC: straight into shared memory), sorted id two ahead
     float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
-    int32_t my_idx = hi0 - (int32_t)lane, my_g = 0;
+    int32_t my_idx = hi0 - (int32_t)lane, my_g = 0, g_next = 0;
     if (my_idx >= range_start) {
         my_g = flatten_ids[my_idx];
-        r0 = __ldg(rec + 3 * (size_t)my_g); r1 = __ldg(rec + 3 * (size_t)my_g + 1); r2 = __ldg(rec + 3 * (size_t)my_g + 2);
+        if (ASYNC) prefetch_record(pre_addr, rec, my_g);
+        else { r0 = __ldg(rec + 3 * (size_t)my_g); r1 = __ldg(rec + 3 * (size_t)my_g + 1); r2 = __ldg(rec + 3 * (size_t)my_g + 2); }
     }
+    if (my_idx - 32 >= range_start) g_next = flatten_ids[my_idx - 32];
     uint32_t act = 0;  // warp-uniform: quads with a pixel whose last contributor is inside the batches seen so far
     for (int32_t hi = hi0; hi >= range_start; hi -= 32) {
         const int32_t lo = max(hi - 31, range_start);
@@ -421,7 +498,9 @@ raster_bwd_quad_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t chann
         for (int q = 0; q < NQ; ++q)
             if (!(act >> q & 1) && __any_sync(0xffffffffu, max(binf[q][0], binf[q][1]) >= lo)) act |= 1u << q;
         uint32_t my_mask = 0;
+        if (ASYNC) cp_async_wait_all();
         if (my_idx >= range_start) {
+            if (ASYNC) { r0 = s_pre[0]; r1 = s_pre[1]; r2 = s_pre[2]; }
             my_mask = quad_mask<NQ>(r0.x, r0.y, r0.z, r0.w, r1.x, r2.z, tc.ox, tc.oy, W, H);
             if ((my_mask & act) == 0) my_mask = 0; else my_mask &= (act | kNonPD);
         }
@@ -437,9 +516,11 @@ raster_bwd_quad_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t chann
         __syncwarp();
         my_idx = hi - 32 - (int32_t)lane;
         if (my_idx >= range_start) {
-            my_g = flatten_ids[my_idx];
-            r0 = __ldg(rec + 3 * (size_t)my_g); r1 = __ldg(rec + 3 * (size_t)my_g + 1); r2 = __ldg(rec + 3 * (size_t)my_g + 2);
+            my_g = g_next;
+            if (ASYNC) prefetch_record(pre_addr, rec, my_g);
+            else { r0 = __ldg(rec + 3 * (size_t)my_g); r1 = __ldg(rec + 3 * (size_t)my_g + 1); r2 = __ldg(rec + 3 * (size_t)my_g + 2); }
         }
+        if (my_idx - 32 >= range_start) g_next = flatten_ids[my_idx - 32];
         for (int t = 0; t < n; ++t) {
             const float4 a = s_rec[3 * t], b4 = s_rec[3 * t + 1], c4 = s_rec[3 * t + 2];
             const int4 im = s_im[t];
@@ -507,9 +588,11 @@ raster_bwd_quad_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t chann
                 v[CDIM + 6] = kInvLog2e * (abs2x.x + abs2x.y);
                 v[CDIM + 7] = kInvLog2e * (abs2y.x + abs2y.y);
             }
-            sink.commit(v, lane, im.z);
+            if (SINK) ssink.commit(v, lane, im.z);
+            else sink.commit(v, lane, im.z);
         }
     }
+    if (SINK) ssink.finish(lane);
 }
 
 template <int CDIM, bool ABS>
@@ -520,18 +603,18 @@ static void launch_bwd_quad(uint32_t C, uint64_t n_isects, uint32_t channels, co
                             const float *v_render_colors, const float *v_render_alphas, float *v_means2d_abs,
                             float *v_means2d, float *v_conics, float *v_colors, float *v_opacities, cudaStream_t st) {
     const uint32_t total = C * tile_width * tile_height;
-#define B2S_BWDQ(NQ_, MINB_, J_)                                                                                     \
-    raster_bwd_quad_kernel<CDIM, ABS, NQ_, MINB_, J_><<<total, 32 * (4 / NQ_), 0, st>>>(                              \
+#define B2S_BWDQ(NQ_, MINB_, J_, S_, A_)                                                                             \
+    raster_bwd_quad_kernel<CDIM, ABS, NQ_, MINB_, J_, S_, A_><<<total, 32 * (4 / NQ_), 0, st>>>(                      \
         total, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, \
         render_alphas, last_ids, v_render_colors, v_render_alphas, v_means2d_abs, v_means2d, v_conics, v_colors,     \
         v_opacities)
     switch (tuning_variant()) {
-        case 1: B2S_BWDQ(4, 20, 0); break;
-        case 2: B2S_BWDQ(2, 16, 0); break;
-        case 3: B2S_BWDQ(2, 10, 0); break;
-        case 4: B2S_BWDQ(4, 16, 0); break;
-        case 5: B2S_BWDQ(4, 16, 2); break;
-        default: B2S_BWDQ(4, 16, 1); break;  // measured on config B: 0.615 ms vs 0.652 (JOINT 0), 0.617 (JOINT 2)
+        case 1: B2S_BWDQ(4, 16, 1, 0, 0); break;   // butterfly commit, register prefetch (r1_c default)
+        case 2: B2S_BWDQ(2, 16, 0, 0, 0); break;
+        case 3: B2S_BWDQ(4, 16, 1, 1, 0); break;   // shared-memory commit, register prefetch
+        case 4: B2S_BWDQ(4, 16, 0, 0, 0); break;
+        case 5: B2S_BWDQ(4, 18, 1, 1, 1); break;   // same, 112 registers
+        default: B2S_BWDQ(4, 16, 1, 1, 1); break;  // shared-memory commit + cp.async prefetch: 0.552 ms vs 0.613 (variant 1)
     }
 #undef B2S_BWDQ
 }

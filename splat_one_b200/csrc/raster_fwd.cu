@@ -179,7 +179,7 @@ __device__ __forceinline__ void fwd_quad(float2 &T2, float2 (&pix2)[CDIM], int32
     T2.y = st1 ? fminf(T2.y, -T2.y) : next_T2.y;
 }
 
-template <int CDIM, int NQ, int MINB, int JOINT>
+template <int CDIM, int NQ, int MINB, int JOINT, int ASYNC>
 __global__ void __launch_bounds__(32 * (4 / NQ), MINB)
 raster_fwd_quad_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channels, const float4 *__restrict__ rec,
                        const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks, uint32_t W,
@@ -191,9 +191,12 @@ raster_fwd_quad_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t chann
     constexpr int NQY = NQ / 2;   // quad rows per warp
     __shared__ float4 s_rec_all[NW][32 * 3];
     __shared__ int2 s_im_all[NW][32];  // {sorted index, quad mask}
+    __shared__ float4 s_pre_all[ASYNC ? NW : 1][ASYNC ? 32 * 3 : 1];  // records of the batch in flight
     const unsigned lane = threadIdx.x & 31, sub = threadIdx.x >> 5;
     float4 *s_rec = s_rec_all[sub];
     int2 *s_im = s_im_all[sub];
+    const float4 *s_pre = s_pre_all[ASYNC ? sub : 0] + (ASYNC ? 3 * lane : 0);
+    const uint32_t pre_addr = (uint32_t)__cvta_generic_to_shared(s_pre);
     const uint32_t tile_lin = blockIdx.x;
     const QuadTile tc = quad_tile<NQ>(tile_lin, tile_width, tile_height, lane, sub);
     if (backgrounds != nullptr) backgrounds += (size_t)tc.cam * channels;
@@ -244,16 +247,21 @@ raster_fwd_quad_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t chann
     }
     const float pxa = tc.px, pxb = tc.px + 8.f;
 
-    // software prefetch of this lane's record for the first batch
+    // prefetch of this lane's record: one batch ahead for the record (ASYNC: straight into shared
+    // memory), two batches ahead for the sorted id it is addressed by
     float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
-    int32_t my_idx = range_start + (int32_t)lane;
+    int32_t my_idx = range_start + (int32_t)lane, g_next = 0;
     if (my_idx < range_end) {
         const int32_t g = flatten_ids[my_idx];
-        r0 = __ldg(rec + 3 * (size_t)g); r1 = __ldg(rec + 3 * (size_t)g + 1); r2 = __ldg(rec + 3 * (size_t)g + 2);
+        if (ASYNC) prefetch_record(pre_addr, rec, g);
+        else { r0 = __ldg(rec + 3 * (size_t)g); r1 = __ldg(rec + 3 * (size_t)g + 1); r2 = __ldg(rec + 3 * (size_t)g + 2); }
     }
+    if (my_idx + 32 < range_end) g_next = flatten_ids[my_idx + 32];
     for (int32_t base = range_start; base < range_end && live != 0; base += 32) {
         uint32_t my_mask = 0;
+        if (ASYNC) cp_async_wait_all();
         if (my_idx < range_end) {
+            if (ASYNC) { r0 = s_pre[0]; r1 = s_pre[1]; r2 = s_pre[2]; }
             my_mask = quad_mask<NQ>(r0.x, r0.y, r0.z, r0.w, r1.x, r2.z, tc.ox, tc.oy, W, H);
             if ((my_mask & live) == 0) my_mask = 0; else my_mask &= (live | kNonPD);
         }
@@ -270,9 +278,10 @@ raster_fwd_quad_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t chann
         // prefetch the next batch while this one is composited
         my_idx = base + 32 + (int32_t)lane;
         if (my_idx < range_end) {
-            const int32_t g = flatten_ids[my_idx];
-            r0 = __ldg(rec + 3 * (size_t)g); r1 = __ldg(rec + 3 * (size_t)g + 1); r2 = __ldg(rec + 3 * (size_t)g + 2);
+            if (ASYNC) prefetch_record(pre_addr, rec, g_next);
+            else { r0 = __ldg(rec + 3 * (size_t)g_next); r1 = __ldg(rec + 3 * (size_t)g_next + 1); r2 = __ldg(rec + 3 * (size_t)g_next + 2); }
         }
+        if (my_idx + 32 < range_end) g_next = flatten_ids[my_idx + 32];
         for (int t = 0; t < n; ++t) {
             const float4 a = s_rec[3 * t], b4 = s_rec[3 * t + 1], c4 = s_rec[3 * t + 2];
             const int2 im = s_im[t];
@@ -350,16 +359,17 @@ static void launch_fwd_quad(uint32_t C, uint64_t n_isects, uint32_t channels, co
                             const int32_t *flatten_ids, float *render_colors, float *render_alphas, int32_t *last_ids,
                             cudaStream_t st) {
     const uint32_t total = C * tile_width * tile_height;
-#define B2S_FWDQ(NQ_, MINB_, J_)                                                                                    \
-    raster_fwd_quad_kernel<CDIM, NQ_, MINB_, J_><<<total, 32 * (4 / NQ_), 0, st>>>(                                  \
+#define B2S_FWDQ(NQ_, MINB_, J_, A_)                                                                                \
+    raster_fwd_quad_kernel<CDIM, NQ_, MINB_, J_, A_><<<total, 32 * (4 / NQ_), 0, st>>>(                              \
         total, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, \
         render_colors, render_alphas, last_ids)
     switch (tuning_variant()) {
-        case 1: B2S_FWDQ(4, 16, 0); break;
-        case 2: B2S_FWDQ(2, 16, 0); break;
-        case 3: B2S_FWDQ(2, 10, 0); break;
-        case 4: B2S_FWDQ(4, 20, 1); break;   // joint quads measured slower here (0.416 vs 0.383 ms)
-        default: B2S_FWDQ(4, 20, 0); break;
+        case 1: B2S_FWDQ(4, 16, 0, 0); break;
+        case 2: B2S_FWDQ(2, 16, 0, 0); break;
+        case 3: B2S_FWDQ(4, 20, 0, 0); break;   // register prefetch of the records (r1_c default)
+        case 4: B2S_FWDQ(4, 20, 1, 0); break;   // joint quads measured slower here (0.416 vs 0.383 ms)
+        case 5: B2S_FWDQ(4, 24, 0, 1); break;   // cp.async record prefetch, 80 registers
+        default: B2S_FWDQ(4, 20, 0, 1); break;  // cp.async record prefetch: 0.362 ms vs 0.372 (fwd + pack, config B)
     }
 #undef B2S_FWDQ
 }
