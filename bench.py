@@ -203,6 +203,44 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------
+def train_step_report(S, scene, dev, reps: int = 30, warm: int = 5):
+    """Extra, not the headline metric: one TRAINING step of the f4 row on the
+    same scene — raw parameters -> splat_activations -> split-SH rasterization -> fused L1+SSIM ->
+    backward to the raw parameters (R/utils/gsplat_utils/gsplat_trainer.py:446-497, 624-628),
+    timed with CUDA events after warm-up."""
+    raw = {
+        "means": scene["means"], "quats": scene["quats"], "scales": torch.log(scene["scales"]),
+        "opacities": torch.logit(scene["opacities"].clamp(1e-4, 1 - 1e-4)),
+        "sh0": scene["sh"][:, :1].contiguous(), "shN": scene["sh"][:, 1:].contiguous(),
+    }
+    P = {k: v.to(dev).requires_grad_() for k, v in raw.items()}
+    c2w = torch.inverse(scene["viewmats"][:1]).to(dev)
+    Ks = scene["Ks"][:1].to(dev)
+    pixels = torch.rand(1, HEIGHT, WIDTH, 3, generator=torch.Generator().manual_seed(7)).to(dev)
+
+    def step():
+        for p in P.values():
+            p.grad = None
+        rc, _, _ = S.rasterize_splats(P, c2w, Ks, WIDTH, HEIGHT, sh_degree=SH_DEGREE, packed=False)
+        loss = S.l1_ssim_loss(rc, pixels, 0.2)
+        loss.backward()
+        return loss
+
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        loss = step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    return {"ms_per_step": ms, "Mpix_per_s": HEIGHT * WIDTH / (ms * 1e-3) / 1e6, "steps": reps, "loss": loss.item(),
+            "what": "raw params -> exp/sigmoid (1 kernel) -> rasterization(colors=(sh0, shN)) -> fused L1+SSIM "
+                    "-> backward; config B scene, random target image"}
+
+
 def run_gpu(args):
     import torch.distributed as dist
 
@@ -399,6 +437,9 @@ def run_gpu(args):
         stage_report = {k: {"avg_ms": round(v["avg_ms"], 4),
                             "GBps": round(alg_bytes.get(k, 0) / (v["avg_ms"] * 1e-3) / 1e9, 1) if v["avg_ms"] > 0 else None}
                         for k, v in stages.items()}
+        train = None
+        if world == 1:
+            train = train_step_report(S, scene, dev)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             mpix, ms, cores, sample = cpu_baseline(2, 1)
@@ -418,6 +459,7 @@ def run_gpu(args):
             "gpu_launches": launches,
             "roofline": roof,
             "stages": stage_report,
+            "train_step": train,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

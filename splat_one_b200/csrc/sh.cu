@@ -570,8 +570,11 @@ sh_colors_staged_fwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, co
 
 // One lane per Gaussian, loop over cameras (like sh_colors_bwd_kernel: same conventions for
 // radii / colors == NULL and the means camera window); gradient rows leave through smem.
-template <int NB, bool SPLIT>
-__global__ void __launch_bounds__(32 * kStageWarps)
+// CFS: the coefficient rows stay in shared memory (a second buffer) and are read from there
+// inside the basis loop instead of living in 3 (NB-1) registers: 140 -> ~96 registers, 12 -> 20
+// warps per SM.  Only for odd row lengths (scalar row reads are conflict-free then).
+template <int NB, bool SPLIT, bool CFS>
+__global__ void __launch_bounds__(32 * kStageWarps, CFS ? 5 : 1)
 sh_colors_staged_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, const float *__restrict__ means,
                             const float *__restrict__ campos, const float *__restrict__ sh0,
                             const float *__restrict__ rest, const int32_t *__restrict__ radii,
@@ -585,6 +588,8 @@ sh_colors_staged_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, co
     const uint32_t R = (K - K0) * 3, RS = stage_row_stride(R);
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float *s = reinterpret_cast<float *>(stage_smem4) + (size_t)warp * 32 * RS;
+    // CFS: second buffer behind the kStageWarps gradient buffers
+    const float *scf = reinterpret_cast<float *>(stage_smem4) + (size_t)(kStageWarps + warp) * 32 * RS + (size_t)lane * RS;
     const uint32_t n0 = (blockIdx.x * kStageWarps + warp) * 32;
     if (n0 >= N) return;  // warp-uniform
     const uint32_t cnt = min(32u, N - n0);
@@ -593,12 +598,18 @@ sh_colors_staged_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, co
     const bool vec = R % 4 == 0;
     const bool want_means = v_means != nullptr && NB > 1 && means_cam_begin < means_cam_end;
     // the DC basis has no direction derivative: sh0 itself is never read here
-    float cf[NFA];
+    float cf[CFS ? 1 : NFA];
     if (want_means && NF > 0) {
-        stage_rows_in(rest + (size_t)n0 * R, cnt, R, RS, s, lane, (reinterpret_cast<uintptr_t>(rest) & 15) == 0);
-        __syncwarp();
-        row_to_regs<NFA>(s + (size_t)lane * RS, cf, vec);
-        __syncwarp();  // the buffer is reused for the gradient rows below
+        if (CFS) {
+            stage_rows_in(rest + (size_t)n0 * R, cnt, R, RS, const_cast<float *>(scf) - (size_t)lane * RS, lane,
+                          (reinterpret_cast<uintptr_t>(rest) & 15) == 0);
+            __syncwarp();
+        } else {
+            stage_rows_in(rest + (size_t)n0 * R, cnt, R, RS, s, lane, (reinterpret_cast<uintptr_t>(rest) & 15) == 0);
+            __syncwarp();
+            row_to_regs<CFS ? 1 : NFA>(s + (size_t)lane * RS, cf, vec);
+            __syncwarp();  // the buffer is reused for the gradient rows below
+        }
     }
     float vc[NFA], vdc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
@@ -627,7 +638,8 @@ sh_colors_staged_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, co
                 if (SPLIT && k == 0) { vdc[0] += B * vr; vdc[1] += B * vg; vdc[2] += B * vb; return; }  // dB0 = 0
                 const int j = 3 * (k - K0);
                 vc[j] += B * vr; vc[j + 1] += B * vg; vc[j + 2] += B * vb;
-                const float w = cf[j] * vr + cf[j + 1] * vg + cf[j + 2] * vb;
+                const float w = CFS ? scf[j] * vr + scf[j + 1] * vg + scf[j + 2] * vb
+                                    : cf[CFS ? 0 : j] * vr + cf[CFS ? 0 : j + 1] * vg + cf[CFS ? 0 : j + 2] * vb;
                 vx += Bx * w; vy += By * w; vz += Bz * w;
             });
             const float d = vx * x + vy * y + vz * z;
@@ -834,12 +846,19 @@ static int launch_staged_bwd(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, c
                              const float *v_colors, float *v_sh0, float *v_rest, float *v_means, uint32_t cb,
                              uint32_t ce, size_t smem, cudaStream_t st) {
     const unsigned grid = div_up(N, 32 * kStageWarps);
+    const uint32_t R = (K - (SPLIT ? 1 : 0)) * 3;
+    const bool cfs = stage_row_stride(R) == R && 2 * smem <= 48 * 1024 && tuning_variant() != 7;
 #define B2S_SHS(NBV)                                                                                                 \
     do {                                                                                                             \
-        auto kern = sh_colors_staged_bwd_kernel<NBV, SPLIT>;                                                         \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-        kern<<<grid, 32 * kStageWarps, smem, st>>>(C, N, K, deg, means, campos, sh0, rest, radii, colors, v_colors,  \
-                                                   v_sh0, v_rest, v_means, cb, ce);                                  \
+        if (cfs) {                                                                                                   \
+            sh_colors_staged_bwd_kernel<NBV, SPLIT, true><<<grid, 32 * kStageWarps, 2 * smem, st>>>(                 \
+                C, N, K, deg, means, campos, sh0, rest, radii, colors, v_colors, v_sh0, v_rest, v_means, cb, ce);    \
+        } else {                                                                                                     \
+            auto kern = sh_colors_staged_bwd_kernel<NBV, SPLIT, false>;                                              \
+            if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            kern<<<grid, 32 * kStageWarps, smem, st>>>(C, N, K, deg, means, campos, sh0, rest, radii, colors,        \
+                                                       v_colors, v_sh0, v_rest, v_means, cb, ce);                    \
+        }                                                                                                            \
     } while (0)
     switch (deg) {
         case 0: B2S_SHS(1); break;
