@@ -610,7 +610,8 @@ static void launch_bwd_quad(uint32_t C, uint64_t n_isects, uint32_t channels, co
         v_opacities)
     switch (tuning_variant()) {
         case 1: B2S_BWDQ(4, 16, 1, 0, 0); break;   // butterfly commit, register prefetch (r1_c default)
-        case 2: B2S_BWDQ(2, 16, 0, 0, 0); break;
+        case 2: B2S_BWDQ(2, 10, 1, 1, 1); break;   // two warps per tile (upper / lower half), 96 registers
+        case 6: B2S_BWDQ(2, 12, 1, 1, 1); break;   // same, 80 registers
         case 3: B2S_BWDQ(4, 16, 1, 1, 0); break;   // shared-memory commit, register prefetch
         case 4: B2S_BWDQ(4, 16, 0, 0, 0); break;
         case 5: B2S_BWDQ(4, 18, 1, 1, 1); break;   // same, 112 registers

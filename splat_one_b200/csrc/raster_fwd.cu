@@ -365,7 +365,8 @@ static void launch_fwd_quad(uint32_t C, uint64_t n_isects, uint32_t channels, co
         render_colors, render_alphas, last_ids)
     switch (tuning_variant()) {
         case 1: B2S_FWDQ(4, 16, 0, 0); break;
-        case 2: B2S_FWDQ(2, 16, 0, 0); break;
+        case 2: B2S_FWDQ(2, 12, 0, 1); break;   // two warps per tile
+        case 6: B2S_FWDQ(2, 16, 0, 1); break;
         case 3: B2S_FWDQ(4, 20, 0, 0); break;   // register prefetch of the records (r1_c default)
         case 4: B2S_FWDQ(4, 20, 1, 0); break;   // joint quads measured slower here (0.416 vs 0.383 ms)
         case 5: B2S_FWDQ(4, 24, 0, 1); break;   // cp.async record prefetch, 80 registers
