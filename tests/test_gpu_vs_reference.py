@@ -1,0 +1,197 @@
+"""GPU parity against the reference's OWN CUDA kernels (the fork's gsplat extension built for
+sm_100a by oracle/build_ref.py into oracle/_ref/, called through its pybind11 entry points,
+CS/ext.cpp:11-56).  Every comparison feeds the SAME inputs to both implementations at the
+operator boundary (SURVEY.md §8a bit-exactness note i).  This is what pins
+`camera_model="spherical"`, for which the reference has no CPU implementation that matches its
+CUDA.  Skipped when oracle/_ref was not built.
+
+Tolerances: integer outputs bit-exact; floats 1e-4 abs/rel (images), 1e-3 rel (gradients);
+decision-threshold flips between two fast-math implementations are bounded by fraction."""
+import math
+
+import pytest
+import torch
+
+import splat_one_b200 as S
+from oracle import ref_cuda
+from parity import assert_grad_close
+from splat_one_b200 import synthetic, wrapper
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_cuda.available(), reason="oracle/_ref not built")]
+DEV = "cuda:0"
+
+
+def _scene(model, N=30000, W=320, H=240, C=2, seed=3):
+    if model == "spherical":
+        sc = synthetic.spherical_scene(N, 512, 256, seed=seed)
+        sc["viewmats"] = sc["viewmats"].repeat(C, 1, 1)
+        sc["viewmats"][1:, :3, 3] = 0.3
+        sc["Ks"] = sc["Ks"].repeat(C, 1, 1)
+        W, H = 512, 256
+    else:
+        sc = synthetic.pinhole_scene(N, W, H, seed=seed, n_cameras=C)
+        if model == "ortho":
+            sc["Ks"][:, 0, 0] = sc["Ks"][:, 1, 1] = 40.0
+    return {k: (v.to(DEV) if isinstance(v, torch.Tensor) else v) for k, v in sc.items()}, W, H
+
+
+@pytest.mark.parametrize("model", ["pinhole", "ortho", "fisheye", "spherical"])
+@pytest.mark.parametrize("comp", [False, True])
+def test_projection_fwd_bwd_vs_reference_cuda(model, comp):
+    R = ref_cuda.load()
+    sc, W, H = _scene(model)
+    cm = ref_cuda.camera_model(R, model)
+    args = (sc["means"], None, sc["quats"], sc["scales"], sc["viewmats"], sc["Ks"], W, H, 0.3, 0.01, 1e10, 0.0)
+    r_radii, r_m2d, r_dep, r_con, r_comp = R.fully_fused_projection_fwd(*args, comp, cm)
+    radii, m2d, dep, con, cmp_ = S.fully_fused_projection(
+        sc["means"], None, sc["quats"], sc["scales"], sc["viewmats"], sc["Ks"], W, H, calc_compensations=comp,
+        camera_model=model)
+    vis = (r_radii > 0) & (radii > 0)
+    assert ((r_radii > 0) != (radii > 0)).float().mean().item() < 1e-4   # culling decisions
+    assert vis.float().mean().item() > 0.2
+    assert ((r_radii - radii).abs()[vis] > 1).sum().item() == 0           # ceil() of a rounded value
+    assert ((r_radii - radii).abs()[vis] > 0).float().mean().item() < 2e-3
+    for name, a, b in (("means2d", m2d, r_m2d), ("depths", dep, r_dep), ("conics", con, r_con)):
+        a, b = a[vis], b[vis]
+        assert torch.allclose(a, b, rtol=2e-4, atol=1e-4), (model, name, (a - b).abs().max().item())
+    if comp:
+        assert torch.allclose(cmp_[vis], r_comp[vis], rtol=1e-4, atol=1e-5)
+    # backward on identical forward state (the reference's radii / conics / compensations)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    v_m2d = torch.randn(r_m2d.shape, device=DEV, generator=g)
+    v_dep = torch.randn(r_dep.shape, device=DEV, generator=g)
+    v_con = torch.randn(r_con.shape, device=DEV, generator=g) * 0.1
+    v_cmp = torch.randn(r_dep.shape, device=DEV, generator=g) if comp else None
+    rv_means, _, rv_quats, rv_scales, _ = R.fully_fused_projection_bwd(
+        sc["means"], None, sc["quats"], sc["scales"], sc["viewmats"], sc["Ks"], W, H, 0.3, cm, r_radii, r_con,
+        r_comp if comp else None, v_m2d, v_dep, v_con, v_cmp, False)
+    P = [sc[k].clone().requires_grad_() for k in ("means", "quats", "scales")]
+    radii, m2d, dep, con, cmp_ = S.fully_fused_projection(P[0], None, P[1], P[2], sc["viewmats"], sc["Ks"], W, H,
+                                                          calc_compensations=comp, camera_model=model)
+    both = ((r_radii > 0) & (radii > 0))
+    loss = (m2d * v_m2d * both[..., None]).sum() + (dep * v_dep * both).sum() + (con * v_con * both[..., None]).sum()
+    if comp:
+        loss = loss + (cmp_ * v_cmp * both).sum()
+    gm, gq, gs = torch.autograd.grad(loss, P)
+    # rows whose visibility differs between the two forwards are excluded on both sides
+    same = ((r_radii > 0) == (radii > 0)).all(dim=0)
+    for name, a, b in (("v_means", gm, rv_means), ("v_quats", gq, rv_quats), ("v_scales", gs, rv_scales)):
+        assert_grad_close(a[same], b[same], what=f"{model} {name} vs reference CUDA", frac_ok=0.999)
+
+
+@pytest.mark.parametrize("C,N,W,H,ts", [(1, 50000, 640, 360, 16), (3, 20000, 320, 200, 16), (2, 5000, 100, 60, 4)])
+def test_isect_bit_exact_vs_reference_cuda(C, N, W, H, ts):
+    R = ref_cuda.load()
+    sc = synthetic.pinhole_scene(N, W, H, seed=11, n_cameras=C)
+    sc = {k: (v.to(DEV) if isinstance(v, torch.Tensor) else v) for k, v in sc.items()}
+    radii, m2d, dep, con, _ = S.fully_fused_projection(sc["means"], None, sc["quats"], sc["scales"], sc["viewmats"],
+                                                       sc["Ks"], W, H)
+    tw, th = math.ceil(W / ts), math.ceil(H / ts)
+    r_tpg, r_ids, r_flat = R.isect_tiles(m2d, radii, dep, None, None, C, ts, tw, th, True, True)
+    tpg, ids, flat = S.isect_tiles(m2d, radii, dep, ts, tw, th)
+    assert torch.equal(tpg, r_tpg) and torch.equal(ids, r_ids) and torch.equal(flat, r_flat)
+    r_off = R.isect_offset_encode(r_ids, C, tw, th)
+    assert torch.equal(S.isect_offset_encode(ids, C, tw, th), r_off)
+    _, _, _, off2 = wrapper.isect_tiles_and_offsets(m2d, radii, dep, ts, tw, th)
+    assert torch.equal(off2, r_off)
+
+
+def test_isect_packed_bit_exact_vs_reference_cuda():
+    R = ref_cuda.load()
+    C, N, W, H = 2, 20000, 320, 200
+    sc = synthetic.pinhole_scene(N, W, H, seed=12, n_cameras=C)
+    sc = {k: (v.to(DEV) if isinstance(v, torch.Tensor) else v) for k, v in sc.items()}
+    cam, gid, radii, m2d, dep, con, _ = S.fully_fused_projection(sc["means"], None, sc["quats"], sc["scales"],
+                                                                 sc["viewmats"], sc["Ks"], W, H, packed=True)
+    r_out = R.fully_fused_projection_packed_fwd(sc["means"], None, sc["quats"], sc["scales"], sc["viewmats"], sc["Ks"],
+                                                W, H, 0.3, 0.01, 1e10, 0.0, False, R.CameraModelType.PINHOLE)
+    r_cam, r_gid = r_out[1], r_out[2]
+    # same visible set up to threshold ties
+    ours = set(zip(cam.tolist(), gid.tolist()))
+    theirs = set(zip(r_cam.tolist(), r_gid.tolist()))
+    assert len(ours ^ theirs) <= 1e-4 * len(theirs) + 2
+    tw, th = math.ceil(W / 16), math.ceil(H / 16)
+    r_tpg, r_ids, r_flat = R.isect_tiles(m2d, radii, dep, cam, gid, C, 16, tw, th, True, True)
+    tpg, ids, flat = S.isect_tiles(m2d, radii, dep, 16, tw, th, packed=True, n_cameras=C, camera_ids=cam,
+                                   gaussian_ids=gid)
+    assert torch.equal(tpg, r_tpg) and torch.equal(ids, r_ids) and torch.equal(flat, r_flat)
+
+
+@pytest.mark.parametrize("D,bg,absgrad", [(3, False, False), (3, True, True), (1, False, False), (4, True, False)])
+def test_rasterize_fwd_bwd_vs_reference_cuda(D, bg, absgrad):
+    R = ref_cuda.load()
+    C, N, W, H = 1, 40000, 480, 270
+    sc = synthetic.pinhole_scene(N, W, H, seed=21, n_cameras=C)
+    sc = {k: (v.to(DEV) if isinstance(v, torch.Tensor) else v) for k, v in sc.items()}
+    radii, m2d, dep, con, _ = S.fully_fused_projection(sc["means"], None, sc["quats"], sc["scales"], sc["viewmats"],
+                                                       sc["Ks"], W, H)
+    g = torch.Generator(device=DEV).manual_seed(2)
+    colors = torch.rand(C, N, D, device=DEV, generator=g)
+    opac = sc["opacities"][None].expand(C, -1).contiguous()
+    backgrounds = torch.rand(C, D, device=DEV, generator=g) if bg else None
+    tw, th = math.ceil(W / 16), math.ceil(H / 16)
+    _, ids, flat = S.isect_tiles(m2d, radii, dep, 16, tw, th)
+    offs = S.isect_offset_encode(ids, C, tw, th)
+    r_rc, r_ra, r_last = R.rasterize_to_pixels_fwd(m2d, con, colors, opac, backgrounds, None, W, H, 16, offs, flat)
+    P = [t.clone().requires_grad_() for t in (m2d, con, colors, opac)]
+    rc, ra = S.rasterize_to_pixels(*P, W, H, 16, offs, flat, backgrounds=backgrounds, absgrad=absgrad)
+    for name, a, b in (("colors", rc, r_rc), ("alphas", ra, r_ra)):
+        err = (a - b).abs()
+        bad = err > 1e-4 + 1e-4 * b.abs()
+        assert bad.float().mean().item() < 1e-3, (name, bad.float().mean().item(), err.max().item())
+        assert err.max().item() < 2e-2, (name, err.max().item())
+    v_rc = torch.randn(rc.shape, device=DEV, generator=g)
+    v_ra = torch.randn(ra.shape, device=DEV, generator=g)
+    r_abs, rv_m2d, rv_con, rv_col, rv_op = R.rasterize_to_pixels_bwd(
+        m2d, con, colors, opac, backgrounds, None, W, H, 16, offs, flat, r_ra, r_last, v_rc, v_ra, absgrad)
+    gm, gc, gcol, gop = torch.autograd.grad((rc * v_rc).sum() + (ra * v_ra).sum(), P)
+    for name, a, b in (("v_means2d", gm, rv_m2d), ("v_conics", gc, rv_con), ("v_colors", gcol, rv_col),
+                       ("v_opacities", gop, rv_op)):
+        assert_grad_close(a, b, what=f"{name} vs reference CUDA", frac_ok=0.998)
+    if absgrad:
+        assert_grad_close(P[0].absgrad, r_abs, what="absgrad vs reference CUDA", frac_ok=0.998)
+
+
+@pytest.mark.parametrize("deg", [0, 1, 2, 3, 4])
+def test_sh_vs_reference_cuda(deg):
+    R = ref_cuda.load()
+    N, K = 5000, 25
+    g = torch.Generator(device=DEV).manual_seed(deg)
+    dirs = torch.randn(N, 3, device=DEV, generator=g)
+    coeffs = torch.randn(N, K, 3, device=DEV, generator=g)
+    masks = torch.rand(N, device=DEV, generator=g) > 0.3
+    r_col = R.compute_sh_fwd(deg, dirs, coeffs, masks)
+    d, c = dirs.clone().requires_grad_(), coeffs.clone().requires_grad_()
+    col = S.spherical_harmonics(deg, d, c, masks=masks)
+    assert torch.allclose(col[masks], r_col[masks], rtol=1e-5, atol=1e-5)
+    v = torch.randn(N, 3, device=DEV, generator=g)
+    rv_c, rv_d = R.compute_sh_bwd(K, deg, dirs, coeffs, masks, v, True)
+    gd, gc = torch.autograd.grad((col * v).sum(), (d, c))
+    assert_grad_close(gc, rv_c, what="v_coeffs vs reference CUDA", frac_ok=1.0)
+    assert_grad_close(gd, rv_d, what="v_dirs vs reference CUDA", frac_ok=1.0)
+
+
+def test_rasterization_end_to_end_vs_reference_cuda_chain():
+    """rasterization() (spherical, config D shaped) against the reference kernels chained the way
+    G/rendering.py chains them."""
+    R = ref_cuda.load()
+    N, W, H = 60000, 512, 256
+    sc = synthetic.spherical_scene(N, W, H, seed=5)
+    sc = {k: (v.to(DEV) if isinstance(v, torch.Tensor) else v) for k, v in sc.items()}
+    rc, ra, meta = S.rasterization(sc["means"], sc["quats"], sc["scales"], sc["opacities"], sc["sh"], sc["viewmats"],
+                                   sc["Ks"], W, H, sh_degree=3, packed=False, camera_model="spherical")
+    radii, m2d, dep, con, _ = R.fully_fused_projection_fwd(
+        sc["means"], None, sc["quats"], sc["scales"], sc["viewmats"], sc["Ks"], W, H, 0.3, 0.01, 1e10, 0.0, False,
+        R.CameraModelType.SPHERICAL)
+    campos = torch.inverse(sc["viewmats"])[:, :3, 3]
+    dirs = sc["means"][None] - campos[:, None]
+    col = R.compute_sh_fwd(3, dirs, sc["sh"][None].contiguous(), radii > 0)
+    col = torch.clamp_min(col + 0.5, 0.0)
+    tw, th = math.ceil(W / 16), math.ceil(H / 16)
+    _, ids, flat = R.isect_tiles(m2d, radii, dep, None, None, 1, 16, tw, th, True, True)
+    offs = R.isect_offset_encode(ids, 1, tw, th)
+    r_rc, r_ra, _ = R.rasterize_to_pixels_fwd(m2d, con, col, sc["opacities"][None].contiguous(), None, None, W, H, 16,
+                                              offs, flat)
+    for a, b in ((rc, r_rc), (ra, r_ra)):
+        err = (a - b).abs()
+        assert (err > 1e-4 + 1e-4 * b.abs()).float().mean().item() < 2e-3, err.max().item()
