@@ -66,7 +66,7 @@ projection_fwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
 // ---------------------------------------------------------------------------------------
 // a3: one thread per Gaussian, loop over cameras; no atomics on the parameter grads.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads)   // (kThreads, 3) = 80 registers spills: 0.059 vs 0.055 ms
 projection_bwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, const float *__restrict__ covars,
                       const float *__restrict__ quats, const float *__restrict__ scales,
                       const float *__restrict__ viewmats, const float *__restrict__ Ks, uint32_t W, uint32_t H,

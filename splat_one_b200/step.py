@@ -48,6 +48,11 @@ class _SplatActivations(torch.autograd.Function):
         scales, opacities = ctx.saved_tensors
         N = opacities.shape[0]
         need_s, need_o = ctx.needs_input_grad
+        # packed + sparse_grad projection hands back sparse COO cotangents (_wrapper.py:1163-1203)
+        if v_scales is not None and v_scales.is_sparse:
+            v_scales = v_scales.to_dense()
+        if v_opacities is not None and v_opacities.is_sparse:
+            v_opacities = v_opacities.to_dense()
         v_scales_raw = _grad_out(scales) if need_s else None
         v_opacities_raw = _grad_out(opacities) if need_o else None
         if N and (need_s or need_o):

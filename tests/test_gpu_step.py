@@ -136,3 +136,51 @@ def test_rasterize_splats_and_loss_match_oracle_step():
     rc_q, _, _ = S.rasterization(det["means"], det["quats"], sc, op, torch.cat([det["sh0"], det["shN"]], 1),
                                  scene["viewmats"].to(DEV), scene["Ks"].to(DEV), W, H, sh_degree=3, packed=True)
     assert (rc_p - rc_q).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize("opts", [dict(antialiased=True), dict(render_mode="RGB+ED"), dict(absgrad=True),
+                                  dict(camera_model="fisheye"), dict(packed=True, sparse_grad=True)])
+def test_rasterize_splats_options_equal_composed_call(opts):
+    """rasterize_splats(...) == activations + cat + rasterization(...) written out as
+    gsplat_trainer.py:446-497 does, for the options the trainer forwards (incl. masks)."""
+    W, H, N = 128, 96, 3000
+    scene = synthetic.pinhole_scene(N, W, H, seed=8, n_cameras=2)
+    raw = {
+        "means": scene["means"], "quats": scene["quats"], "scales": torch.log(scene["scales"]),
+        "opacities": torch.logit(scene["opacities"].clamp(1e-4, 1 - 1e-4)),
+        "sh0": scene["sh"][:, :1].contiguous(), "shN": scene["sh"][:, 1:].contiguous(),
+    }
+    Pg = {k: v.to(DEV).requires_grad_() for k, v in raw.items()}
+    Pc = {k: v.to(DEV).requires_grad_() for k, v in raw.items()}
+    vm, Ks = scene["viewmats"].to(DEV), scene["Ks"].to(DEV)
+    c2w = torch.inverse(vm)
+    g = torch.Generator().manual_seed(4)
+    masks = (torch.rand(2, H, W, generator=g) > 0.1).to(DEV)
+    o = dict(opts)
+    rc, ra, info = S.rasterize_splats(Pg, c2w, Ks, W, H, masks=masks, sh_degree=3, **o)
+    aa = o.pop("antialiased", False)
+    rc2, ra2, info2 = S.rasterization(
+        Pc["means"], Pc["quats"], torch.exp(Pc["scales"]), torch.sigmoid(Pc["opacities"]),
+        torch.cat([Pc["sh0"], Pc["shN"]], 1), torch.linalg.inv(c2w), Ks, W, H, sh_degree=3,
+        rasterize_mode="antialiased" if aa else "classic", **{"packed": False, **o})
+    rc2 = rc2.clone()
+    rc2[~masks] = 0
+    # the two pose inverses differ in the last bit, which can flip isolated alpha >= 1/255 decisions
+    for a, b in ((rc, rc2), (ra, ra2)):
+        err = (a - b).abs()
+        assert (err > 2e-6 + 1e-5 * b.abs()).float().mean().item() < 1e-3, err.max()
+        assert err.max().item() < 5e-3, err.max()
+    assert (rc[~masks] == 0).all()
+    v = torch.randn(rc.shape, generator=g).to(DEV)
+    if o.get("absgrad"):
+        info["means2d"].retain_grad()
+        info2["means2d"].retain_grad()
+    (rc * v).sum().backward()
+    (rc2 * v).sum().backward()
+    for k in raw:
+        a, b = Pg[k].grad, Pc[k].grad
+        a = a.to_dense() if a.is_sparse else a
+        b = b.to_dense() if b.is_sparse else b
+        assert_grad_close(a, b, what=f"rasterize_splats grad {k} ({opts})", frac_ok=0.999)
+    if o.get("absgrad"):
+        assert_grad_close(info["means2d"].absgrad, info2["means2d"].absgrad, what="absgrad", frac_ok=0.999)

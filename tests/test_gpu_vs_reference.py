@@ -51,9 +51,13 @@ def test_projection_fwd_bwd_vs_reference_cuda(model, comp):
     assert vis.float().mean().item() > 0.2
     assert ((r_radii - radii).abs()[vis] > 1).sum().item() == 0           # ceil() of a rounded value
     assert ((r_radii - radii).abs()[vis] > 0).float().mean().item() < 2e-3
+    # spherical: lat = asin(y/r) is ill-conditioned at the poles (d asin = d(y/r) / sqrt(1 - (y/r)²)), so
+    # two fp32 evaluations of y/r differ by up to ~1e-3 px there; everywhere else 1e-4 holds
+    atol = {"means2d": 5e-3 if model == "spherical" else 1e-4, "depths": 1e-4, "conics": 1e-4}
     for name, a, b in (("means2d", m2d, r_m2d), ("depths", dep, r_dep), ("conics", con, r_con)):
         a, b = a[vis], b[vis]
-        assert torch.allclose(a, b, rtol=2e-4, atol=1e-4), (model, name, (a - b).abs().max().item())
+        assert torch.allclose(a, b, rtol=2e-4, atol=atol[name]), (model, name, (a - b).abs().max().item())
+        assert ((a - b).abs() > 1e-4 + 2e-4 * b.abs()).float().mean().item() < 1e-3, (model, name)
     if comp:
         assert torch.allclose(cmp_[vis], r_comp[vis], rtol=1e-4, atol=1e-5)
     # backward on identical forward state (the reference's radii / conics / compensations)
