@@ -48,6 +48,13 @@ B200SPLAT_API const char *b200splat_last_error(void);
 /* Compile-time facts, for diagnostics: returns "sm_100a". */
 B200SPLAT_API const char *b200splat_arch(void);
 
+/* Copy n_words 32-bit words from device memory to PINNED host memory from inside a kernel (no
+ * DMA engine): the read-back of n_isects / nnz between the `*_count` and `*_fill` halves of the
+ * two-phase calls (replaces the blocking `.item()` of CS/isect_tiles.cu:201 and
+ * CS/fully_fused_projection_packed_fwd.cu:352-353).  The host waits on an event recorded behind
+ * this call on the same stream. */
+B200SPLAT_API int b200splat_copy_small(const void *src, void *dst_pinned_host, uint32_t n_words, void *stream);
+
 /* ------------------------------------------------------------------------------------
  * a2  fully_fused_projection_fwd        CS/bindings.h:95-116, kernel
  *     CS/fully_fused_projection_fwd.cu:20-216.

@@ -17,7 +17,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("B200SPLAT_LIB", _PKG / "libb200splat.so"))
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 _P = c_void_p
 _U32 = c_uint32
@@ -31,6 +31,7 @@ SIGNATURES = {
     "b200splat_abi_version": (_I, []),
     "b200splat_last_error": (c_char_p, []),
     "b200splat_arch": (c_char_p, []),
+    "b200splat_copy_small": (_I, [_P, _P, _U32, _P]),
     "b200splat_projection_fwd": (_I, _PROJ_COMMON + [_F, _F, _F, _F, _I, _P, _P, _P, _P, _P, _P]),
     "b200splat_projection_bwd": (
         _I, _PROJ_COMMON + [_F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -24,13 +24,18 @@ from .wrapper import (
     fully_fused_projection,
     gather_rows,
     sh_view_colors_packed,
-    isect_tiles_and_offsets,
+    isect_tiles_and_offsets_begin,
     rasterize_to_pixels,
     sh_view_colors,
     sh_view_colors_split,
     spherical_harmonics,
     staged_colors_supported,
 )
+
+
+import os as _os
+
+_ISECT_LATE = _os.environ.get("B200SPLAT_ISECT_LATE", "0") == "1"  # A/B: queue the intersection stage after the colours
 
 
 def rasterization(
@@ -152,6 +157,18 @@ def rasterization(
         "opacities": opacities,
     })
 
+    # ---- tile intersection, first half (a6): count, depth order and the n_isects read-back are
+    # queued here, so the host's wait for n_isects overlaps the colour stage as well.
+    # (concurrent=True would put this half on a side stream next to the colour kernels: measured
+    # no gain at config B — both are bandwidth-bound — and 0.4 ms worse with host copies in flight.)
+    tile_width = math.ceil(width / float(tile_size))
+    tile_height = math.ceil(height / float(tile_size))
+    isect_args = dict(packed=packed, n_cameras=C, camera_ids=camera_ids, gaussian_ids=gaussian_ids, concurrent=False)
+    isect_finish = None
+    if not _ISECT_LATE:
+        isect_finish = isect_tiles_and_offsets_begin(means2d, radii, depths, tile_size, tile_width, tile_height,
+                                                     **isect_args)
+
     # ---- colours (a5) -----------------------------------------------------------------
     if sh_degree is None:
         if packed:
@@ -188,13 +205,11 @@ def rasterization(
         if backgrounds is not None:
             backgrounds = torch.zeros(C, 1, device=backgrounds.device)
 
-    # ---- tile intersection (a6, a7) ---------------------------------------------------
-    tile_width = math.ceil(width / float(tile_size))
-    tile_height = math.ceil(height / float(tile_size))
-    tiles_per_gauss, isect_ids, flatten_ids, isect_offsets = isect_tiles_and_offsets(
-        means2d, radii, depths, tile_size, tile_width, tile_height,
-        packed=packed, n_cameras=C, camera_ids=camera_ids, gaussian_ids=gaussian_ids,
-    )
+    # ---- tile intersection, second half (a6, a7): tile order, ids, offsets ------------------
+    if isect_finish is None:
+        isect_finish = isect_tiles_and_offsets_begin(means2d, radii, depths, tile_size, tile_width, tile_height,
+                                                     **isect_args)
+    tiles_per_gauss, isect_ids, flatten_ids, isect_offsets = isect_finish()
 
     meta.update({
         "tile_width": tile_width,

@@ -50,7 +50,7 @@ class _Profiler:
         "projection_fwd": 1, "projection_bwd": 1, "projection_packed_count": 3, "projection_packed_fill": 1,
         "projection_packed_bwd": 1, "sh_fwd": 1, "sh_bwd": 1, "camera_centers": 1, "sh_colors_fwd": 1,
         "sh_colors_bwd": 1, "sh_colors_packed_fwd": 1, "sh_colors_packed_bwd": 1, "isect_count": 2, "isect_fill": 1,
-        "isect_sort": 0, "isect_sorted": 5, "isect_depth_order": 3, "isect_tile_order": 2, "invert_4x4": 1, "isect_offset_encode": 1, "rasterize_pack": 1, "rasterize_fwd": 1, "rasterize_bwd": 1,
+        "isect_sort": 0, "isect_sorted": 5, "isect_depth_order": 3, "isect_tile_order": 2, "invert_4x4": 1, "copy_small": 1, "isect_offset_encode": 1, "rasterize_pack": 1, "rasterize_fwd": 1, "rasterize_bwd": 1,
         "raster_indices_count": 2, "raster_indices_fill": 1, "quat_scale_to_covar_preci_fwd": 1,
         "quat_scale_to_covar_preci_bwd": 1, "world_to_cam_fwd": 1, "world_to_cam_bwd": 1, "proj_fwd": 1, "proj_bwd": 1,
         "selective_adam_update": 1, "compute_relocation": 1, "sh_colors_staged_fwd": 1, "sh_colors_staged_bwd": 1,
@@ -107,30 +107,61 @@ def _stream(device: torch.device):
 _PINNED = threading.local()
 
 
-def _read_back(t: Tensor, ready: Optional["torch.cuda.Event"] = None):
-    """Values of a tiny device tensor on the host: one copy into a per-thread pinned buffer.
-    With `ready` (an event recorded when `t` was produced) the copy runs on a side stream, so
-    kernels queued on the current stream AFTER the event keep running while the host waits."""
-    buf = getattr(_PINNED, "buf", None)
-    if buf is None or buf.dtype != t.dtype or buf.numel() < t.numel():
-        buf = torch.empty((max(t.numel(), 8),), dtype=t.dtype, pin_memory=True)
-        _PINNED.buf = buf
-    view = buf[: t.numel()]
-    if ready is None:
-        view.copy_(t, non_blocking=True)
-        torch.cuda.current_stream(t.device).synchronize()
-        return view.tolist()
+def _side_stream(device) -> "torch.cuda.Stream":
     side = getattr(_PINNED, "streams", None)
     if side is None:
         side = _PINNED.streams = {}
-    st = side.get(t.device)
+    st = side.get(device)
     if st is None:
-        st = side[t.device] = torch.cuda.Stream(device=t.device)
-    st.wait_event(ready)
-    with torch.cuda.stream(st):
-        view.copy_(t, non_blocking=True)
-    st.synchronize()
-    return view.tolist()
+        st = side[device] = torch.cuda.Stream(device=device)
+    return st
+
+
+_RING = 256  # pinned read-back slots per thread (16 bytes each), used round-robin
+_LEGACY_READBACK = os.environ.get("B200SPLAT_LEGACY_READBACK", "0") == "1"  # A/B switch: blocking .tolist()
+
+
+def _start_read_back(t: Tensor, ready: Optional["torch.cuda.Event"], device):
+    """Queue the read-back of a tiny device tensor (<= 16 bytes) and return a callable that waits
+    for it and returns the values.  A one-warp kernel stores the words straight into a slot of a
+    per-thread pinned (device-mapped) host buffer and the host waits on an event recorded behind
+    it: no copy engine is involved, so the read-back cannot queue behind an unrelated large
+    cudaMemcpyAsync of the application, and kernels queued behind the event keep running while
+    the host waits.  (`ready` is kept for callers that recorded their own event; unused.)"""
+    if _LEGACY_READBACK:
+        return lambda: t.tolist()
+    st = getattr(_PINNED, "state", None)
+    if st is None:
+        ring = torch.zeros((_RING, 2), dtype=torch.int64, pin_memory=True)
+        st = _PINNED.state = {"ring": ring, "i64": ring.numpy(), "i32": ring.view(torch.int32).numpy(), "next": 0,
+                              "events": [None] * _RING}
+    n = t.numel()
+    n_bytes = n * t.element_size()
+    assert t.dtype in (torch.int64, torch.int32) and n_bytes <= 16 and t.is_contiguous(), (t.dtype, t.shape)
+    k = st["next"] % _RING
+    st["next"] += 1
+    lib = get_lib()
+    stream = torch.cuda.current_stream(device)
+    with torch.cuda.device(device):
+        check(lib.b200splat_copy_small(_ptr(t), ctypes.c_void_p(st["ring"].data_ptr() + 16 * k), n_bytes // 4,
+                                       ctypes.c_void_p(stream.cuda_stream)), lib)
+        if profiler.enabled:
+            profiler.calls["copy_small"] = profiler.calls.get("copy_small", 0) + 1
+        done = st["events"][k]
+        if done is None:
+            done = st["events"][k] = torch.cuda.Event()
+        done.record(stream)
+    view = st["i64"] if t.dtype == torch.int64 else st["i32"]
+
+    def wait():
+        done.synchronize()
+        return view[k, :n].tolist()
+
+    return wait
+
+
+def _read_back(t: Tensor, ready: Optional["torch.cuda.Event"] = None):
+    return _start_read_back(t, ready, t.device)()
 
 
 def _check_cuda(*tensors: Optional[Tensor]) -> None:
@@ -677,7 +708,7 @@ class _FullyFusedProjectionPacked(torch.autograd.Function):
             native("projection_packed_count", lib, dev, C, N, _ptr(means), _ptr(covars), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks),
                     width, height, eps2d, near_plane, far_plane, radius_clip, cm, _ptr(block_accum),
                     _ptr(nnz_dev))
-            nnz = int(nnz_dev.item())  # the one host sync (CS/...packed_fwd.cu:352-353)
+            nnz = int(_read_back(nnz_dev)[0])  # the one host sync (CS/...packed_fwd.cu:352-353)
         indptr = torch.zeros((C + 1,), device=dev, dtype=torch.int32)
         camera_ids = torch.empty((nnz,), device=dev, dtype=torch.int64)
         gaussian_ids = torch.empty((nnz,), device=dev, dtype=torch.int64)
@@ -750,7 +781,7 @@ class _FullyFusedProjectionPacked(torch.autograd.Function):
 # tile intersection (a6) and offset encode (a7)
 # ----------------------------------------------------------------------------------------
 @torch.no_grad()
-def _isect_tiles_impl(
+def _isect_tiles_begin(
     means2d: Tensor,  # [C, N, 2] or [nnz, 2]
     radii: Tensor,  # [C, N] or [nnz]
     depths: Tensor,  # [C, N] or [nnz]
@@ -763,9 +794,14 @@ def _isect_tiles_impl(
     camera_ids: Optional[Tensor] = None,
     gaussian_ids: Optional[Tensor] = None,
     want_offsets: bool = False,
+    concurrent: bool = False,
 ):
-    """isect_tiles; with `want_offsets` also the [C, tile_height, tile_width] offsets of
-    isect_offset_encode, which the depth-first path produces in its final pass for free."""
+    """isect_tiles in two halves: this call validates, allocates and queues everything that does
+    not need `n_isects` (count, scan, depth order, the read-back) and returns `finish`, which waits
+    for `n_isects`, allocates the outputs and queues the rest.  With `want_offsets` `finish()` also
+    returns the [C, tile_height, tile_width] offsets of isect_offset_encode, which the depth-first
+    path produces in its final pass for free.  `concurrent`: run the first half on a side stream
+    (see below) so that work the caller queues between the two calls overlaps it."""
     if packed:
         nnz = means2d.size(0)
         assert means2d.shape == (nnz, 2), means2d.size()
@@ -802,29 +838,64 @@ def _isect_tiles_impl(
     assert tile_n_bits + cam_n_bits <= 32, (tile_n_bits, cam_n_bits)
 
     tiles_per_gauss = torch.empty(radii.shape, device=dev, dtype=torch.int32)
-    n_isects, neg_depth = 0, False
     depth_first = sort and not _FORCE_GENERIC_SORT
     depth_ws, depth_sel = None, ctypes.c_int(0)
+    cum_tiles = n_isects_dev = None
+    side = ready = None
     if n_elems:
         cum_tiles = torch.empty((n_elems,), device=dev, dtype=torch.int64)
         n_isects_dev = torch.empty((2,), device=dev, dtype=torch.int64)
         ws_bytes = lib.b200splat_scan_workspace_bytes(n_elems)
         ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
-        native("isect_count", lib, dev, int(packed), C, N, nnz, _ptr(means2d), _ptr(radii), _ptr(depths), tile_size,
-               tile_width, tile_height, _ptr(tiles_per_gauss), _ptr(cum_tiles), _ptr(n_isects_dev), _ptr(ws), ws_bytes)
-        ready = None
+        dws_bytes = 0
         if depth_first:
-            # phase 1 of the depth-first ordering needs only n_elems: it is queued BEFORE the host
-            # reads n_isects back (on a side stream), so that round trip overlaps ~0.1 ms of device work
-            ready = torch.cuda.Event()
-            ready.record(torch.cuda.current_stream(dev))
             dws_bytes = lib.b200splat_isect_depth_order_workspace_bytes(n_elems)
             depth_ws = torch.empty((dws_bytes,), device=dev, dtype=torch.uint8)
-            native("isect_depth_order", lib, dev, n_elems, _ptr(depths), _ptr(tiles_per_gauss), _ptr(depth_ws),
-                   dws_bytes, ctypes.byref(depth_sel))
-        n_isects, neg = _read_back(n_isects_dev, ready)  # the one host sync (CS/isect_tiles.cu:201)
-        neg_depth = bool(neg)
+        main = torch.cuda.current_stream(dev)
+        if concurrent and depth_first:
+            # everything up to the read-back runs on a side stream: the caller's next kernels on the
+            # current stream (the colour stage) execute concurrently with the count + depth-order
+            # phase.  All buffers were allocated above, BEFORE this event, so the side stream never
+            # touches a block whose previous use on the current stream is still pending.
+            side = _side_stream(dev)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            side.wait_event(fork)
+        with torch.cuda.stream(side if side is not None else main):
+            native("isect_count", lib, dev, int(packed), C, N, nnz, _ptr(means2d), _ptr(radii), _ptr(depths),
+                   tile_size, tile_width, tile_height, _ptr(tiles_per_gauss), _ptr(cum_tiles), _ptr(n_isects_dev),
+                   _ptr(ws), ws_bytes)
+            # the read-back is queued right behind the count ...
+            pending = _start_read_back(n_isects_dev, None, dev)
+            if depth_first:
+                # ... and phase 1 of the depth-first ordering, which needs only n_elems, behind it: the
+                # host's round trip for n_isects overlaps ~0.1 ms of device work
+                native("isect_depth_order", lib, dev, n_elems, _ptr(depths), _ptr(tiles_per_gauss), _ptr(depth_ws),
+                       dws_bytes, ctypes.byref(depth_sel))
+                if side is not None:
+                    join = torch.cuda.Event()
+                    join.record(side)
+    else:
+        pending = None
 
+    @torch.no_grad()
+    def finish():
+        n_isects, neg_depth = 0, False
+        if pending is not None:
+            n_isects, neg = pending()  # the one host sync (CS/isect_tiles.cu:201)
+            neg_depth = bool(neg)
+        if side is not None:
+            torch.cuda.current_stream(dev).wait_event(join)
+        return _isect_finish(lib, dev, packed, C, N, nnz, camera_ids, means2d, radii, depths, tiles_per_gauss, cum_tiles,
+                             depth_ws, depth_sel.value, depth_first, neg_depth, n_isects, sort, tile_size, tile_width,
+                             tile_height, tile_n_bits, cam_n_bits, want_offsets)
+
+    return finish
+
+
+def _isect_finish(lib, dev, packed, C, N, nnz, camera_ids, means2d, radii, depths, tiles_per_gauss, cum_tiles, depth_ws,
+                  depth_sel, depth_first, neg_depth, n_isects, sort, tile_size, tile_width, tile_height, tile_n_bits,
+                  cam_n_bits, want_offsets):
     isect_ids = torch.empty((n_isects,), device=dev, dtype=torch.int64)
     flatten_ids = torch.empty((n_isects,), device=dev, dtype=torch.int32)
     if n_isects:
@@ -835,7 +906,7 @@ def _isect_tiles_impl(
             offsets = (torch.empty((C, tile_height, tile_width), device=dev, dtype=torch.int32)
                        if want_offsets else None)
             native("isect_tile_order", lib, dev, int(packed), C, N, nnz, _ptr(camera_ids), _ptr(means2d), _ptr(radii),
-                   _ptr(depths), _ptr(depth_ws), depth_sel.value, n_isects, tile_size, tile_width, tile_height,
+                   _ptr(depths), _ptr(depth_ws), depth_sel, n_isects, tile_size, tile_width, tile_height,
                    _ptr(isect_ids), _ptr(flatten_ids), _ptr(offsets), _ptr(ws), ws_bytes)
             return tiles_per_gauss, isect_ids, flatten_ids, offsets
         native("isect_fill", lib, dev, int(packed), C, N, nnz, _ptr(camera_ids), _ptr(means2d), _ptr(radii),
@@ -872,8 +943,8 @@ def isect_tiles(
     Returns (tiles_per_gauss int32 [C,N]|[nnz], isect_ids int64 [n_isects],
     flatten_ids int32 [n_isects]); bit-exact with the reference given the same inputs.
     """
-    return _isect_tiles_impl(means2d, radii, depths, tile_size, tile_width, tile_height, sort, packed, n_cameras,
-                             camera_ids, gaussian_ids)[:3]
+    return _isect_tiles_begin(means2d, radii, depths, tile_size, tile_width, tile_height, sort, packed, n_cameras,
+                              camera_ids, gaussian_ids)()[:3]
 
 
 @torch.no_grad()
@@ -881,12 +952,27 @@ def isect_tiles_and_offsets(means2d, radii, depths, tile_size, tile_width, tile_
                             n_cameras=None, camera_ids=None, gaussian_ids=None):
     """`isect_tiles(...)` followed by `isect_offset_encode(...)` (G/rendering.py:497-510) as one
     operator: returns (tiles_per_gauss, isect_ids, flatten_ids, isect_offsets)."""
-    tpg, ids, flat, offs = _isect_tiles_impl(means2d, radii, depths, tile_size, tile_width, tile_height, True, packed,
-                                             n_cameras, camera_ids, gaussian_ids, want_offsets=True)
-    if offs is None:
-        C = n_cameras if packed else means2d.shape[0]
-        offs = isect_offset_encode(ids, C, tile_width, tile_height)
-    return tpg, ids, flat, offs
+    return isect_tiles_and_offsets_begin(means2d, radii, depths, tile_size, tile_width, tile_height, packed, n_cameras,
+                                         camera_ids, gaussian_ids, concurrent=False)()
+
+
+@torch.no_grad()
+def isect_tiles_and_offsets_begin(means2d, radii, depths, tile_size, tile_width, tile_height, packed=False,
+                                  n_cameras=None, camera_ids=None, gaussian_ids=None, concurrent=True):
+    """First half of `isect_tiles_and_offsets`; returns a callable producing its result.  What
+    `rasterization()` queues between the two halves (the colour stage) runs concurrently with the
+    count / depth-order phase when `concurrent`."""
+    fin = _isect_tiles_begin(means2d, radii, depths, tile_size, tile_width, tile_height, True, packed, n_cameras,
+                             camera_ids, gaussian_ids, want_offsets=True, concurrent=concurrent)
+
+    def finish():
+        tpg, ids, flat, offs = fin()
+        if offs is None:
+            C = n_cameras if packed else means2d.shape[0]
+            offs = isect_offset_encode(ids, C, tile_width, tile_height)
+        return tpg, ids, flat, offs
+
+    return finish
 
 
 @torch.no_grad()
