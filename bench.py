@@ -434,6 +434,15 @@ def run_gpu(args):
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "algorithmic_bytes": alg_bytes.get(dom, 0), "avg_launch_ms": stages[dom]["avg_ms"]}
+        # the north star's "raster stages": forward + backward kernels together
+        raster = None
+        if "rasterize_fwd" in stages and "rasterize_bwd" in stages:
+            t_r = (stages["rasterize_fwd"]["avg_ms"] + stages["rasterize_bwd"]["avg_ms"]) * 1e-3
+            b_r = alg_bytes["rasterize_fwd"] + alg_bytes["rasterize_bwd"]
+            raster = {"kernels": "rasterize_fwd + rasterize_bwd", "algorithmic_bytes": b_r, "ms": t_r * 1e3,
+                      "achieved": b_r / t_r / 1e9, "peak": peak, "unit": "GB/s", "frac": b_r / t_r / 1e9 / peak,
+                      "bound": "fp32 issue (ncu: DRAM throughput ~3 % of peak, issue slots 69-78 % active; "
+                               "profiles/r1_e_summary.md)"}
         stage_report = {k: {"avg_ms": round(v["avg_ms"], 4),
                             "GBps": round(alg_bytes.get(k, 0) / (v["avg_ms"] * 1e-3) / 1e9, 1) if v["avg_ms"] > 0 else None}
                         for k, v in stages.items()}
@@ -458,6 +467,7 @@ def run_gpu(args):
                             "rendered image + alpha + grad norm D2H; Gaussians stay resident (model state)"},
             "gpu_launches": launches,
             "roofline": roof,
+            "raster_stages": raster,
             "stages": stage_report,
             "train_step": train,
             "cpu_baseline": cpu,

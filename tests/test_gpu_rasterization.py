@@ -289,3 +289,50 @@ def test_rasterization_packed_sparse_grad_matches_oracle(n_cameras):
     for n, a, b in zip(names, g_got, g_ref):
         a = a.to_dense() if a.is_sparse else a
         assert_grad_close(a, b, rtol=2e-3, what=f"sparse/{n}", frac_ok=0.995)
+
+
+def test_two_python_threads_render_concurrently():
+    """splat_one calls the rasterizer from its training thread and from the Qt viewer thread at the
+    same time (R/app/gsplat_manager.py:185 vs :204); ctypes releases the GIL, so the library, the
+    per-thread pinned read-back ring and the per-thread CUDA streams must be re-entrant.  Two
+    threads render different scenes in a loop on their own streams; every result must equal the
+    single-threaded one bit for bit (integer outputs) / exactly (same kernels, same inputs)."""
+    import threading
+
+    dev = "cuda:0"
+    scenes = [synthetic.pinhole_scene(6000 + 500 * i, 160 + 16 * i, 120, seed=20 + i) for i in range(2)]
+    args = []
+    for sc in scenes:
+        P = [sc[k].to(dev) for k in ("means", "quats", "scales", "opacities", "sh")]
+        args.append((P, sc["viewmats"].to(dev), sc["Ks"].to(dev), sc["width"], sc["height"]))
+
+    def render(i, packed):
+        P, vm, Ks, W, H = args[i]
+        with torch.no_grad():
+            rc, ra, meta = S.rasterization(*P, vm, Ks, W, H, sh_degree=3, packed=packed)
+        return rc, ra, meta["flatten_ids"], meta["isect_offsets"]
+
+    expected = [[render(i, packed) for packed in (False, True)] for i in range(2)]
+    torch.cuda.synchronize()
+    errors = []
+
+    def worker(i):
+        try:
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                for it in range(12):
+                    packed = bool(it & 1)
+                    rc, ra, flat, offs = render(i, packed)
+                    stream.synchronize()
+                    e = expected[i][int(packed)]
+                    assert torch.equal(flat, e[2]) and torch.equal(offs, e[3]), f"thread {i} iter {it}: ids differ"
+                    assert torch.equal(rc, e[0]) and torch.equal(ra, e[1]), f"thread {i} iter {it}: image differs"
+        except Exception as ex:  # noqa: BLE001
+            errors.append(repr(ex))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors

@@ -27,14 +27,15 @@ if R is None:
     print(json.dumps({"unavailable": "oracle/_ref/gsplat_ref_csrc.so not built (python oracle/build_ref.py)"}))
     sys.exit(0)
 dev = torch.device("cuda:0")
-N, W, H = (int(a) for a in (sys.argv[1:4] + ["1000000", "1920", "1080"][len(sys.argv) - 1:]))
-sc = synthetic.pinhole_scene(N, W, H, seed=42)
+N, W, H = (int(a) for a in (sys.argv[1:4] + ["1000000", "1920", "1080"][len(sys.argv[1:4]):]))
+MODEL = sys.argv[4] if len(sys.argv) > 4 else "pinhole"
+sc = synthetic.spherical_scene(N, W, H, seed=42) if MODEL == "spherical" else synthetic.pinhole_scene(N, W, H, seed=42)
 P = {k: sc[k].to(dev) for k in ("means", "quats", "scales", "opacities", "sh", "viewmats", "Ks")}
 g = torch.Generator().manual_seed(1)
 vc = torch.randn(1, H, W, 3, generator=g).to(dev)
 va = torch.randn(1, H, W, 1, generator=g).to(dev)
 tw, th = math.ceil(W / 16), math.ceil(H / 16)
-PIN = R.CameraModelType.PINHOLE
+PIN = ref_cuda.camera_model(R, MODEL)
 stages = {}
 
 
@@ -91,7 +92,7 @@ def our_step():
     for p in A.values():
         p.grad = None
     rc, ra, _ = S.rasterization(A["means"], A["quats"], A["scales"], A["opacities"], A["sh"], P["viewmats"], P["Ks"], W,
-                                H, sh_degree=3, packed=False)
+                                H, sh_degree=3, packed=False, camera_model=MODEL)
     torch.autograd.backward([rc, ra], [vc, va])
     return rc
 
@@ -117,7 +118,7 @@ err = (rc_our - rc_ref).abs()
 names = ("means", "quats", "scales", "opacities", "sh")
 gdiff = {n: ((A[n].grad - gr).abs().max() / (gr.abs().max() + 1e-20)).item() for n, gr in zip(names, g_ref)}
 print(json.dumps({
-    "workload": f"{N} Gaussians, SH3, {W}x{H} pinhole, fwd+bwd, n_isects={n_isects}",
+    "workload": f"{N} Gaussians, SH3, {W}x{H} {MODEL}, fwd+bwd, n_isects={n_isects}",
     "reference_cuda_ms": round(t_ref, 4), "reference_cuda_Mpix_s": round(W * H / t_ref / 1e3, 1),
     "reference_cuda_stages_ms": ref_stages,
     "b200splat_ms": round(t_our, 4), "b200splat_Mpix_s": round(W * H / t_our / 1e3, 1),
