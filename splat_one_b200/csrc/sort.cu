@@ -65,11 +65,14 @@ gather_counts_kernel(uint64_t n_elems, const uint32_t *__restrict__ order, const
 // occupy one contiguous output range, so the lanes are mapped to OUTPUT positions (lane l
 // writes positions l, l + 32, ...: fully coalesced 128-byte stores) and each finds its
 // Gaussian by a 5-step binary search over the 32 in-warp start offsets (warp shuffles).
+// KeyT: uint16_t when cam|tile fits 16 bits (every BASELINE config) — the two digit passes then
+// move 6-byte instead of 8-byte pairs — else uint32_t.
+template <typename KeyT>
 __global__ void __launch_bounds__(kThreads)
 expand_kernel(int packed, uint32_t N, uint64_t n_elems, const uint32_t *__restrict__ order,
               const int64_t *__restrict__ cum_sorted, const int64_t *__restrict__ camera_ids,
               const float *__restrict__ means2d, const int32_t *__restrict__ radii, float ts, uint32_t tw, uint32_t th,
-              uint32_t tile_n_bits, uint32_t *__restrict__ tile_keys, uint32_t *__restrict__ vals) {
+              uint32_t tile_n_bits, KeyT *__restrict__ tile_keys, uint32_t *__restrict__ vals) {
     const unsigned lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp * 32 >= n_elems) return;  // warp-uniform
@@ -115,7 +118,7 @@ expand_kernel(int packed, uint32_t N, uint64_t n_elems, const uint32_t *__restri
             if (ry * g_w > k) --ry;
             if ((ry + 1) * g_w <= k) ++ry;
             const uint32_t rx = k - ry * g_w;
-            tile_keys[warp_base + p] = g_cam | (((g_xy0 >> 16) + ry) * tw + (g_xy0 & 0xffffu) + rx);
+            tile_keys[warp_base + p] = (KeyT)(g_cam | (((g_xy0 >> 16) + ry) * tw + (g_xy0 & 0xffffu) + rx));
             vals[warp_base + p] = g_idx;
         }
     }
@@ -123,8 +126,9 @@ expand_kernel(int packed, uint32_t N, uint64_t n_elems, const uint32_t *__restri
 
 // step 5: 64-bit ids from the sorted (cam|tile, flat index) pairs, and — fused, optional —
 // the per-tile offsets of a7 (same rule as offset_encode_kernel in isect.cu)
+template <typename KeyT>
 __global__ void __launch_bounds__(kThreads)
-assemble_kernel(uint64_t n_isects, const uint32_t *__restrict__ tile_keys, const uint32_t *__restrict__ vals,
+assemble_kernel(uint64_t n_isects, const KeyT *__restrict__ tile_keys, const uint32_t *__restrict__ vals,
                 const float *__restrict__ depths, int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids,
                 uint32_t total_tiles, uint32_t n_tiles, uint32_t tile_n_bits, int32_t *__restrict__ offsets) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -179,15 +183,19 @@ static DepthLayout depth_layout(uint64_t n_elems) {
     return L;
 }
 
+// sized for 32-bit keys (the 16-bit variant needs less)
 static TileLayout tile_layout(uint64_t n_isects) {
     TileLayout L;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes); return r; };
     L.tkeys_a = take(4 * n_isects); L.tkeys_b = take(4 * n_isects);
     L.tvals_a = take(4 * n_isects); L.tvals_b = take(4 * n_isects);
-    size_t b2 = 0;
+    size_t b2 = 0, b3 = 0;
     cub::DoubleBuffer<uint32_t> k(nullptr, nullptr), v(nullptr, nullptr);
     cub::DeviceRadixSort::SortPairs(nullptr, b2, k, v, (int64_t)(n_isects ? n_isects : 1), 0, 32, (cudaStream_t)0);
+    cub::DoubleBuffer<uint16_t> k16(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, b3, k16, v, (int64_t)(n_isects ? n_isects : 1), 0, 16, (cudaStream_t)0);
+    if (b3 > b2) b2 = b3;
     L.cub_bytes = b2 + 256;
     L.cub = take(L.cub_bytes);
     L.end = o;
@@ -268,6 +276,36 @@ extern "C" int b200splat_isect_depth_order(uint64_t n_elems, const float *depths
     return 0;
 }
 
+template <typename KeyT>
+static int tile_order_run(int packed, uint32_t C, uint32_t N, uint64_t n_elems, uint64_t n_isects,
+                          const int64_t *camera_ids, const float *means2d, const int32_t *radii, const float *depths,
+                          const uint32_t *order, const int64_t *cum, uint32_t tile_size, uint32_t tile_width,
+                          uint32_t tile_height, uint32_t tile_n_bits, uint32_t cam_n_bits, int64_t *isect_ids,
+                          int32_t *flatten_ids, int32_t *offsets, char *ws, const TileLayout &L, cudaStream_t st,
+                          const char *where) {
+    auto u32 = [&](size_t off) { return reinterpret_cast<uint32_t *>(ws + off); };
+    KeyT *ka = reinterpret_cast<KeyT *>(ws + L.tkeys_a), *kb = reinterpret_cast<KeyT *>(ws + L.tkeys_b);
+    const uint32_t n_tiles = tile_width * tile_height;
+    // 3. expand
+    expand_kernel<KeyT><<<div_up(n_elems, kThreads), kThreads, 0, st>>>(packed, N, n_elems, order, cum, camera_ids,
+                                                                        means2d, radii, (float)tile_size, tile_width,
+                                                                        tile_height, tile_n_bits, ka, u32(L.tvals_a));
+    B2S_CHECK_LAUNCH(where);
+    // 4. stable sort by cam|tile
+    cub::DoubleBuffer<KeyT> tk(ka, kb);
+    cub::DoubleBuffer<uint32_t> tv(u32(L.tvals_a), u32(L.tvals_b));
+    size_t cb = L.cub_bytes;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(ws + L.cub, cb, tk, tv, (int64_t)n_isects, 0,
+                                                    (int)(tile_n_bits + cam_n_bits), st);
+    if (e != cudaSuccess) return fail_cuda(where, e);
+    // 5. assemble
+    assemble_kernel<KeyT><<<div_up(n_isects, kThreads), kThreads, 0, st>>>(n_isects, tk.Current(), tv.Current(), depths,
+                                                                           isect_ids, flatten_ids, C * n_tiles, n_tiles,
+                                                                           tile_n_bits, offsets);
+    B2S_CHECK_LAUNCH(where);
+    return 0;
+}
+
 // ---- phase 2: expand, stable tile sort, assemble (+ offsets) ---------------------------------
 extern "C" size_t b200splat_isect_tile_order_workspace_bytes(uint64_t n_isects) {
     return tile_layout(n_isects).end;
@@ -297,26 +335,16 @@ extern "C" int b200splat_isect_tile_order(int packed, uint32_t C, uint32_t N, ui
                 "workspace too small (see b200splat_isect_tile_order_workspace_bytes)");
     const char *dws = reinterpret_cast<const char *>(depth_workspace);
     char *ws = reinterpret_cast<char *>(workspace);
-    auto u32 = [&](size_t off) { return reinterpret_cast<uint32_t *>(ws + off); };
     const uint32_t *order = reinterpret_cast<const uint32_t *>(dws + (depth_selector ? D.gvals_b : D.gvals_a));
     const int64_t *cum = reinterpret_cast<const int64_t *>(dws + D.cum);
-    // 3. expand
-    expand_kernel<<<div_up(n_elems, kThreads), kThreads, 0, st>>>(packed, N, n_elems, order, cum, camera_ids, means2d,
-                                                                  radii, (float)tile_size, tile_width, tile_height,
-                                                                  tile_n_bits, u32(L.tkeys_a), u32(L.tvals_a));
-    B2S_CHECK_LAUNCH(where);
-    // 4. stable sort by cam|tile
-    cub::DoubleBuffer<uint32_t> tk(u32(L.tkeys_a), u32(L.tkeys_b)), tv(u32(L.tvals_a), u32(L.tvals_b));
-    size_t cb = L.cub_bytes;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(ws + L.cub, cb, tk, tv, (int64_t)n_isects, 0,
-                                                    (int)(tile_n_bits + cam_n_bits), st);
-    if (e != cudaSuccess) return fail_cuda(where, e);
-    // 5. assemble
-    assemble_kernel<<<div_up(n_isects, kThreads), kThreads, 0, st>>>(n_isects, tk.Current(), tv.Current(), depths,
-                                                                     isect_ids, flatten_ids, C * n_tiles, n_tiles,
-                                                                     tile_n_bits, offsets);
-    B2S_CHECK_LAUNCH(where);
-    return 0;
+    const int rc = (tile_n_bits + cam_n_bits <= 16 && tuning_variant() != 8)
+                       ? tile_order_run<uint16_t>(packed, C, N, n_elems, n_isects, camera_ids, means2d, radii, depths, order,
+                                                  cum, tile_size, tile_width, tile_height, tile_n_bits, cam_n_bits,
+                                                  isect_ids, flatten_ids, offsets, ws, L, st, where)
+                       : tile_order_run<uint32_t>(packed, C, N, n_elems, n_isects, camera_ids, means2d, radii, depths, order,
+                                                  cum, tile_size, tile_width, tile_height, tile_n_bits, cam_n_bits,
+                                                  isect_ids, flatten_ids, offsets, ws, L, st, where);
+    return rc;
 }
 
 // both phases in one call (workspace = phase-1 layout followed by phase-2 layout)
