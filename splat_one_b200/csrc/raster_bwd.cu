@@ -568,7 +568,7 @@ raster_bwd_quad_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t chann
                 }
             }
 #undef B2S_BQ
-            if (!__any_sync(0xffffffffu, hit)) continue;
+            if (SINK != 2 && !__any_sync(0xffffffffu, hit)) continue;  // SINK 2: commit unconditionally
             // negated moments -> gradients (conic entries in the record are scaled by log2 e)
             float v[NV];
 #pragma unroll
@@ -613,7 +613,7 @@ static void launch_bwd_quad(uint32_t C, uint64_t n_isects, uint32_t channels, co
         case 2: B2S_BWDQ(2, 10, 1, 1, 1); break;   // two warps per tile (upper / lower half), 96 registers
         case 6: B2S_BWDQ(2, 12, 1, 1, 1); break;   // same, 80 registers
         case 3: B2S_BWDQ(4, 16, 1, 1, 0); break;   // shared-memory commit, register prefetch
-        case 4: B2S_BWDQ(4, 16, 0, 0, 0); break;
+        case 4: B2S_BWDQ(4, 16, 1, 2, 1); break;   // as default, without the per-pair hit vote
         case 5: B2S_BWDQ(4, 18, 1, 1, 1); break;   // same, 112 registers
         default: B2S_BWDQ(4, 16, 1, 1, 1); break;  // shared-memory commit + cp.async prefetch: 0.552 ms vs 0.613 (variant 1)
     }

@@ -59,6 +59,7 @@ class _Profiler:
 
     def __init__(self):
         self.enabled = False
+        self.only = None  # None: time every native call; else the set of names to bracket with events
         self.reset()
 
     def reset(self):
@@ -85,12 +86,15 @@ def native(name: str, lib, device, *args):
     with torch.cuda.device(device):
         st = _stream(device)
         if profiler.enabled:
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            rc = fn(*args, st)
-            b.record()
-            profiler.events.setdefault(name, []).append((a, b))
             profiler.calls[name] = profiler.calls.get(name, 0) + 1
+            if profiler.only is None or name in profiler.only:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                rc = fn(*args, st)
+                b.record()
+                profiler.events.setdefault(name, []).append((a, b))
+            else:
+                rc = fn(*args, st)
         else:
             rc = fn(*args, st)
     check(rc, lib)
