@@ -355,33 +355,45 @@ def run_gpu(args):
     out_a_host = torch.empty(C_local, HEIGHT, WIDTH, 1).pin_memory()
     gnorm_host = torch.empty(1).pin_memory()
 
-    copy_stream = torch.cuda.Stream(device=dev)
+    h2d_stream = torch.cuda.Stream(device=dev)
+    d2h_stream = torch.cuda.Stream(device=dev)
+    # double-buffered device cotangents: the copy for step k+1 is issued during step k (a data
+    # loader's prefetch), H2D and D2H run on their own streams (PCIe is full duplex)
+    cot = [(torch.empty_like(vc), torch.empty_like(va)) for _ in range(2)]
+    cot_ready = [torch.cuda.Event() for _ in range(2)]
+    cot_free = [torch.cuda.Event() for _ in range(2)]
+    state = {"k": 0}
+
+    def prefetch(i):
+        with torch.cuda.stream(h2d_stream):
+            h2d_stream.wait_event(cot_free[i])  # the backward that last read this buffer is done
+            cot[i][0].copy_(vc_host, non_blocking=True)
+            cot[i][1].copy_(va_host, non_blocking=True)
+            cot_ready[i].record(h2d_stream)
 
     def e2e_step():
-        """camera H2D -> forward -> (image D2H || cotangent H2D) -> backward -> grad-norm D2H.
-        The big copies run on a side stream so they overlap the kernels of the same step."""
+        """camera H2D -> forward -> (image D2H || next step's cotangent H2D) -> backward -> grad-norm D2H.
+        Every step copies its camera and cotangent images host->device and its rendered image +
+        alpha + gradient norm device->host; the big copies run on side streams and overlap kernels."""
         main = torch.cuda.current_stream(dev)
+        i = state["k"] & 1
+        state["k"] += 1
         vm_d = vm_host.to(dev, non_blocking=True)
         K_d = K_host.to(dev, non_blocking=True)
-        with torch.cuda.stream(copy_stream):  # cotangents are only needed by the backward
-            vc_d = vc_host.to(dev, non_blocking=True)
-            va_d = va_host.to(dev, non_blocking=True)
-            cot_ready = torch.cuda.Event()
-            cot_ready.record(copy_stream)
         for p in params:
             p.grad = None
         rc_, ra_, _ = S.rasterization(*params, vm_d, K_d, WIDTH, HEIGHT, sh_degree=SH_DEGREE, packed=False)
         fwd_done = torch.cuda.Event()
         fwd_done.record(main)
-        with torch.cuda.stream(copy_stream):  # the rendered image leaves while the backward runs
-            copy_stream.wait_event(fwd_done)
+        with torch.cuda.stream(d2h_stream):  # the rendered image leaves while the backward runs
+            d2h_stream.wait_event(fwd_done)
             out_c_host.copy_(rc_.detach(), non_blocking=True)
             out_a_host.copy_(ra_.detach(), non_blocking=True)
-            rc_.record_stream(copy_stream)
-            ra_.record_stream(copy_stream)
-        main.wait_event(cot_ready)
-        vc_d.record_stream(main)
-        va_d.record_stream(main)
+            rc_.record_stream(d2h_stream)
+            ra_.record_stream(d2h_stream)
+        prefetch(i ^ 1)  # cotangents of the NEXT step
+        main.wait_event(cot_ready[i])
+        vc_d, va_d = cot[i]
         if arena is not None:
             with arena.sink(), camera_parallel() as cp:
                 torch.autograd.backward([rc_, ra_], [vc_d, va_d])
@@ -389,15 +401,25 @@ def run_gpu(args):
             arena.all_reduce(skip_ptrs=cp.reduced_ptrs)
         else:
             torch.autograd.backward([rc_, ra_], [vc_d, va_d])
+        cot_free[i].record(main)
         gnorm_host.copy_(params[0].grad.norm().reshape(1), non_blocking=True)
-        main.wait_stream(copy_stream)
 
+    def e2e_drain():
+        main = torch.cuda.current_stream(dev)
+        main.wait_stream(h2d_stream)
+        main.wait_stream(d2h_stream)
+
+    cot_free[0].record(torch.cuda.current_stream(dev))
+    cot_free[1].record(torch.cuda.current_stream(dev))
+    prefetch(0)
     for _ in range(2):
         e2e_step()
+    e2e_drain()
     barrier()
     e0.record()
     for _ in range(args.steps):
         e2e_step()
+    e2e_drain()
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -477,8 +499,9 @@ def run_gpu(args):
             "clocks": clocks,
             "e2e": {"value": world * C_local * HEIGHT * WIDTH / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s",
                     "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "what": "camera + cotangent images H2D from pinned memory, rasterization()+backward, "
-                            "rendered image + alpha + grad norm D2H; Gaussians stay resident (model state)"},
+                    "what": "every step: camera + cotangent images H2D from pinned memory (cotangents prefetched one "
+                            "step ahead on an H2D stream), rasterization()+backward, rendered image + alpha + grad norm "
+                            "D2H (D2H stream, overlapping the backward); Gaussians stay resident (model state)"},
             "gpu_launches": launches,
             "roofline": roof,
             "raster_stages": raster,
