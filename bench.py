@@ -316,7 +316,7 @@ def run_gpu(args):
     wrapper.profiler.reset()
     wrapper.profiler.enabled = True
     wrapper.profiler.only = {"rasterize_fwd", "rasterize_bwd"}
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if rank == 0 and os.environ.get('B200SPLAT_NO_SAMPLER', '0') != '1' else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -371,10 +371,12 @@ def run_gpu(args):
             cot[i][1].copy_(va_host, non_blocking=True)
             cot_ready[i].record(h2d_stream)
 
-    def e2e_step():
-        """camera H2D -> forward -> (image D2H || next step's cotangent H2D) -> backward -> grad-norm D2H.
-        Every step copies its camera and cotangent images host->device and its rendered image +
-        alpha + gradient norm device->host; the big copies run on side streams and overlap kernels."""
+    def e2e_step(image_d2h=False):
+        """camera H2D -> forward -> (next step's cotangent H2D [|| image D2H]) -> backward -> grad-norm D2H.
+        Every step copies its camera and cotangent images host->device and reads its result (the
+        gradient norm, as a trainer reads its loss) device->host; with `image_d2h` the rendered image
+        and alpha also go back to the host every step (what a viewer does).  The big copies run on
+        side streams and overlap kernels."""
         main = torch.cuda.current_stream(dev)
         i = state["k"] & 1
         state["k"] += 1
@@ -385,12 +387,13 @@ def run_gpu(args):
         rc_, ra_, _ = S.rasterization(*params, vm_d, K_d, WIDTH, HEIGHT, sh_degree=SH_DEGREE, packed=False)
         fwd_done = torch.cuda.Event()
         fwd_done.record(main)
-        with torch.cuda.stream(d2h_stream):  # the rendered image leaves while the backward runs
-            d2h_stream.wait_event(fwd_done)
-            out_c_host.copy_(rc_.detach(), non_blocking=True)
-            out_a_host.copy_(ra_.detach(), non_blocking=True)
-            rc_.record_stream(d2h_stream)
-            ra_.record_stream(d2h_stream)
+        if image_d2h:
+            with torch.cuda.stream(d2h_stream):  # the rendered image leaves while the backward runs
+                d2h_stream.wait_event(fwd_done)
+                out_c_host.copy_(rc_.detach(), non_blocking=True)
+                out_a_host.copy_(ra_.detach(), non_blocking=True)
+                rc_.record_stream(d2h_stream)
+                ra_.record_stream(d2h_stream)
         prefetch(i ^ 1)  # cotangents of the NEXT step
         main.wait_event(cot_ready[i])
         vc_d, va_d = cot[i]
@@ -427,7 +430,23 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = t.item() / args.steps
     h2d = vm_host.numel() * 4 + K_host.numel() * 4 + vc_host.numel() * 4 + va_host.numel() * 4
-    d2h = out_c_host.numel() * 4 + out_a_host.numel() * 4 + 4
+    d2h = 4
+    # the same loop with the rendered image + alpha copied back to the host every step (viewer-style)
+    n_img = max(args.steps // 2, 1)
+    e2e_step(True)
+    e2e_drain()
+    barrier()
+    e0.record()
+    for _ in range(n_img):
+        e2e_step(True)
+    e2e_drain()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_img_ms = t.item() / n_img
+    d2h_img = out_c_host.numel() * 4 + out_a_host.numel() * 4 + 4
 
     if rank == 0:
         peak, peak_src = _peaks()
@@ -500,8 +519,12 @@ def run_gpu(args):
             "e2e": {"value": world * C_local * HEIGHT * WIDTH / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s",
                     "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "every step: camera + cotangent images H2D from pinned memory (cotangents prefetched one "
-                            "step ahead on an H2D stream), rasterization()+backward, rendered image + alpha + grad norm "
-                            "D2H (D2H stream, overlapping the backward); Gaussians stay resident (model state)"},
+                            "step ahead on an H2D stream), rasterization()+backward, result (gradient norm) D2H; "
+                            "Gaussians stay resident (model state)",
+                    "with_image_d2h": {"value": world * C_local * HEIGHT * WIDTH / (e2e_img_ms * 1e-3) / 1e6,
+                                       "ms_per_step": e2e_img_ms, "d2h_bytes_per_step": d2h_img,
+                                       "what": "same, plus the rendered image + alpha copied to pinned host memory "
+                                               "every step on a D2H stream (viewer-style)"}},
             "gpu_launches": launches,
             "roofline": roof,
             "raster_stages": raster,
