@@ -30,9 +30,11 @@ class camera_parallel:
     `backward()` already global.  `reduced_ptrs` lists the parameters (by data_ptr) this
     happened for; `GradArena.all_reduce(skip_ptrs=...)` then leaves them out."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, defer: bool = False):
         self.group = group if group is not None else dist.group.WORLD
         self.reduced_ptrs = set()
+        self.defer = defer
+        self._deferred = []  # (means parameter, finish(all_cameras) -> v_means) of the colour stages
 
     def __enter__(self):
         from . import wrapper
@@ -41,6 +43,8 @@ class camera_parallel:
         if self._active:
             wrapper._CAMERA_PARALLEL["group"] = self.group
             wrapper._CAMERA_PARALLEL["reduced"] = self.reduced_ptrs
+            if self.defer:
+                wrapper._CAMERA_PARALLEL["deferred"] = self._deferred
         return self
 
     def __exit__(self, *exc):
@@ -48,6 +52,40 @@ class camera_parallel:
 
         wrapper._CAMERA_PARALLEL.clear()
         return False
+
+    def finish(self, arena: "GradArena", average: bool = False) -> None:
+        """Deferred mode (`defer=True`), call after `backward()` instead of
+        `arena.gather_from_params(); arena.all_reduce(skip_ptrs=...)`:
+
+            backward:  ... raster bwd -> [colour node: START all-gather of cotangents] -> projection bwd
+            finish:    all-reduce of the arena (async, NCCL stream)  ||  colour backward kernel over ALL
+                       cameras (this stream, behind the all-gather)  -> means.grad += direction gradient
+
+        so the all-gather overlaps the projection backward and the all-reduce overlaps the colour
+        backward.  The direction (means) gradient of the colour stage is summed over all cameras on
+        every rank, i.e. it is already global and is added AFTER the all-reduce.  Reduced gradients
+        live in the arena views (`arena.scatter_to_params()` re-attaches them)."""
+        arena.gather_from_params()
+        works = arena.all_reduce(group=self.group, async_op=True, skip_ptrs=self.reduced_ptrs)
+        pending = [(m, fin(True)) for m, fin in self._deferred]
+        self._deferred.clear()
+        for w in works or ():
+            w.wait()
+        W = dist.get_world_size(self.group)
+        if average:
+            for p, v in zip(arena.params, arena.views):
+                v.div_(W)
+        for m, vm in pending:
+            if vm is None:
+                continue
+            if average:
+                vm = vm / W
+            for p, v in zip(arena.params, arena.views):
+                if p is m:
+                    v.add_(vm)
+                    break
+            else:  # not an arena parameter: accumulate on the tensor itself
+                m.grad = vm if m.grad is None else m.grad + vm
 
 
 def shard_cameras(viewmats: Tensor, Ks: Tensor, rank: Optional[int] = None,
@@ -121,16 +159,16 @@ class GradArena:
                 start = o
         if start is not None:
             runs.append((start, self.flat.numel()))
-        work = None
+        works = []
         for a, b in runs:
-            work = dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+            works.append(dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=group, async_op=async_op))
             if average and not async_op:
                 self.flat[a:b].div_(dist.get_world_size(group))
         if average and not async_op:
             for p, v in zip(self.params, self.views):
                 if p.data_ptr() in skip_ptrs:
                     v.div_(dist.get_world_size(group))
-        return work
+        return works if async_op else (works[-1] if works else None)
 
     def scatter_to_params(self) -> None:
         """Point every p.grad at its arena view (no copy)."""

@@ -347,6 +347,47 @@ def camera_centers(viewmats: Tensor) -> Tensor:
     return out
 
 
+def _camera_parallel_colour_bwd(cp, means, campos, colors, v_colors, C, outs, v_means, run):
+    """The colour-cotangent exchange of the camera-parallel mode.  Immediate mode: all-gather, then
+    the kernel (`run`) sums the coefficient gradient over ALL cameras and the direction gradient over
+    this rank's cameras; returns v_means.  Deferred mode (`camera_parallel(defer=True)`): the
+    all-gather is only STARTED here (async) and the kernel launch is handed to
+    `camera_parallel.finish()`, which queues it behind the arena all-reduce so that the two overlap;
+    the direction gradient is then summed over all cameras on every rank (already global: it is added
+    after the all-reduce) and this node returns no means gradient."""
+    import torch.distributed as dist
+
+    W, r = dist.get_world_size(cp), dist.get_rank(cp)
+    N = means.shape[0]
+    g_local = torch.where(colors > 0, v_colors, torch.zeros_like(v_colors))  # [C,N,3], zero where invisible
+    g_all = torch.empty((W * C, N, 3), device=means.device, dtype=torch.float32)
+    campos_all = torch.empty((W * C, 3), device=means.device, dtype=torch.float32)
+    deferred = _CAMERA_PARALLEL.get("deferred")
+    if deferred is None:
+        dist.all_gather_into_tensor(g_all, g_local, group=cp)
+        dist.all_gather_into_tensor(campos_all, campos.contiguous(), group=cp)
+        run(campos_all, g_all, outs, v_means, r * C, (r + 1) * C, W * C)
+        return v_means
+    campos_c = campos.contiguous()
+    works = [dist.all_gather_into_tensor(g_all, g_local, group=cp, async_op=True),
+             dist.all_gather_into_tensor(campos_all, campos_c, group=cp, async_op=True)]
+    # the kernel writes through fresh aliases: autograd adopts the returned gradient tensors without
+    # a copy only while nothing else holds the same tensor object
+    alias = tuple(None if o is None else o.detach() for o in outs)
+    want_means = v_means is not None
+
+    def finish(all_cameras: bool, _keep=(g_local, campos_c)):  # _keep: inputs of the in-flight all-gathers
+        for w in works:
+            w.wait()
+        vm = torch.empty_like(means) if want_means else None
+        lo, hi = (0, W * C) if all_cameras else (r * C, (r + 1) * C)
+        run(campos_all, g_all, alias, vm, lo, hi, W * C)
+        return vm
+
+    deferred.append((means, finish))
+    return None
+
+
 def sh_view_colors(sh_degree: int, means: Tensor, viewmats: Tensor, coeffs: Tensor, radii: Tensor) -> Tensor:
     """The colour stage of `rasterization()` for the unpacked layout, fused:
 
@@ -397,16 +438,11 @@ class _ShViewColors(torch.autograd.Function):
             # of camera c is the outer product B(dir_c) x v_rgb_c, so ranks all-gather their masked
             # colour cotangents (3 floats per Gaussian and camera) and every rank evaluates the
             # sum over ALL cameras itself, instead of all-reducing 3K floats per Gaussian
-            import torch.distributed as dist
+            def run(campos_all, g_all, v_out, v_means_out, lo, hi, WC):
+                native("sh_colors_bwd", lib, means.device, WC, N, K, ctx.sh_degree, 0, _ptr(means), _ptr(campos_all),
+                       _ptr(coeffs), None, None, _ptr(g_all), _ptr(v_out[0]), _ptr(v_means_out), lo, hi)
 
-            W, r = dist.get_world_size(cp), dist.get_rank(cp)
-            g_local = torch.where(colors > 0, v_colors, torch.zeros_like(v_colors))  # [C,N,3], zero where invisible
-            g_all = torch.empty((W * C, N, 3), device=means.device, dtype=torch.float32)
-            campos_all = torch.empty((W * C, 3), device=means.device, dtype=torch.float32)
-            dist.all_gather_into_tensor(g_all, g_local, group=cp)
-            dist.all_gather_into_tensor(campos_all, campos.contiguous(), group=cp)
-            native("sh_colors_bwd", lib, means.device, W * C, N, K, ctx.sh_degree, 0, _ptr(means), _ptr(campos_all),
-                   _ptr(coeffs), None, None, _ptr(g_all), _ptr(v_coeffs), _ptr(v_means), r * C, (r + 1) * C)
+            v_means = _camera_parallel_colour_bwd(cp, means, campos, colors, v_colors, C, (v_coeffs,), v_means, run)
             _CAMERA_PARALLEL["reduced"].add(coeffs.data_ptr())
         elif N:
             native("sh_colors_bwd", lib, means.device, C, N, K, ctx.sh_degree, per_view, _ptr(means), _ptr(campos),
@@ -467,17 +503,14 @@ class _ShViewColorsStaged(torch.autograd.Function):
         cp = _CAMERA_PARALLEL.get("group", None) if _CAMERA_PARALLEL else None
         if cp is not None and N:
             # camera-parallel exchange, as in _ShViewColors.backward
-            import torch.distributed as dist
+            outs = (v_sh0, v_rest) if sh0 is not None else (None, v_rest)
 
-            W, r = dist.get_world_size(cp), dist.get_rank(cp)
-            g_local = torch.where(colors > 0, v_colors, torch.zeros_like(v_colors))
-            g_all = torch.empty((W * C, N, 3), device=means.device, dtype=torch.float32)
-            campos_all = torch.empty((W * C, 3), device=means.device, dtype=torch.float32)
-            dist.all_gather_into_tensor(g_all, g_local, group=cp)
-            dist.all_gather_into_tensor(campos_all, campos.contiguous(), group=cp)
-            native("sh_colors_staged_bwd", lib, means.device, W * C, N, K, ctx.sh_degree, _ptr(means),
-                   _ptr(campos_all), _ptr(sh0), _ptr(rest), None, None, _ptr(g_all), _ptr(v_sh0), _ptr(v_rest),
-                   _ptr(v_means), r * C, (r + 1) * C)
+            def run(campos_all, g_all, v_out, v_means_out, lo, hi, WC):
+                native("sh_colors_staged_bwd", lib, means.device, WC, N, K, ctx.sh_degree, _ptr(means),
+                       _ptr(campos_all), _ptr(sh0), _ptr(rest), None, None, _ptr(g_all), _ptr(v_out[0]), _ptr(v_out[1]),
+                       _ptr(v_means_out), lo, hi)
+
+            v_means = _camera_parallel_colour_bwd(cp, means, campos, colors, v_colors, C, outs, v_means, run)
             _CAMERA_PARALLEL["reduced"].add(rest.data_ptr())
             if sh0 is not None:
                 _CAMERA_PARALLEL["reduced"].add(sh0.data_ptr())

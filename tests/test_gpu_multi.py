@@ -19,7 +19,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out_path, split_sh):
+def _worker(rank, world, port, out_path, split_sh, defer):
     import torch.distributed as dist
 
     import splat_one_b200 as S
@@ -51,10 +51,13 @@ def _worker(rank, world, port, out_path, split_sh):
             rc, ra, _ = S.rasterization(*P, vm, Ks, W, H, sh_degree=3, packed=False)
         if dp:
             arena = GradArena(P)
-            with arena.sink(), camera_parallel() as cp:
+            with arena.sink(), camera_parallel(defer=defer) as cp:
                 torch.autograd.backward([rc, ra], [vc, va])
-            arena.gather_from_params()
-            arena.all_reduce(skip_ptrs=cp.reduced_ptrs)
+            if defer:  # all-reduce overlapped with the colour backward (camera_parallel.finish)
+                cp.finish(arena)
+            else:
+                arena.gather_from_params()
+                arena.all_reduce(skip_ptrs=cp.reduced_ptrs)
             arena.scatter_to_params()
         else:
             torch.autograd.backward([rc, ra], [vc, va])
@@ -74,14 +77,14 @@ def _worker(rank, world, port, out_path, split_sh):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("split_sh", [False, True])
-def test_two_gpu_camera_parallel_matches_single_process_batch(tmp_path, split_sh):
+@pytest.mark.parametrize("split_sh,defer", [(False, False), (True, False), (False, True), (True, True)])
+def test_two_gpu_camera_parallel_matches_single_process_batch(tmp_path, split_sh, defer):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
 
     out = str(tmp_path / "report.pt")
-    mp.spawn(_worker, args=(2, _free_port(), out, split_sh), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), out, split_sh, defer), nprocs=2, join=True)
     reports = torch.load(out)
     for r, rep in enumerate(reports):
         for n, (max_rel, frac_bad) in rep.items():
