@@ -112,7 +112,7 @@ __device__ __forceinline__ int run_start(int i) { return i < 2 ? 6 * i : 5 * i +
 template <bool WITH_C>
 __device__ __forceinline__ void stage_tiles(const float *__restrict__ A, const float *__restrict__ B,
                                             const float *__restrict__ Cc, uint32_t H, uint32_t W, int x0, int y0,
-                                            float2 *s_ab, float *s_c) {
+                                            float2 *s_ab, float *s_c, int halo_rows = kHalo) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int off[4];   // element offset inside an image row, or -1 when the column is outside the image
 #pragma unroll
@@ -120,7 +120,7 @@ __device__ __forceinline__ void stage_tiles(const float *__restrict__ A, const f
         const int f = lane + 32 * i, px3 = f / 3, x = x0 - kHalf + px3;
         off[i] = (f < kRowF && x >= 0 && x < (int)W) ? x * 3 + (f - 3 * px3) : -1;
     }
-    for (int r = warp; r < kHalo; r += 8) {
+    for (int r = warp; r < halo_rows; r += 8) {
         const int y = y0 - kHalf + r;
         const bool row_ok = y >= 0 && y < (int)H;
         const size_t base = (size_t)(row_ok ? y : 0) * W * 3;
@@ -140,30 +140,34 @@ __device__ __forceinline__ void stage_tiles(const float *__restrict__ A, const f
     }
 }
 
-__global__ void __launch_bounds__(256, 3)
+template <int TY>
+__global__ void __launch_bounds__(256, TY == 16 ? 4 : 3)
 l1_ssim_fwd_kernel(uint32_t H, uint32_t W, const float *__restrict__ img, const float *__restrict__ tgt,
                    const Window win, float *__restrict__ d_mu, float *__restrict__ d_xx, float *__restrict__ d_xy,
                    float *__restrict__ partials) {
+    constexpr int HY = TY + 2 * kHalf;        // apron rows
+    constexpr int CS = HY + 1;                // transposed column stride (odd)
+    constexpr int RPT = TY / 8;               // consecutive output rows per thread, vertical pass
     extern __shared__ float2 smem2[];
-    float2 *s_ab = smem2;                        // [kHalo][kRowS]   {img, tgt}
-    float2 *s_m = s_ab + kHalo * kRowS;          // [kTile][kColS]   {sum g a, sum g b}
-    float2 *s_q = s_m + kTile * kColS;           // [kTile][kColS]   {sum g a², sum g b²}
-    float *s_p = reinterpret_cast<float *>(s_q + kTile * kColS);  // [kTile][kColS]  sum g a b
+    float2 *s_ab = smem2;                        // [HY][kRowS]   {img, tgt}
+    float2 *s_m = s_ab + HY * kRowS;          // [kTile][CS]   {sum g a, sum g b}
+    float2 *s_q = s_m + kTile * CS;           // [kTile][CS]   {sum g a², sum g b²}
+    float *s_p = reinterpret_cast<float *>(s_q + kTile * CS);  // [kTile][CS]  sum g a b
     const uint32_t cam = blockIdx.z;
-    const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
+    const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * TY;
     const size_t img_off = (size_t)cam * H * W * 3;
-    stage_tiles<false>(img + img_off, tgt + img_off, nullptr, H, W, x0, y0, s_ab, nullptr);
+    stage_tiles<false>(img + img_off, tgt + img_off, nullptr, H, W, x0, y0, s_ab, nullptr, HY);
     __syncthreads();
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int px = x0 + tx;
     float l1 = 0.f, ss = 0.f;
-    float o_mu[kRowsPerThread][3], o_xx[kRowsPerThread][3], o_xy[kRowsPerThread][3];
+    float o_mu[RPT][3], o_xx[RPT][3], o_xy[RPT][3];
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
         // horizontal pass: thread = (apron row r, run of kRun output columns); packed fp32x2
         // accumulation of the {a, b} and {a², b²} pairs (FFMA2), scalar a·b
-        if (threadIdx.x < kHalo * kRunsPerRow) {
-            const int r = threadIdx.x % kHalo, xr = run_start(threadIdx.x / kHalo);
+        if (threadIdx.x < HY * kRunsPerRow) {
+            const int r = threadIdx.x % HY, xr = run_start(threadIdx.x / HY);
             float2 hm[kRun], hq[kRun];
             float hp[kRun];
 #pragma unroll
@@ -186,25 +190,25 @@ l1_ssim_fwd_kernel(uint32_t H, uint32_t W, const float *__restrict__ img, const 
             }
 #pragma unroll
             for (int j = 0; j < kRun; ++j) {
-                s_m[(xr + j) * kColS + r] = hm[j];
-                s_q[(xr + j) * kColS + r] = hq[j];
-                s_p[(xr + j) * kColS + r] = hp[j];
+                s_m[(xr + j) * CS + r] = hm[j];
+                s_q[(xr + j) * CS + r] = hq[j];
+                s_p[(xr + j) * CS + r] = hp[j];
             }
         }
         __syncthreads();
-        // vertical pass: thread = (column tx, kRowsPerThread consecutive rows)
+        // vertical pass: thread = (column tx, RPT consecutive rows)
         {
-            const int ly0 = ty * kRowsPerThread;
-            float2 vm[kRowsPerThread], vq[kRowsPerThread];
-            float vp[kRowsPerThread];
+            const int ly0 = ty * RPT;
+            float2 vm[RPT], vq[RPT];
+            float vp[RPT];
 #pragma unroll
-            for (int j = 0; j < kRowsPerThread; ++j) { vm[j] = f2(0.f, 0.f); vq[j] = f2(0.f, 0.f); vp[j] = 0.f; }
+            for (int j = 0; j < RPT; ++j) { vm[j] = f2(0.f, 0.f); vq[j] = f2(0.f, 0.f); vp[j] = 0.f; }
 #pragma unroll
-            for (int e = 0; e < kRowsPerThread + kWin - 1; ++e) {
-                const float2 m = s_m[tx * kColS + ly0 + e], q = s_q[tx * kColS + ly0 + e];
-                const float p = s_p[tx * kColS + ly0 + e];
+            for (int e = 0; e < RPT + kWin - 1; ++e) {
+                const float2 m = s_m[tx * CS + ly0 + e], q = s_q[tx * CS + ly0 + e];
+                const float p = s_p[tx * CS + ly0 + e];
 #pragma unroll
-                for (int j = 0; j < kRowsPerThread; ++j) {
+                for (int j = 0; j < RPT; ++j) {
                     const int k = e - j;
                     if (k >= 0 && k < kWin) {
                         const float g = win.g[k];
@@ -215,7 +219,7 @@ l1_ssim_fwd_kernel(uint32_t H, uint32_t W, const float *__restrict__ img, const 
                 }
             }
 #pragma unroll
-            for (int j = 0; j < kRowsPerThread; ++j) {
+            for (int j = 0; j < RPT; ++j) {
                 const int ly = ly0 + j, py = y0 + ly;
                 const float mu1 = vm[j].x, mu2 = vm[j].y, exx = vq[j].x, eyy = vq[j].y, exy = vp[j];
                 const bool inside = px < (int)W && py < (int)H;
@@ -245,8 +249,8 @@ l1_ssim_fwd_kernel(uint32_t H, uint32_t W, const float *__restrict__ img, const 
     }
     if (d_mu != nullptr) {
 #pragma unroll
-        for (int j = 0; j < kRowsPerThread; ++j) {
-            const int py = y0 + ty * kRowsPerThread + j;
+        for (int j = 0; j < RPT; ++j) {
+            const int py = y0 + ty * RPT + j;
             if (px < (int)W && py < (int)H) {
                 const size_t o = img_off + ((size_t)py * W + px) * 3;
 #pragma unroll
@@ -294,30 +298,35 @@ l1_ssim_finalize_kernel(uint32_t n_blocks, const float *__restrict__ partials, d
 
 // v_img = v_loss * [ (1-lambda)/n_l1 * sign(img - tgt)
 //                    - lambda/n_ssim * (G*d_mu + 2 img (G*d_xx) + tgt (G*d_xy)) ]      (G* = zero-padded window)
-__global__ void __launch_bounds__(256, 3)
+// TY: output rows per block (32, or 16: a 26-row apron = 50 KB of shared memory, 4 blocks/SM instead of 2)
+template <int TY>
+__global__ void __launch_bounds__(256, TY == 16 ? 4 : 3)
 l1_ssim_bwd_kernel(uint32_t H, uint32_t W, const float *__restrict__ img, const float *__restrict__ tgt,
                    const Window win, const float *__restrict__ d_mu, const float *__restrict__ d_xx,
                    const float *__restrict__ d_xy, const float *__restrict__ v_loss, float s_l1, float s_ssim,
                    float *__restrict__ v_img) {
+    constexpr int HY = TY + 2 * kHalf;        // apron rows
+    constexpr int CS = HY + 1;                // transposed column stride (odd)
+    constexpr int RPT = TY / 8;               // consecutive output rows per thread, vertical pass
     extern __shared__ float2 smem2[];
-    float2 *s_ab = smem2;                        // [kHalo][kRowS]  {d_mu, d_xx}
-    float2 *s_m = s_ab + kHalo * kRowS;          // [kTile][kColS]  horizontal sums of the pair
-    float *s_c = reinterpret_cast<float *>(s_m + kTile * kColS);   // [kHalo][kRowS]  d_xy
-    float *s_p = s_c + kHalo * kRowS;            // [kTile][kColS]
+    float2 *s_ab = smem2;                        // [HY][kRowS]  {d_mu, d_xx}
+    float2 *s_m = s_ab + HY * kRowS;          // [kTile][CS]  horizontal sums of the pair
+    float *s_c = reinterpret_cast<float *>(s_m + kTile * CS);   // [HY][kRowS]  d_xy
+    float *s_p = s_c + HY * kRowS;            // [kTile][CS]
     const uint32_t cam = blockIdx.z;
-    const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
+    const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * TY;
     const size_t img_off = (size_t)cam * H * W * 3;
-    stage_tiles<true>(d_mu + img_off, d_xx + img_off, d_xy + img_off, H, W, x0, y0, s_ab, s_c);
+    stage_tiles<true>(d_mu + img_off, d_xx + img_off, d_xy + img_off, H, W, x0, y0, s_ab, s_c, HY);
     __syncthreads();
     const float gl = v_loss != nullptr ? __ldg(v_loss) : 1.f;
     const float k_l1 = gl * s_l1, k_ss = gl * s_ssim;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int px = x0 + tx;
-    float out[kRowsPerThread][3];
+    float out[RPT][3];
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
-        if (threadIdx.x < kHalo * kRunsPerRow) {
-            const int r = threadIdx.x % kHalo, xr = run_start(threadIdx.x / kHalo);
+        if (threadIdx.x < HY * kRunsPerRow) {
+            const int r = threadIdx.x % HY, xr = run_start(threadIdx.x / HY);
             float2 hm[kRun];
             float hp[kRun];
 #pragma unroll
@@ -338,23 +347,23 @@ l1_ssim_bwd_kernel(uint32_t H, uint32_t W, const float *__restrict__ img, const 
             }
 #pragma unroll
             for (int j = 0; j < kRun; ++j) {
-                s_m[(xr + j) * kColS + r] = hm[j];
-                s_p[(xr + j) * kColS + r] = hp[j];
+                s_m[(xr + j) * CS + r] = hm[j];
+                s_p[(xr + j) * CS + r] = hp[j];
             }
         }
         __syncthreads();
         {
-            const int ly0 = ty * kRowsPerThread;
-            float2 vm[kRowsPerThread];
-            float vp[kRowsPerThread];
+            const int ly0 = ty * RPT;
+            float2 vm[RPT];
+            float vp[RPT];
 #pragma unroll
-            for (int j = 0; j < kRowsPerThread; ++j) { vm[j] = f2(0.f, 0.f); vp[j] = 0.f; }
+            for (int j = 0; j < RPT; ++j) { vm[j] = f2(0.f, 0.f); vp[j] = 0.f; }
 #pragma unroll
-            for (int e = 0; e < kRowsPerThread + kWin - 1; ++e) {
-                const float2 m = s_m[tx * kColS + ly0 + e];
-                const float p = s_p[tx * kColS + ly0 + e];
+            for (int e = 0; e < RPT + kWin - 1; ++e) {
+                const float2 m = s_m[tx * CS + ly0 + e];
+                const float p = s_p[tx * CS + ly0 + e];
 #pragma unroll
-                for (int j = 0; j < kRowsPerThread; ++j) {
+                for (int j = 0; j < RPT; ++j) {
                     const int k = e - j;
                     if (k >= 0 && k < kWin) {
                         const float g = win.g[k];
@@ -364,7 +373,7 @@ l1_ssim_bwd_kernel(uint32_t H, uint32_t W, const float *__restrict__ img, const 
                 }
             }
 #pragma unroll
-            for (int j = 0; j < kRowsPerThread; ++j) {
+            for (int j = 0; j < RPT; ++j) {
                 const int py = y0 + ly0 + j;
                 float v = 0.f;
                 if (px < (int)W && py < (int)H) {
@@ -379,8 +388,8 @@ l1_ssim_bwd_kernel(uint32_t H, uint32_t W, const float *__restrict__ img, const 
         __syncthreads();
     }
 #pragma unroll
-    for (int j = 0; j < kRowsPerThread; ++j) {
-        const int py = y0 + ty * kRowsPerThread + j;
+    for (int j = 0; j < RPT; ++j) {
+        const int py = y0 + ty * RPT + j;
         if (px < (int)W && py < (int)H) {
             const size_t o = img_off + ((size_t)py * W + px) * 3;
 #pragma unroll
@@ -421,8 +430,10 @@ extern "C" int b200splat_invert_4x4(uint32_t C, const float *mats, float *out, v
     return 0;
 }
 
+constexpr int kFwdTY = 32;  // output rows per forward block (16 measured slower for the forward: 0.104 vs 0.089 ms)
+
 static inline uint32_t ssim_blocks(uint32_t C, uint32_t H, uint32_t W) {
-    return C * div_up(H, kTile) * div_up(W, kTile);
+    return C * div_up(H, kFwdTY) * div_up(W, kTile);
 }
 
 extern "C" size_t b200splat_l1_ssim_workspace_bytes(uint32_t C, uint32_t H, uint32_t W) {
@@ -441,11 +452,11 @@ extern "C" int b200splat_l1_ssim_fwd(uint32_t C, uint32_t H, uint32_t W, const f
                 "workspace too small (see b200splat_l1_ssim_workspace_bytes)");
     static const Window win = make_window();
     cudaStream_t st = (cudaStream_t)stream;
-    const dim3 grid(div_up(W, kTile), div_up(H, kTile), C);
-    const size_t smem = (size_t)(kHalo * kRowS * 2 + kTile * kColS * 5) * sizeof(float);
-    cudaFuncSetAttribute(l1_ssim_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const dim3 grid(div_up(W, kTile), div_up(H, kFwdTY), C);
+    const size_t smem = (size_t)((kFwdTY + 2 * kHalf) * kRowS * 2 + kTile * (kFwdTY + 2 * kHalf + 1) * 5) * sizeof(float);
+    cudaFuncSetAttribute(l1_ssim_fwd_kernel<kFwdTY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     float *partials = reinterpret_cast<float *>(workspace);
-    l1_ssim_fwd_kernel<<<grid, 256, smem, st>>>(H, W, img, target, win, d_mu, d_xx, d_xy, partials);
+    l1_ssim_fwd_kernel<kFwdTY><<<grid, 256, smem, st>>>(H, W, img, target, win, d_mu, d_xx, d_xy, partials);
     B2S_CHECK_LAUNCH(where);
     const double n_l1 = (double)C * H * W * 3, n_ssim = (double)C * (H - 2 * kHalf) * (W - 2 * kHalf) * 3;
     l1_ssim_finalize_kernel<<<1, 256, 0, st>>>(ssim_blocks(C, H, W), partials, n_l1, n_ssim, ssim_lambda, out3);
@@ -461,13 +472,16 @@ extern "C" int b200splat_l1_ssim_bwd(uint32_t C, uint32_t H, uint32_t W, const f
     B2S_REQUIRE(C >= 1 && C <= 65535, where, "1..65535 images");
     static const Window win = make_window();
     cudaStream_t st = (cudaStream_t)stream;
-    const dim3 grid(div_up(W, kTile), div_up(H, kTile), C);
-    const size_t smem = (size_t)(kHalo * kRowS * 3 + kTile * kColS * 3) * sizeof(float);
-    cudaFuncSetAttribute(l1_ssim_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool tall = tuning_variant() == 9;  // A/B: 32-row tiles (2 blocks/SM)
+    const int TYv = tall ? 32 : 16;
+    const dim3 grid(div_up(W, kTile), div_up(H, TYv), C);
+    const size_t smem = (size_t)((TYv + 2 * kHalf) * kRowS * 3 + kTile * (TYv + 2 * kHalf + 1) * 3) * sizeof(float);
+    cudaFuncSetAttribute(l1_ssim_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(l1_ssim_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const double n_l1 = (double)C * H * W * 3, n_ssim = (double)C * (H - 2 * kHalf) * (W - 2 * kHalf) * 3;
-    l1_ssim_bwd_kernel<<<grid, 256, smem, st>>>(H, W, img, target, win, d_mu, d_xx, d_xy, v_loss,
-                                                (float)((1.0 - (double)ssim_lambda) / n_l1),
-                                                (float)(-(double)ssim_lambda / n_ssim), v_img);
+    const float k1 = (float)((1.0 - (double)ssim_lambda) / n_l1), k2 = (float)(-(double)ssim_lambda / n_ssim);
+    if (tall) l1_ssim_bwd_kernel<32><<<grid, 256, smem, st>>>(H, W, img, target, win, d_mu, d_xx, d_xy, v_loss, k1, k2, v_img);
+    else l1_ssim_bwd_kernel<16><<<grid, 256, smem, st>>>(H, W, img, target, win, d_mu, d_xx, d_xy, v_loss, k1, k2, v_img);
     B2S_CHECK_LAUNCH(where);
     return 0;
 }
