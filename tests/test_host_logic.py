@@ -79,3 +79,44 @@ def test_sh_argument_checks():
         S.spherical_harmonics(3, torch.zeros(4, 3), torch.zeros(4, 9, 3))
     with pytest.raises(AssertionError):
         S.spherical_harmonics(1, torch.zeros(4, 3), torch.zeros(5, 4, 3))
+
+
+def test_step_api_argument_checks_and_no_cpu_fallback():
+    """f4 row: the fused training-step entry points validate like the operators and have no CPU path."""
+    N = 6
+    with pytest.raises(AssertionError):
+        S.splat_activations(torch.zeros(N, 2), torch.zeros(N))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        S.splat_activations(torch.zeros(N, 3), torch.zeros(N))
+    with pytest.raises(AssertionError, match="11x11"):
+        S.l1_ssim_loss(torch.zeros(1, 8, 32, 3), torch.zeros(1, 8, 32, 3))
+    with pytest.raises(AssertionError):
+        S.l1_ssim_loss(torch.zeros(1, 16, 16, 3), torch.zeros(1, 16, 17, 3))
+    with pytest.raises(AssertionError):
+        S.l1_ssim_loss(torch.zeros(1, 16, 16, 4), torch.zeros(1, 16, 16, 4))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        S.l1_ssim_loss(torch.zeros(1, 16, 16, 3), torch.zeros(1, 16, 16, 3))
+    from splat_one_b200.step import invert_poses
+
+    with pytest.raises(RuntimeError, match="CUDA"):
+        invert_poses(torch.eye(4)[None])
+    # poses that require a gradient go through torch (pose optimisation), CPU included
+    p = torch.eye(4)[None].clone().requires_grad_()
+    assert torch.allclose(invert_poses(p), torch.eye(4)[None])
+
+
+def test_rasterization_split_sh_table_asserts():
+    N = 10
+    ok = dict(means=torch.zeros(N, 3), quats=torch.zeros(N, 4), scales=torch.zeros(N, 3), opacities=torch.zeros(N),
+              viewmats=torch.eye(4)[None], Ks=torch.eye(3)[None], width=32, height=32)
+    with pytest.raises(AssertionError, match="sh_degree"):
+        S.rasterization(**ok, colors=(torch.zeros(N, 1, 3), torch.zeros(N, 15, 3)))
+    with pytest.raises(AssertionError):
+        S.rasterization(**ok, colors=(torch.zeros(N, 2, 3), torch.zeros(N, 15, 3)), sh_degree=3)
+    with pytest.raises(AssertionError):
+        S.rasterization(**ok, colors=(torch.zeros(N, 1, 3), torch.zeros(N + 1, 15, 3)), sh_degree=3)
+    with pytest.raises(AssertionError):  # (sh_degree+1)^2 <= 1 + shN.shape[1]
+        S.rasterization(**ok, colors=(torch.zeros(N, 1, 3), torch.zeros(N, 3, 3)), sh_degree=3)
+    # CPU tensors take the concatenating route and then fail loudly at the first kernel
+    with pytest.raises(RuntimeError, match="CUDA"):
+        S.rasterization(**ok, colors=(torch.zeros(N, 1, 3), torch.zeros(N, 15, 3)), sh_degree=3)
