@@ -10,7 +10,7 @@ ext.cpp; vendored glm) with nvcc directly — the reference's own build system (
 outputs are object files and `gsplat_ref_csrc.so` under oracle/_ref/ (git-ignored; it travels
 to the GPU box with the snapshot).  The module exposes the pybind11 entry points of
 CS/ext.cpp:11-56 (`fully_fused_projection_fwd`, `isect_tiles`, `rasterize_to_pixels_fwd`, ...),
-which tests/test_gpu_vs_reference.py and tools/reference_cuda_bench.py call with raw tensors —
+which tests/test_gpu_vs_reference.py and tests/reference_cuda_ab.py call with raw tensors —
 no reference Python code is needed on the box.
 """
 import concurrent.futures as cf

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Developer benchmark (extra evidence, not the contract's reference arm): the reference's OWN CUDA
+"""A/B checker (test infrastructure; extra evidence, not the contract's reference arm): the reference's OWN CUDA
 kernels (oracle/_ref/gsplat_ref_csrc.so, built for sm_100a by oracle/build_ref.py) chained the way
 G/rendering.py + the autograd Functions of G/cuda/_wrapper.py chain them, on config B, on the same
 B200 and the same synthetic scene as bench.py — next to this repo's rasterization()+backward.
@@ -7,7 +7,7 @@ B200 and the same synthetic scene as bench.py — next to this repo's rasterizat
 The reference chain is driven with raw pybind calls (no reference Python, which does not exist on the
 GPU box): forward = projection, dirs / masks / SH / +0.5 / clamp, isect_tiles, offset encode, raster;
 backward = raster bwd, clamp / SH bwd / v_dirs, projection bwd — i.e. the reference WITHOUT its Python
-and autograd overhead, which favours the reference.      python tools/reference_cuda_bench.py [N W H]
+and autograd overhead, which favours the reference.      python tests/reference_cuda_ab.py [N W H [model]]
 """
 import json
 import math
