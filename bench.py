@@ -533,7 +533,9 @@ def run_gpu(args):
             "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "n_gaussians": N_GAUSS, "cameras_per_gpu": C_local,
-                       "visible_pairs": V, "n_isects": I, "l2_policy": "per-step working set ~1 GB > 126 MB L2",
+                       "visible_pairs": V, "n_isects": I, "tiles_per_visible_gaussian": round(I / max(V, 1), 3),
+                       "listed_pairs_per_pixel": round(I * 256 / max(P, 1), 1),
+                       "l2_policy": "per-step working set ~1 GB > 126 MB L2",
                        "parallelism": f"camera-sharded dp{world}" + (" + all-gather of colour cotangents (12 MB/rank) + NCCL allreduce of 44 MB grads" if world > 1 else "")},
             "clocks": clocks,
             "e2e": {"value": world * C_local * HEIGHT * WIDTH / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s",
