@@ -4,15 +4,19 @@ hot path of inuex35/splat_one's gsplat fork, in PyTorch/numpy, float32 by defaul
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl
 reference` legs may import this package; the product (`splat_one_b200/`) never does.
 
-Parity status: PINNED for pinhole / ortho / fisheye projection, SH, tile intersection and
-offset encode against the reference's own pure-PyTorch implementation
-(`gsplat/cuda/_torch_impl.py`, imported from /root/reference by `oracle/gen_golden.py`,
-vectors committed under tests/golden/).  The reference ships NO CPU-runnable
-implementation of `rasterize_to_pixels` (its `_rasterize_to_pixels` needs nerfacc + a CUDA
-op, _torch_impl.py:536, 610-645) and NO test of `camera_model="spherical"`; for those two
-the CUDA source is the only spec and the restatement below is "parity unpinned" against
-executed reference output (cross-checked instead between two independent restatements:
-`rasterize_to_pixels` here vs oracle/raster_ref.c, and by finite differences).
+Parity status: PINNED.
+  * pinhole / ortho / fisheye projection, SH, tile intersection, offset encode and the un-fused
+    operators against the reference's own pure-PyTorch implementation (`gsplat/cuda/_torch_impl.py`,
+    imported from /root/reference by `oracle/gen_golden.py`; vectors under tests/golden/*_ref.npz);
+  * `rasterize_to_pixels` against the reference's own `_rasterize_to_pixels` run on the CPU
+    (`raster_ref_d1/d3.npz`; its nerfacc dependency restated in oracle/nerfacc_stub.py);
+  * what the reference's CPU code cannot pin — `camera_model="spherical"` (forward, closed-form
+    VJP, packed rules), the packed projection's rules and the CUDA rasterizer itself — against
+    vectors produced on a B200 by the reference's OWN CUDA kernels (`oracle/build_ref.py` builds
+    them into oracle/_ref, `oracle/gen_golden_refcuda.py` wrote tests/golden/refcuda_*.npz;
+    tests/test_refcuda_golden.py checks this file against them in the CPU suite).
+Still unpinned (CUDA-only or un-vendored algorithms, restated from source / publication):
+`selective_adam_update`, `compute_relocation`, and the SSIM of oracle/step_ref.py.
 
 Where `_torch_impl` and the fork's CUDA disagree, the CUDA is what splat_one executes and
 what is restated (`fork_faithful=True`, SURVEY.md §8c list); `fork_faithful=False`
