@@ -15,8 +15,9 @@ Parity status: PINNED.
     vectors produced on a B200 by the reference's OWN CUDA kernels (`oracle/build_ref.py` builds
     them into oracle/_ref, `oracle/gen_golden_refcuda.py` wrote tests/golden/refcuda_*.npz;
     tests/test_refcuda_golden.py checks this file against them in the CPU suite).
-Still unpinned (CUDA-only or un-vendored algorithms, restated from source / publication):
-`selective_adam_update`, `compute_relocation`, and the SSIM of oracle/step_ref.py.
+`selective_adam_update` / `compute_relocation` (CUDA only in the reference) are restated from source here
+and pinned on the GPU box by tests/test_gpu_vs_reference.py.  Still unpinned (un-vendored
+dependency, restated from its publication): the SSIM of oracle/step_ref.py.
 
 Where `_torch_impl` and the fork's CUDA disagree, the CUDA is what splat_one executes and
 what is restated (`fork_faithful=True`, SURVEY.md §8c list); `fork_faithful=False`

@@ -199,3 +199,83 @@ def test_rasterization_end_to_end_vs_reference_cuda_chain():
     for a, b in ((rc, r_rc), (ra, r_ra)):
         err = (a - b).abs()
         assert (err > 1e-4 + 1e-4 * b.abs()).float().mean().item() < 2e-3, err.max().item()
+
+
+def test_selective_adam_and_relocation_vs_reference_cuda():
+    """f3 row: the optimizer / densifier kernels against the reference's own (CS/adam.cu,
+    CS/compute_relocation.cu) — these have no CPU implementation in the reference."""
+    R = ref_cuda.load()
+    N, M = 4001, 48
+    g = torch.Generator(device=DEV).manual_seed(9)
+    param = torch.randn(N, M, device=DEV, generator=g)
+    grad = torch.randn(N, M, device=DEV, generator=g)
+    m1 = torch.randn(N, M, device=DEV, generator=g) * 0.1
+    m2 = torch.rand(N, M, device=DEV, generator=g) * 0.01
+    vis = torch.rand(N, device=DEV, generator=g) > 0.4
+    ours = [t.clone() for t in (param, m1, m2)]
+    ref = [t.clone() for t in (param, m1, m2)]
+    for _ in range(3):
+        S.selective_adam_update(ours[0], grad, ours[1], ours[2], vis, 1e-2, 0.9, 0.999, 1e-8, N, M)
+        R.selective_adam_update(ref[0], grad, ref[1], ref[2], vis, 1e-2, 0.9, 0.999, 1e-8, N, M)
+    for name, a, b in zip(("param", "exp_avg", "exp_avg_sq"), ours, ref):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-7), (name, (a - b).abs().max().item())
+    assert torch.equal(ours[0][~vis], param[~vis])  # invisible Gaussians untouched
+
+    n_max = 51
+    binoms = torch.zeros(n_max, n_max, device=DEV)
+    for n in range(n_max):
+        for k in range(n + 1):
+            binoms[n, k] = math.comb(n, k)
+    op = torch.rand(N, device=DEV, generator=g) * 0.98 + 0.01
+    sc = torch.rand(N, 3, device=DEV, generator=g) + 0.01
+    ratios = torch.randint(1, n_max + 1, (N,), device=DEV, generator=g)
+    new_op, new_sc = S.compute_relocation(op, sc, ratios.clone(), binoms)
+    r_op, r_sc = R.compute_relocation(op, sc, ratios.int(), binoms, n_max)
+    assert torch.allclose(new_op, r_op, rtol=1e-5, atol=1e-7) and torch.allclose(new_sc, r_sc, rtol=2e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("model", ["pinhole", "ortho", "fisheye", "spherical"])
+def test_unfused_ops_vs_reference_cuda(model):
+    """f2 row: quat_scale_to_covar_preci, world_to_cam and proj (all camera models) forward and
+    backward against the reference's own kernels."""
+    R = ref_cuda.load()
+    N, C, W, H = 3000, 2, 200, 120
+    g = torch.Generator(device=DEV).manual_seed(13)
+    quats = torch.randn(N, 4, device=DEV, generator=g)
+    scales = torch.rand(N, 3, device=DEV, generator=g) * 0.2 + 0.01
+    means = torch.randn(N, 3, device=DEV, generator=g) + torch.tensor([0.0, 0.0, 5.0], device=DEV)
+    viewmats = torch.eye(4, device=DEV).repeat(C, 1, 1)
+    viewmats[1, :3, 3] = torch.tensor([0.2, -0.1, 0.3], device=DEV)
+    Ks = torch.tensor([[150.0, 0.0, W / 2], [0.0, 150.0, H / 2], [0.0, 0.0, 1.0]], device=DEV).repeat(C, 1, 1)
+
+    q, s = quats.clone().requires_grad_(), scales.clone().requires_grad_()
+    cov, pre = S.quat_scale_to_covar_preci(q, s)
+    r_cov, r_pre = R.quat_scale_to_covar_preci_fwd(quats, scales, True, True, False)
+    assert torch.allclose(cov, r_cov, rtol=1e-5, atol=1e-6) and torch.allclose(pre, r_pre, rtol=1e-4, atol=1e-3)
+    v1, v2 = torch.randn(cov.shape, device=DEV, generator=g), torch.randn(pre.shape, device=DEV, generator=g) * 1e-3
+    gq, gs = torch.autograd.grad((cov * v1).sum() + (pre * v2).sum(), (q, s))
+    rq, rs = R.quat_scale_to_covar_preci_bwd(quats, scales, v1, v2, False)
+    assert_grad_close(gq, rq, what="v_quats", frac_ok=0.999)
+    assert_grad_close(gs, rs, what="v_scales", frac_ok=0.999)
+
+    m, c = means.clone().requires_grad_(), r_cov.clone().requires_grad_()
+    mc, cc = S.world_to_cam(m, c, viewmats)
+    r_mc, r_cc = R.world_to_cam_fwd(means, r_cov, viewmats)
+    assert torch.allclose(mc, r_mc, rtol=1e-5, atol=1e-6) and torch.allclose(cc, r_cc, rtol=1e-5, atol=1e-6)
+    v3, v4 = torch.randn(mc.shape, device=DEV, generator=g), torch.randn(cc.shape, device=DEV, generator=g)
+    gm, gc = torch.autograd.grad((mc * v3).sum() + (cc * v4).sum(), (m, c))
+    rm, rc_, _ = R.world_to_cam_bwd(means, r_cov, viewmats, v3, v4, True, True, False)
+    assert_grad_close(gm, rm, what="v_means", frac_ok=0.999)
+    assert_grad_close(gc, rc_, what="v_covars", frac_ok=0.999)
+
+    cm = ref_cuda.camera_model(R, model)
+    mcl, ccl = r_mc.clone().requires_grad_(), r_cc.clone().requires_grad_()
+    m2, c2 = S.proj(mcl, ccl, Ks, W, H, camera_model=model)
+    r_m2, r_c2 = R.proj_fwd(r_mc, r_cc, Ks, W, H, cm)
+    assert torch.allclose(m2, r_m2, rtol=2e-4, atol=5e-3 if model == "spherical" else 1e-3), (m2 - r_m2).abs().max()
+    assert torch.allclose(c2, r_c2, rtol=1e-3, atol=1e-3), (c2 - r_c2).abs().max()
+    v5, v6 = torch.randn(m2.shape, device=DEV, generator=g), torch.randn(c2.shape, device=DEV, generator=g) * 0.1
+    gm2, gc2 = torch.autograd.grad((m2 * v5).sum() + (c2 * v6).sum(), (mcl, ccl))
+    rm2, rc2 = R.proj_bwd(r_mc, r_cc, Ks, W, H, cm, v5, v6)
+    assert_grad_close(gm2, rm2, what=f"proj v_means ({model})", frac_ok=0.998)
+    assert_grad_close(gc2, rc2, what=f"proj v_covars ({model})", frac_ok=0.998)
