@@ -485,6 +485,20 @@ B200SPLAT_API int b200splat_sh_colors_staged_bwd(
  * host synchronisation (torch.linalg.inv syncs to report singular inputs). */
 B200SPLAT_API int b200splat_invert_4x4(uint32_t C, const float *mats, float *out, void *stream);
 
+/* Packed (COO) colour stage for the split table: as b200splat_sh_colors_packed_fwd/bwd with
+ * per_view = 0, coefficients read from sh0 [N,1,3] / shN [N,K-1,3].  v_sh0 / v_shN accumulate:
+ * zero-fill them first. */
+B200SPLAT_API int b200splat_sh_colors_packed_split_fwd(
+    uint32_t nnz, uint32_t C, uint32_t N, uint32_t K, uint32_t degrees_to_use,
+    const float *means, const float *campos, const float *sh0, const float *shN,
+    const int64_t *camera_ids, const int64_t *gaussian_ids, float *colors, void *stream);
+
+B200SPLAT_API int b200splat_sh_colors_packed_split_bwd(
+    uint32_t nnz, uint32_t C, uint32_t N, uint32_t K, uint32_t degrees_to_use,
+    const float *means, const float *campos, const float *sh0, const float *shN,
+    const int64_t *camera_ids, const int64_t *gaussian_ids, const float *colors,
+    const float *v_colors, float *v_sh0, float *v_shN, float *v_means, void *stream);
+
 B200SPLAT_API int b200splat_splat_activations_fwd(
     uint32_t N, const float *scales_raw, const float *opacities_raw,
     float *scales, float *opacities, void *stream);

@@ -17,7 +17,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("B200SPLAT_LIB", _PKG / "libb200splat.so"))
 
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 _P = c_void_p
 _U32 = c_uint32
@@ -48,6 +48,9 @@ SIGNATURES = {
     "b200splat_sh_colors_bwd": (_I, [_U32, _U32, _U32, _U32, _I, _P, _P, _P, _P, _P, _P, _P, _P, _U32, _U32, _P]),
     "b200splat_sh_colors_packed_fwd": (_I, [_U32, _U32, _U32, _U32, _U32, _I, _P, _P, _P, _P, _P, _P, _P]),
     "b200splat_sh_colors_packed_bwd": (_I, [_U32, _U32, _U32, _U32, _U32, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "b200splat_sh_colors_packed_split_fwd": (_I, [_U32, _U32, _U32, _U32, _U32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "b200splat_sh_colors_packed_split_bwd": (_I, [_U32, _U32, _U32, _U32, _U32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                                  _P, _P]),
     "b200splat_isect_count": (_I, [_I, _U32, _U32, _U32, _P, _P, _P, _U32, _U32, _U32, _P, _P, _P, _P, c_size_t, _P]),
     "b200splat_isect_sorted_workspace_bytes": (c_size_t, [_U64, _U64]),
     "b200splat_isect_sorted": (_I, [_I, _U32, _U32, _U32, _P, _P, _P, _P, _P, _U64, _U32, _U32, _U32, _P, _P, _P, _P,

@@ -330,14 +330,23 @@ template <int NB>
 __global__ void __launch_bounds__(kThreads)
 sh_colors_packed_fwd_kernel(uint32_t nnz, uint32_t N, uint32_t K, uint32_t deg, int per_view,
                             const float *__restrict__ means, const float *__restrict__ campos,
-                            const float *__restrict__ coeffs, const int64_t *__restrict__ camera_ids,
+                            const float *__restrict__ sh0, const float *__restrict__ coeffs,
+                            const int64_t *__restrict__ camera_ids,
                             const int64_t *__restrict__ gaussian_ids, float *__restrict__ colors) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nnz) return;
     const uint64_t n = (uint64_t)gaussian_ids[i], c = (uint64_t)camera_ids[i];
-    const float *row = coeffs + (per_view ? c * N + n : n) * K * 3;
     float cf[NB * 3];
-    load_row<NB>(row, cf, ((K * 3) % 4 == 0) && ((reinterpret_cast<uintptr_t>(coeffs) & 15) == 0));
+    if (sh0 != nullptr) {
+        // split table (sh0 [N,1,3], coeffs = shN [N,K-1,3]; gsplat_trainer.py:474 without the cat)
+        cf[0] = __ldg(sh0 + 3 * n); cf[1] = __ldg(sh0 + 3 * n + 1); cf[2] = __ldg(sh0 + 3 * n + 2);
+        const float *rowN = coeffs + n * (K - 1) * 3;
+#pragma unroll
+        for (int k = 3; k < NB * 3; k++) cf[k] = __ldg(rowN + k - 3);
+    } else {
+        const float *row = coeffs + (per_view ? c * N + n : n) * K * 3;
+        load_row<NB>(row, cf, ((K * 3) % 4 == 0) && ((reinterpret_cast<uintptr_t>(coeffs) & 15) == 0));
+    }
     float x = 0.f, y = 0.f, z = 0.f;
     if (NB > 1) {
         const float dx = __ldg(means + 3 * n) - campos[3 * c], dy = __ldg(means + 3 * n + 1) - campos[3 * c + 1],
@@ -361,9 +370,10 @@ template <int NB>
 __global__ void __launch_bounds__(kThreads)
 sh_colors_packed_bwd_kernel(uint32_t nnz, uint32_t N, uint32_t K, uint32_t deg, int per_view, int unique,
                             int means_unique, const float *__restrict__ means, const float *__restrict__ campos,
-                            const float *__restrict__ coeffs, const int64_t *__restrict__ camera_ids,
+                            const float *__restrict__ sh0, const float *__restrict__ coeffs,
+                            const int64_t *__restrict__ camera_ids,
                             const int64_t *__restrict__ gaussian_ids, const float *__restrict__ colors,
-                            const float *__restrict__ v_colors, float *__restrict__ v_coeffs,
+                            const float *__restrict__ v_colors, float *__restrict__ v_sh0, float *__restrict__ v_coeffs,
                             float *__restrict__ v_means) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nnz) return;
@@ -384,7 +394,14 @@ sh_colors_packed_bwd_kernel(uint32_t nnz, uint32_t N, uint32_t K, uint32_t deg, 
     float vc[NB * 3];
     if (v_means != nullptr && NB > 1) {
         float cf[NB * 3];
-        load_row<NB>(coeffs + row_id * K * 3, cf, vec_ok);
+        if (sh0 != nullptr) {
+            cf[0] = cf[1] = cf[2] = 0.f;  // the DC basis has no direction derivative
+            const float *rowN = coeffs + n * (K - 1) * 3;
+#pragma unroll
+            for (int k = 3; k < NB * 3; k++) cf[k] = __ldg(rowN + k - 3);
+        } else {
+            load_row<NB>(coeffs + row_id * K * 3, cf, vec_ok);
+        }
         float vx = 0.f, vy = 0.f, vz = 0.f;
         sh_for_each_basis<true>(deg, x, y, z, [&](int k, float B, float Bx, float By, float Bz) {
             vc[3 * k] = B * vr; vc[3 * k + 1] = B * vg; vc[3 * k + 2] = B * vb;
@@ -402,6 +419,19 @@ sh_colors_packed_bwd_kernel(uint32_t nnz, uint32_t N, uint32_t K, uint32_t deg, 
         sh_for_each_basis<false>(deg, x, y, z, [&](int k, float B, float, float, float) {
             vc[3 * k] = B * vr; vc[3 * k + 1] = B * vg; vc[3 * k + 2] = B * vb;
         });
+    }
+    if (sh0 != nullptr) {
+        float *v0 = v_sh0 + 3 * n, *vN = v_coeffs + n * (K - 1) * 3;
+        if (unique) {
+            v0[0] = vc[0]; v0[1] = vc[1]; v0[2] = vc[2];
+#pragma unroll
+            for (int k = 3; k < NB * 3; k++) vN[k - 3] = vc[k];
+        } else {
+            atomicAdd(v0, vc[0]); atomicAdd(v0 + 1, vc[1]); atomicAdd(v0 + 2, vc[2]);
+#pragma unroll
+            for (int k = 3; k < NB * 3; k++) atomicAdd(vN + k - 3, vc[k]);
+        }
+        return;
     }
     float *vrow = v_coeffs + row_id * K * 3;
     if (unique) {
@@ -763,18 +793,17 @@ extern "C" int b200splat_sh_colors_bwd(uint32_t C, uint32_t N, uint32_t K, uint3
     return 0;
 }
 
-extern "C" int b200splat_sh_colors_packed_fwd(uint32_t nnz, uint32_t C, uint32_t N, uint32_t K, uint32_t deg,
-                                              int per_view, const float *means, const float *campos,
-                                              const float *coeffs, const int64_t *camera_ids,
-                                              const int64_t *gaussian_ids, float *colors, void *stream) {
-    const char *where = "b200splat_sh_colors_packed_fwd";
+static int packed_fwd_impl(const char *where, uint32_t nnz, uint32_t C, uint32_t N, uint32_t K, uint32_t deg,
+                           int per_view, const float *means, const float *campos, const float *sh0,
+                           const float *coeffs, const int64_t *camera_ids, const int64_t *gaussian_ids, float *colors,
+                           void *stream) {
     (void)C;
     B2S_REQUIRE(deg <= 4, where, "degrees_to_use must be <= 4");
     B2S_REQUIRE((deg + 1) * (deg + 1) <= K, where, "K too small for degrees_to_use");
     if (nnz == 0) return 0;
     const unsigned grid = div_up(nnz, kThreads);
     cudaStream_t st = (cudaStream_t)stream;
-#define B2S_SHP(NB) sh_colors_packed_fwd_kernel<NB><<<grid, kThreads, 0, st>>>(nnz, N, K, deg, per_view, means, campos, coeffs, camera_ids, gaussian_ids, colors)
+#define B2S_SHP(NB) sh_colors_packed_fwd_kernel<NB><<<grid, kThreads, 0, st>>>(nnz, N, K, deg, per_view, means, campos, sh0, coeffs, camera_ids, gaussian_ids, colors)
     switch (deg) {
         case 0: B2S_SHP(1); break;
         case 1: B2S_SHP(4); break;
@@ -787,19 +816,18 @@ extern "C" int b200splat_sh_colors_packed_fwd(uint32_t nnz, uint32_t C, uint32_t
     return 0;
 }
 
-extern "C" int b200splat_sh_colors_packed_bwd(uint32_t nnz, uint32_t C, uint32_t N, uint32_t K, uint32_t deg,
-                                              int per_view, const float *means, const float *campos,
-                                              const float *coeffs, const int64_t *camera_ids,
-                                              const int64_t *gaussian_ids, const float *colors,
-                                              const float *v_colors, float *v_coeffs, float *v_means, void *stream) {
-    const char *where = "b200splat_sh_colors_packed_bwd";
+static int packed_bwd_impl(const char *where, uint32_t nnz, uint32_t C, uint32_t N, uint32_t K, uint32_t deg,
+                           int per_view, const float *means, const float *campos, const float *sh0,
+                           const float *coeffs, const int64_t *camera_ids, const int64_t *gaussian_ids,
+                           const float *colors, const float *v_colors, float *v_sh0, float *v_coeffs, float *v_means,
+                           void *stream) {
     B2S_REQUIRE(deg <= 4, where, "degrees_to_use must be <= 4");
     B2S_REQUIRE((deg + 1) * (deg + 1) <= K, where, "K too small for degrees_to_use");
     if (nnz == 0) return 0;
     const unsigned grid = div_up(nnz, kThreads);
     cudaStream_t st = (cudaStream_t)stream;
     const int unique = (per_view || C == 1) ? 1 : 0, means_unique = (C == 1) ? 1 : 0;
-#define B2S_SHP(NB) sh_colors_packed_bwd_kernel<NB><<<grid, kThreads, 0, st>>>(nnz, N, K, deg, per_view, unique, means_unique, means, campos, coeffs, camera_ids, gaussian_ids, colors, v_colors, v_coeffs, v_means)
+#define B2S_SHP(NB) sh_colors_packed_bwd_kernel<NB><<<grid, kThreads, 0, st>>>(nnz, N, K, deg, per_view, unique, means_unique, means, campos, sh0, coeffs, camera_ids, gaussian_ids, colors, v_colors, v_sh0, v_coeffs, v_means)
     switch (deg) {
         case 0: B2S_SHP(1); break;
         case 1: B2S_SHP(4); break;
@@ -909,4 +937,45 @@ extern "C" int b200splat_sh_colors_staged_bwd(uint32_t C, uint32_t N, uint32_t K
                                  v_means, means_cam_begin, means_cam_end, smem, st);
     B2S_CHECK_LAUNCH(where);
     return 0;
+}
+
+extern "C" int b200splat_sh_colors_packed_fwd(uint32_t nnz, uint32_t C, uint32_t N, uint32_t K, uint32_t deg,
+                                              int per_view, const float *means, const float *campos,
+                                              const float *coeffs, const int64_t *camera_ids,
+                                              const int64_t *gaussian_ids, float *colors, void *stream) {
+    return packed_fwd_impl("b200splat_sh_colors_packed_fwd", nnz, C, N, K, deg, per_view, means, campos, nullptr, coeffs,
+                           camera_ids, gaussian_ids, colors, stream);
+}
+
+extern "C" int b200splat_sh_colors_packed_bwd(uint32_t nnz, uint32_t C, uint32_t N, uint32_t K, uint32_t deg,
+                                              int per_view, const float *means, const float *campos,
+                                              const float *coeffs, const int64_t *camera_ids,
+                                              const int64_t *gaussian_ids, const float *colors,
+                                              const float *v_colors, float *v_coeffs, float *v_means, void *stream) {
+    return packed_bwd_impl("b200splat_sh_colors_packed_bwd", nnz, C, N, K, deg, per_view, means, campos, nullptr, coeffs,
+                           camera_ids, gaussian_ids, colors, v_colors, nullptr, v_coeffs, v_means, stream);
+}
+
+// split table: sh0 [N,1,3] + shN [N,K-1,3] (shared, never per view); v_sh0 / v_shN must be zero-filled by
+// the caller when a Gaussian can be invisible or seen by several cameras (rows are accumulated)
+extern "C" int b200splat_sh_colors_packed_split_fwd(uint32_t nnz, uint32_t C, uint32_t N, uint32_t K, uint32_t deg,
+                                                    const float *means, const float *campos, const float *sh0,
+                                                    const float *shN, const int64_t *camera_ids,
+                                                    const int64_t *gaussian_ids, float *colors, void *stream) {
+    const char *where = "b200splat_sh_colors_packed_split_fwd";
+    B2S_REQUIRE(sh0 != nullptr && K >= 1, where, "sh0 is required");
+    return packed_fwd_impl(where, nnz, C, N, K, deg, 0, means, campos, sh0, shN, camera_ids, gaussian_ids, colors,
+                           stream);
+}
+
+extern "C" int b200splat_sh_colors_packed_split_bwd(uint32_t nnz, uint32_t C, uint32_t N, uint32_t K, uint32_t deg,
+                                                    const float *means, const float *campos, const float *sh0,
+                                                    const float *shN, const int64_t *camera_ids,
+                                                    const int64_t *gaussian_ids, const float *colors,
+                                                    const float *v_colors, float *v_sh0, float *v_shN, float *v_means,
+                                                    void *stream) {
+    const char *where = "b200splat_sh_colors_packed_split_bwd";
+    B2S_REQUIRE(sh0 != nullptr && v_sh0 != nullptr, where, "sh0 and v_sh0 are required");
+    return packed_bwd_impl(where, nnz, C, N, K, deg, 0, means, campos, sh0, shN, camera_ids, gaussian_ids, colors,
+                           v_colors, v_sh0, v_shN, v_means, stream);
 }

@@ -24,6 +24,7 @@ from .wrapper import (
     fully_fused_projection,
     gather_rows,
     sh_view_colors_packed,
+    sh_view_colors_packed_split,
     isect_tiles_and_offsets_begin,
     rasterize_to_pixels,
     sh_view_colors,
@@ -78,16 +79,16 @@ def rasterization(
     meta: Dict = {}
 
     # extension (splat_one_b200/step.py): `colors=(sh0, shN)` is the SH table of
-    # gsplat_trainer.py:474 before its `torch.cat`; the un-packed colour stage reads the two
-    # tensors in place, every other configuration concatenates as the caller would have
+    # gsplat_trainer.py:474 before its `torch.cat`; the colour stages read the two tensors in place
+    # (pose gradients and over-long tables concatenate as the caller would have)
     sh_split = None
     if isinstance(colors, (tuple, list)):
         sh0, shN = colors
         assert sh_degree is not None, "a split (sh0, shN) table needs sh_degree"
         assert sh0.dim() == 3 and sh0.shape[1:] == (1, 3) and shN.dim() == 3 and shN.shape[2] == 3, (sh0.shape, shN.shape)
         assert sh0.shape[0] == shN.shape[0], (sh0.shape, shN.shape)
-        if (not packed and not viewmats.requires_grad and sh0.is_cuda
-                and staged_colors_supported(1 + shN.shape[1], True)):
+        if (not viewmats.requires_grad and sh0.is_cuda
+                and (packed or staged_colors_supported(1 + shN.shape[1], True))):
             sh_split = (sh0, shN)
             colors = sh0  # placeholder for the shape asserts below
         else:
@@ -176,7 +177,10 @@ def rasterization(
         else:
             colors = colors.expand(C, -1, -1) if colors.dim() == 2 else colors
     else:
-        if sh_split is not None:
+        if sh_split is not None and packed:
+            colors = sh_view_colors_packed_split(sh_degree, means, viewmats, sh_split[0], sh_split[1], camera_ids,
+                                                 gaussian_ids)  # [nnz, 3]
+        elif sh_split is not None:
             colors = sh_view_colors_split(sh_degree, means, viewmats, sh_split[0], sh_split[1], radii)  # [C, N, 3]
         elif packed and not viewmats.requires_grad:
             # same maths, one fused kernel per direction over the COO rows

@@ -49,7 +49,8 @@ class _Profiler:
     KERNELS = {
         "projection_fwd": 1, "projection_bwd": 1, "projection_packed_count": 3, "projection_packed_fill": 1,
         "projection_packed_bwd": 1, "sh_fwd": 1, "sh_bwd": 1, "camera_centers": 1, "sh_colors_fwd": 1,
-        "sh_colors_bwd": 1, "sh_colors_packed_fwd": 1, "sh_colors_packed_bwd": 1, "isect_count": 2, "isect_fill": 1,
+        "sh_colors_bwd": 1, "sh_colors_packed_fwd": 1, "sh_colors_packed_bwd": 1, "sh_colors_packed_split_fwd": 1,
+        "sh_colors_packed_split_bwd": 1, "isect_count": 2, "isect_fill": 1,
         "isect_sort": 0, "isect_sorted": 5, "isect_depth_order": 3, "isect_tile_order": 2, "invert_4x4": 1, "copy_small": 1, "isect_offset_encode": 1, "rasterize_pack": 1, "rasterize_fwd": 1, "rasterize_bwd": 1,
         "raster_indices_count": 2, "raster_indices_fill": 1, "quat_scale_to_covar_preci_fwd": 1,
         "quat_scale_to_covar_preci_bwd": 1, "world_to_cam_fwd": 1, "world_to_cam_bwd": 1, "proj_fwd": 1, "proj_bwd": 1,
@@ -576,6 +577,53 @@ class _ShViewColorsPacked(torch.autograd.Function):
                    _ptr(campos), _ptr(coeffs), _ptr(camera_ids), _ptr(gaussian_ids), _ptr(colors),
                    _ptr(v_colors.contiguous()), _ptr(v_coeffs), _ptr(v_means))
         return None, v_means, None, (v_coeffs if ctx.needs_input_grad[3] else None), None, None
+
+
+def sh_view_colors_packed_split(sh_degree: int, means: Tensor, viewmats: Tensor, sh0: Tensor, shN: Tensor,
+                                camera_ids: Tensor, gaussian_ids: Tensor) -> Tensor:
+    """`sh_view_colors_packed(deg, means, viewmats, torch.cat([sh0, shN], 1), camera_ids, gaussian_ids)`
+    (R/utils/gsplat_utils/gsplat_trainer.py:474 + G/rendering.py:370-392) without the concatenation
+    and its split backward: the COO colour kernels read `sh0 [N,1,3]` / `shN [N,K-1,3]` in place."""
+    N = means.shape[0]
+    assert sh0.shape == (N, 1, 3) and shN.dim() == 3 and shN.shape[0] == N and shN.shape[2] == 3, (sh0.shape, shN.shape)
+    assert (sh_degree + 1) ** 2 <= 1 + shN.shape[1], (sh_degree, shN.shape)
+    campos = camera_centers(viewmats)
+    return _ShViewColorsPackedSplit.apply(sh_degree, means.contiguous(), campos, sh0.contiguous(), shN.contiguous(),
+                                          camera_ids.contiguous(), gaussian_ids.contiguous())
+
+
+class _ShViewColorsPackedSplit(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sh_degree, means, campos, sh0, shN, camera_ids, gaussian_ids):
+        _check_cuda(means, campos, sh0, shN, camera_ids, gaussian_ids)
+        _f32(means), _f32(sh0), _f32(shN)
+        if camera_ids.dtype != torch.int64 or gaussian_ids.dtype != torch.int64:
+            raise RuntimeError("b200splat: camera_ids / gaussian_ids must be int64")
+        lib = get_lib()
+        C, N, nnz = campos.shape[0], means.shape[0], gaussian_ids.shape[0]
+        K = 1 + shN.shape[1]
+        colors = torch.empty((nnz, 3), device=means.device, dtype=torch.float32)
+        if nnz:
+            native("sh_colors_packed_split_fwd", lib, means.device, nnz, C, N, K, sh_degree, _ptr(means), _ptr(campos),
+                   _ptr(sh0), _ptr(shN), _ptr(camera_ids), _ptr(gaussian_ids), _ptr(colors))
+        ctx.save_for_backward(means, campos, sh0, shN, camera_ids, gaussian_ids, colors)
+        ctx.sh_degree = sh_degree
+        return colors
+
+    @staticmethod
+    def backward(ctx, v_colors):
+        means, campos, sh0, shN, camera_ids, gaussian_ids, colors = ctx.saved_tensors
+        lib = get_lib()
+        C, N, nnz = campos.shape[0], means.shape[0], gaussian_ids.shape[0]
+        K = 1 + shN.shape[1]
+        v_sh0, v_shN = torch.zeros_like(sh0), torch.zeros_like(shN)
+        v_means = torch.zeros_like(means) if ctx.needs_input_grad[1] else None
+        if nnz:
+            native("sh_colors_packed_split_bwd", lib, means.device, nnz, C, N, K, ctx.sh_degree, _ptr(means),
+                   _ptr(campos), _ptr(sh0), _ptr(shN), _ptr(camera_ids), _ptr(gaussian_ids), _ptr(colors),
+                   _ptr(v_colors.contiguous()), _ptr(v_sh0), _ptr(v_shN), _ptr(v_means))
+        return (None, v_means, None, (v_sh0 if ctx.needs_input_grad[3] else None),
+                (v_shN if ctx.needs_input_grad[4] else None), None, None)
 
 
 class _GatherRows(torch.autograd.Function):

@@ -184,3 +184,32 @@ def test_rasterize_splats_options_equal_composed_call(opts):
         assert_grad_close(a, b, what=f"rasterize_splats grad {k} ({opts})", frac_ok=0.999)
     if o.get("absgrad"):
         assert_grad_close(info["means2d"].absgrad, info2["means2d"].absgrad, what="absgrad", frac_ok=0.999)
+
+
+@pytest.mark.parametrize("C", [1, 2])
+@pytest.mark.parametrize("deg", [0, 3])
+def test_packed_split_colour_stage_equals_concatenated_table(C, deg):
+    """COO colour kernels reading sh0 / shN in place == the same kernels on torch.cat([sh0, shN], 1)
+    (C = 1: rows written once; C = 2: rows accumulated with atomics), forward and gradients."""
+    N, K = 3000, 16
+    g = torch.Generator().manual_seed(31 + C)
+    means = (torch.randn(N, 3, generator=g) + torch.tensor([0.0, 0.0, 4.0])).to(DEV)
+    table = (torch.randn(N, K, 3, generator=g) * 0.3).to(DEV)
+    viewmats = torch.eye(4).repeat(C, 1, 1)
+    viewmats[:, :3, 3] = torch.randn(C, 3, generator=g) * 0.2
+    viewmats = viewmats.to(DEV)
+    vis = torch.rand(C, N, generator=g) > 0.3
+    cam, gid = torch.nonzero(vis, as_tuple=True)
+    cam, gid = cam.to(DEV), gid.to(DEV)
+    v = torch.randn(cam.numel(), 3, generator=g).to(DEV)
+
+    m1, t1 = means.clone().requires_grad_(), table.clone().requires_grad_()
+    ref = wrapper.sh_view_colors_packed(deg, m1, viewmats, t1, cam, gid)
+    gm_ref, gt_ref = torch.autograd.grad((ref * v).sum(), (m1, t1))
+    m2 = means.clone().requires_grad_()
+    sh0, shN = table[:, :1].contiguous().requires_grad_(), table[:, 1:].contiguous().requires_grad_()
+    got = wrapper.sh_view_colors_packed_split(deg, m2, viewmats, sh0, shN, cam, gid)
+    gm, g0, gN = torch.autograd.grad((got * v).sum(), (m2, sh0, shN))
+    assert torch.allclose(got, ref, rtol=1e-6, atol=1e-6)
+    assert_grad_close(torch.cat([g0, gN], 1), gt_ref, what="v_table", frac_ok=1.0)
+    assert_grad_close(gm, gm_ref, what="v_means", frac_ok=1.0)
