@@ -155,3 +155,35 @@ def _worker_exchange(rank, world, port, out_dir):
 @pytest.mark.timeout(600)
 def test_colour_cotangent_exchange_equals_gradient_allreduce(tmp_path):
     mp.spawn(_worker_exchange, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+
+
+def _async_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from splat_one_b200.distributed import GradArena
+
+        P = [torch.zeros(5, 3, requires_grad=True), torch.zeros(5, requires_grad=True), torch.zeros(5, 2, 3, requires_grad=True)]
+        for i, p in enumerate(P):
+            p.grad = torch.full_like(p, float(rank + 1 + i))
+        arena = GradArena(P)
+        arena.gather_from_params()
+        # async: one work handle per contiguous run of non-skipped segments (the middle parameter is skipped)
+        works = arena.all_reduce(async_op=True, skip_ptrs={P[1].data_ptr()})
+        assert isinstance(works, list) and len(works) == 2
+        for w in works:
+            w.wait()
+        assert torch.all(arena.views[0] == 1 + 2) and torch.all(arena.views[2] == 3 + 4)
+        assert torch.all(arena.views[1] == float(rank + 2))  # skipped: still the local value
+        # sync call returns the last handle (or None) as before
+        assert arena.all_reduce(skip_ptrs={p.data_ptr() for p in P}) is None
+        if rank == 0:
+            open(os.path.join(out_dir, "ok"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_arena_async_all_reduce_returns_one_work_per_run(tmp_path):
+    mp.spawn(_async_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok")
