@@ -68,3 +68,32 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f"{f} imports the oracle"
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: include/b200splat.h must compile as C99 (no C++-isms, no torch
+    types) and a plain C program must link against libb200splat.so and call it."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "t.c"
+    src.write_text(
+        '#include "b200splat.h"\n#include <stdio.h>\n'
+        "int main(void) {\n"
+        "  if (b200splat_abi_version() <= 0) return 1;\n"
+        "  /* validation error path, no GPU needed */\n"
+        "  if (b200splat_sh_fwd(1, 1, 36, 5, 0, 0, 0, 0, 0) == 0) return 2;\n"
+        '  printf("%s|%s\\n", b200splat_arch(), b200splat_last_error());\n'
+        "  return 0;\n}\n")
+    exe = tmp_path / "t"
+    lib_dir = os.path.dirname(str(_lib.LIB_PATH))
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src),
+                        "-o", str(exe), "-L", lib_dir, "-lb200splat", f"-Wl,-rpath,{lib_dir}"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert out.stdout.startswith("sm_100a|") and "degrees_to_use" in out.stdout
