@@ -214,9 +214,12 @@ B200SPLAT_API int b200splat_sh_colors_packed_bwd(
  *   (inclusive scan) and n_isects_out (device int64[2]: [0] = n_isects, [1] = 1 if some
  *   visible depth has its sign bit set, which sign-extends into the tile/camera fields of
  *   the reference key and is routed to the generic sort; depths may be NULL).
+ *   cum_tiles may be NULL: only tiles_per_gauss and the total n_isects are produced then (no
+ *   scan; the depth-first ordering below scans the counts itself, in depth order).
  * Phase 2 (`_fill`): unsorted keys `cam | tile | depth bits` + flat indices.
  * Phase 3 (`_sort`): stable LSD radix sort of (key,value) on bits [0, end_bit) over a
- *   pair of ping-pong buffers (the reference's cub::DoubleBuffer, CS/isect_tiles.cu:262-299);
+ *   pair of ping-pong buffers (the reference's cub::DoubleBuffer, CS/isect_tiles.cu:262-299;
+ *   here the library's own onesweep passes, csrc/sort.cu — no CUB);
  *   `*selector_out` says which buffer holds the result.  Workspace size from
  *   `_sort_workspace_bytes`.
  * packed != 0: n_elems = nnz and camera_ids [nnz] int64 gives the camera of each row;

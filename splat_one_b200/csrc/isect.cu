@@ -29,23 +29,37 @@ __device__ __forceinline__ TileRect tile_rect(float mx, float my, float radius, 
     return r;
 }
 
+// SUM: also accumulate the total (n_isects) with one atomic per block — the depth-first ordering
+// needs only the total at this point, not the running sums of CS/isect_tiles.cu:200.
+template <bool SUM>
 __global__ void __launch_bounds__(kThreads)
 isect_count_kernel(uint64_t n_elems, const float *__restrict__ means2d, const int32_t *__restrict__ radii,
                    const float *__restrict__ depths, float ts, uint32_t tw, uint32_t th,
-                   int32_t *__restrict__ tiles_per_gauss, int64_t *__restrict__ neg_depth_flag) {
+                   int32_t *__restrict__ tiles_per_gauss, int64_t *__restrict__ neg_depth_flag,
+                   unsigned long long *__restrict__ total_out) {
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_elems) return;
-    const float radius = (float)radii[idx];
     int32_t cnt = 0;
-    if (radius > 0.f) {
-        const float2 m = reinterpret_cast<const float2 *>(means2d)[idx];
-        const TileRect r = tile_rect(m.x, m.y, radius, ts, tw, th);
-        cnt = (int32_t)((r.y1 - r.y0) * (r.x1 - r.x0));
-        // a set sign bit sign-extends into the tile/camera fields of the reference key
-        // (CS/isect_tiles.cu:92): outside the contract, routed to the generic sort
-        if (cnt > 0 && depths != nullptr && __float_as_int(depths[idx]) < 0) *neg_depth_flag = 1;
+    if (idx < n_elems) {
+        const float radius = (float)radii[idx];
+        if (radius > 0.f) {
+            const float2 m = reinterpret_cast<const float2 *>(means2d)[idx];
+            const TileRect r = tile_rect(m.x, m.y, radius, ts, tw, th);
+            cnt = (int32_t)((r.y1 - r.y0) * (r.x1 - r.x0));
+            // a set sign bit sign-extends into the tile/camera fields of the reference key
+            // (CS/isect_tiles.cu:92): outside the contract, routed to the generic sort
+            if (cnt > 0 && depths != nullptr && __float_as_int(depths[idx]) < 0) *neg_depth_flag = 1;
+        }
+        tiles_per_gauss[idx] = cnt;
     }
-    tiles_per_gauss[idx] = cnt;
+    if (SUM) {
+        __shared__ unsigned long long s_sum;
+        if (threadIdx.x == 0) s_sum = 0;
+        __syncthreads();
+        const unsigned w = (unsigned)__reduce_add_sync(0xffffffffu, (unsigned)cnt);
+        if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_sum, (unsigned long long)w);
+        __syncthreads();
+        if (threadIdx.x == 0 && s_sum) atomicAdd(total_out, s_sum);
+    }
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -121,9 +135,17 @@ extern "C" int b200splat_isect_count(int packed, uint32_t C, uint32_t N, uint32_
     const uint64_t n_elems = packed ? (uint64_t)nnz : (uint64_t)C * N;
     cudaMemsetAsync(n_isects_out, 0, 2 * sizeof(int64_t), st);
     if (n_elems == 0) return 0;
-    isect_count_kernel<<<div_up(n_elems, kThreads), kThreads, 0, st>>>(n_elems, means2d, radii, depths, (float)tile_size,
-                                                                        tile_width, tile_height, tiles_per_gauss,
-                                                                        n_isects_out + 1);
+    if (cum_tiles == nullptr) {
+        // total only (the depth-first ordering scans the counts later, in depth order)
+        isect_count_kernel<true><<<div_up(n_elems, kThreads), kThreads, 0, st>>>(
+            n_elems, means2d, radii, depths, (float)tile_size, tile_width, tile_height, tiles_per_gauss, n_isects_out + 1,
+            reinterpret_cast<unsigned long long *>(n_isects_out));
+        B2S_CHECK_LAUNCH(where);
+        return 0;
+    }
+    isect_count_kernel<false><<<div_up(n_elems, kThreads), kThreads, 0, st>>>(
+        n_elems, means2d, radii, depths, (float)tile_size, tile_width, tile_height, tiles_per_gauss, n_isects_out + 1,
+        nullptr);
     B2S_CHECK_LAUNCH(where);
     const int rc = lookback_scan_i32_to_i64(tiles_per_gauss, cum_tiles, n_elems, n_isects_out, scan_workspace,
                                             scan_workspace_bytes_, st);

@@ -167,14 +167,16 @@ lookback_scan_kernel(const int32_t *__restrict__ in, int64_t *__restrict__ out, 
 }
 
 // inclusive scan; *total_out (device) = sum of all elements (0 when n == 0).
+// `workspace_is_zero`: the caller has already zeroed the workspace on this stream (saves the memset node).
 static inline int lookback_scan_i32_to_i64(const int32_t *in, int64_t *out, uint64_t n, int64_t *total_out,
-                                           void *workspace, size_t workspace_bytes, cudaStream_t st) {
+                                           void *workspace, size_t workspace_bytes, cudaStream_t st,
+                                           bool workspace_is_zero = false) {
     if (n == 0) {
         return cudaMemsetAsync(total_out, 0, sizeof(int64_t), st) == cudaSuccess ? 0 : 1;
     }
     const size_t need = scan_workspace_bytes(n);
     if (workspace == nullptr || workspace_bytes < need) return 2;
-    if (cudaMemsetAsync(workspace, 0, need, st) != cudaSuccess) return 1;
+    if (!workspace_is_zero && cudaMemsetAsync(workspace, 0, need, st) != cudaSuccess) return 1;
     const unsigned tiles = (unsigned)((n + kScanTile - 1) / kScanTile);
     unsigned *ticket = reinterpret_cast<unsigned *>(workspace);
     unsigned long long *state = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(workspace) + 16);

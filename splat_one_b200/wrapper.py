@@ -44,14 +44,15 @@ class _Profiler:
     """Optional per-native-call CUDA-event timing + kernel-launch counting (bench.py).
     Disabled by default: `native()` is then a plain call."""
 
-    # kernels launched by this library per native call (csrc/*.cu); the radix sort's
-    # launches are CUB's and counted separately as "library"
+    # kernels launched by this library per native call (csrc/*.cu), memset nodes not counted;
+    # the sorts are own onesweep passes (csrc/sort.cu): depth order = keys + 4 passes + scan,
+    # tile order = expand + 2 passes (<= 16 key bits) + offsets, generic sort = histogram + 6 passes
     KERNELS = {
         "projection_fwd": 1, "projection_bwd": 1, "projection_packed_count": 3, "projection_packed_fill": 1,
         "projection_packed_bwd": 1, "sh_fwd": 1, "sh_bwd": 1, "camera_centers": 1, "sh_colors_fwd": 1,
         "sh_colors_bwd": 1, "sh_colors_packed_fwd": 1, "sh_colors_packed_bwd": 1, "sh_colors_packed_split_fwd": 1,
-        "sh_colors_packed_split_bwd": 1, "isect_count": 2, "isect_fill": 1,
-        "isect_sort": 0, "isect_sorted": 5, "isect_depth_order": 3, "isect_tile_order": 2, "invert_4x4": 1, "copy_small": 1, "isect_offset_encode": 1, "rasterize_pack": 1, "rasterize_fwd": 1, "rasterize_bwd": 1,
+        "sh_colors_packed_split_bwd": 1, "isect_count": 1, "isect_fill": 1,
+        "isect_sort": 7, "isect_sorted": 10, "isect_depth_order": 6, "isect_tile_order": 4, "invert_4x4": 1, "copy_small": 1, "isect_offset_encode": 1, "rasterize_pack": 1, "rasterize_fwd": 1, "rasterize_bwd": 1,
         "raster_indices_count": 2, "raster_indices_fill": 1, "quat_scale_to_covar_preci_fwd": 1,
         "quat_scale_to_covar_preci_bwd": 1, "world_to_cam_fwd": 1, "world_to_cam_bwd": 1, "proj_fwd": 1, "proj_bwd": 1,
         "selective_adam_update": 1, "compute_relocation": 1, "sh_colors_staged_fwd": 1, "sh_colors_staged_bwd": 1,
@@ -928,10 +929,13 @@ def _isect_tiles_begin(
     cum_tiles = n_isects_dev = None
     side = ready = None
     if n_elems:
-        cum_tiles = torch.empty((n_elems,), device=dev, dtype=torch.int64)
         n_isects_dev = torch.empty((2,), device=dev, dtype=torch.int64)
-        ws_bytes = lib.b200splat_scan_workspace_bytes(n_elems)
-        ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
+        ws, ws_bytes = None, 0
+        if not depth_first:
+            # generic path: running sums in input order for isect_fill (CS/isect_tiles.cu:200)
+            cum_tiles = torch.empty((n_elems,), device=dev, dtype=torch.int64)
+            ws_bytes = lib.b200splat_scan_workspace_bytes(n_elems)
+            ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
         dws_bytes = 0
         if depth_first:
             dws_bytes = lib.b200splat_isect_depth_order_workspace_bytes(n_elems)
@@ -962,9 +966,13 @@ def _isect_tiles_begin(
                     join.record(side)
     else:
         pending = None
+        ws = None
+    # buffers touched by the first half stay referenced until finish() has joined it: with
+    # `concurrent` they are used on the side stream, which the caching allocator does not track
+    keep_alive = (ws, n_isects_dev, depth_ws)
 
     @torch.no_grad()
-    def finish():
+    def finish(_keep=keep_alive):
         n_isects, neg_depth = 0, False
         if pending is not None:
             n_isects, neg = pending()  # the one host sync (CS/isect_tiles.cu:201)
@@ -994,6 +1002,17 @@ def _isect_finish(lib, dev, packed, C, N, nnz, camera_ids, means2d, radii, depth
                    _ptr(depths), _ptr(depth_ws), depth_sel, n_isects, tile_size, tile_width, tile_height,
                    _ptr(isect_ids), _ptr(flatten_ids), _ptr(offsets), _ptr(ws), ws_bytes)
             return tiles_per_gauss, isect_ids, flatten_ids, offsets
+        if cum_tiles is None:
+            # the depth-first first half produced only the total; inputs outside its contract (depths
+            # with the sign bit set) fall back to fill + full-key sort, which needs the running sums
+            n_elems = nnz if packed else C * N
+            cum_tiles = torch.empty((n_elems,), device=dev, dtype=torch.int64)
+            ws_bytes = lib.b200splat_scan_workspace_bytes(n_elems)
+            ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
+            scratch = torch.empty((2,), device=dev, dtype=torch.int64)
+            native("isect_count", lib, dev, int(packed), C, N, nnz, _ptr(means2d), _ptr(radii), _ptr(depths),
+                   tile_size, tile_width, tile_height, _ptr(tiles_per_gauss), _ptr(cum_tiles), _ptr(scratch),
+                   _ptr(ws), ws_bytes)
         native("isect_fill", lib, dev, int(packed), C, N, nnz, _ptr(camera_ids), _ptr(means2d), _ptr(radii),
                _ptr(depths), _ptr(cum_tiles), tile_size, tile_width, tile_height, _ptr(isect_ids), _ptr(flatten_ids))
         if sort:
@@ -1043,7 +1062,7 @@ def isect_tiles_and_offsets(means2d, radii, depths, tile_size, tile_width, tile_
 
 @torch.no_grad()
 def isect_tiles_and_offsets_begin(means2d, radii, depths, tile_size, tile_width, tile_height, packed=False,
-                                  n_cameras=None, camera_ids=None, gaussian_ids=None, concurrent=True):
+                                  n_cameras=None, camera_ids=None, gaussian_ids=None, concurrent=False):
     """First half of `isect_tiles_and_offsets`; returns a callable producing its result.  What
     `rasterization()` queues between the two halves (the colour stage) runs concurrently with the
     count / depth-order phase when `concurrent`."""
