@@ -349,8 +349,8 @@ __device__ __forceinline__ void fisheye_proj_vjp(const V3 &p, const M3 &cov, con
 #define B2S_PI 3.14159265358979323846
 __device__ __forceinline__ M23 spherical_jac(const V3 &p, uint32_t W, uint32_t H, float r) {
     float x = p.x, y = p.y, z = p.z;
-    float xz_norm = sqrtf(x * x + z * z + 1e-8f);
-    float denom_xz = x * x + z * z + 1e-8f;
+    float denom_xz = fmaf(z, z, x * x) + 1e-8f;
+    float xz_norm = sqrtf(denom_xz);
     float denom_r2 = r * r + 1e-8f;
     M23 J;
     J.m[0][0] = (float)(W / (2 * B2S_PI) * (double)(z / denom_xz));
@@ -364,7 +364,7 @@ __device__ __forceinline__ M23 spherical_jac(const V3 &p, uint32_t W, uint32_t H
 __device__ __forceinline__ void spherical_proj(const V3 &p, const M3 &cov, uint32_t W, uint32_t H, M2 &cov2d,
                                                V2 &mean2d) {
     float x = p.x, y = p.y, z = p.z;
-    float r = sqrtf(x * x + y * y + z * z);
+    float r = sqrtf(fmaf(z, z, fmaf(y, y, x * x)));  // same contraction as the reference build (see project_one)
     float longitude = atan2f(x, z);
     float latitude = asinf(y / r);
     float normalized_latitude = (float)((double)latitude / (B2S_PI / 2.0));
@@ -403,7 +403,11 @@ __device__ __forceinline__ bool project_one(const V3 &mean, const M3 &covar, con
                                             int camera_model, bool packed_rules, ProjOut &o) {
     V3 pc = m3_mulv(cam.R, mean);
     pc.x += cam.t.x; pc.y += cam.t.y; pc.z += cam.t.z;
-    float rnorm = sqrtf(pc.x * pc.x + pc.y * pc.y + pc.z * pc.z);
+    // |mean_c| with the reference build's contraction, fma(z, z, fma(y, y, x·x)) (glm::length in
+    // CS/fully_fused_projection_fwd.cu:73-85, 204-209 as nvcc compiles it): the bits of this value are
+    // the depth half of the sort keys, and for the spherical model y/|mean_c| feeds asin, whose
+    // derivative near the poles turns one ulp into 1e-2 px
+    float rnorm = sqrtf(fmaf(pc.z, pc.z, fmaf(pc.y, pc.y, pc.x * pc.x)));
     if (camera_model != B200SPLAT_SPHERICAL) {
         if (pc.z < near_plane || pc.z > far_plane) return false;
     } else {
