@@ -315,6 +315,11 @@ B200SPLAT_API int b200splat_isect_offset_encode(
  * when the fast path does not apply: it needs tile_size == 16 and channels <= 4).  With
  * records the warp-per-tile kernels run (same results); without, the generic kernels.
  * The same table serves the forward and the backward call.
+ *
+ * `quad_masks` (optional, may be NULL; only used together with `records`): [n_isects] bytes of
+ * scratch.  The forward call stores, for every (tile, Gaussian) list entry it stages, which 8x8
+ * quads of the tile the Gaussian can reach with alpha >= 1/255; the backward call of the same
+ * (records, offsets, flatten_ids) reads them instead of repeating the exact rectangle test.
  * ---------------------------------------------------------------------------------- */
 B200SPLAT_API size_t b200splat_rasterize_records_bytes(uint32_t n_gauss, uint32_t channels, uint32_t tile_size);
 
@@ -330,7 +335,7 @@ B200SPLAT_API int b200splat_rasterize_fwd(
     uint32_t image_width, uint32_t image_height,
     uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
     const int32_t *tile_offsets, const int32_t *flatten_ids,
-    const void *records,
+    const void *records, uint8_t *quad_masks,
     float *render_colors, float *render_alphas, int32_t *last_ids,
     void *stream);
 
@@ -345,7 +350,7 @@ B200SPLAT_API int b200splat_rasterize_bwd(
     uint32_t image_width, uint32_t image_height,
     uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
     const int32_t *tile_offsets, const int32_t *flatten_ids,
-    const void *records,
+    const void *records, const uint8_t *quad_masks,
     const float *render_alphas, const int32_t *last_ids,
     const float *v_render_colors, const float *v_render_alphas,
     float *v_means2d_abs, float *v_means2d, float *v_conics, float *v_colors,

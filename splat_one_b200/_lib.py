@@ -68,10 +68,10 @@ SIGNATURES = {
     "b200splat_rasterize_records_bytes": (c_size_t, [_U32, _U32, _U32]),
     "b200splat_rasterize_pack": (_I, [_U32, _U32, _P, _P, _P, _P, _P, _P]),
     "b200splat_rasterize_fwd": (
-        _I, [_U32, _U32, _U64, _U32, _P, _P, _P, _P, _P, _P, _U32, _U32, _U32, _U32, _U32, _P, _P, _P,
+        _I, [_U32, _U32, _U64, _U32, _P, _P, _P, _P, _P, _P, _U32, _U32, _U32, _U32, _U32, _P, _P, _P, _P,
              _P, _P, _P, _P]),
     "b200splat_rasterize_bwd": (
-        _I, [_U32, _U32, _U64, _U32, _P, _P, _P, _P, _P, _P, _U32, _U32, _U32, _U32, _U32, _P, _P, _P,
+        _I, [_U32, _U32, _U64, _U32, _P, _P, _P, _P, _P, _P, _U32, _U32, _U32, _U32, _U32, _P, _P, _P, _P,
              _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "b200splat_raster_indices_count": (
         _I, [_U32, _U32, _U32, _U32, _U64, _P, _P, _P, _U32, _U32, _U32, _U32, _U32, _P, _P, _P, _P, _P, _P, _P,

@@ -47,11 +47,16 @@ def _deps_mtime() -> float:
     return max(p.stat().st_mtime for p in hdrs)
 
 
+def _flags():
+    # B200SPLAT_TUNING=1: also compile the A/B kernel variants selected by B200SPLAT_TUNING_VARIANT
+    return NVCC_FLAGS + (["-DB2S_TUNING"] if os.environ.get("B200SPLAT_TUNING", "0") == "1" else [])
+
+
 def _compile(src: Path, force: bool, verbose: bool) -> Path:
     obj = OBJ / (src.stem + ".o")
     if not force and obj.exists() and obj.stat().st_mtime >= max(src.stat().st_mtime, _deps_mtime()):
         return obj
-    cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+    cmd = [_nvcc(), *_flags(), "-c", str(src), "-o", str(obj)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     (OBJ / (src.stem + ".ptxas.log")).write_text(r.stderr)
     if r.returncode != 0:

@@ -3,6 +3,11 @@
 
 namespace b2s {
 
+const int g_tuning_variant = [] {
+    const char *e = getenv("B200SPLAT_TUNING_VARIANT");
+    return e ? atoi(e) : 0;
+}();
+
 std::string &last_error() {
     static thread_local std::string e;
     return e;

@@ -30,11 +30,11 @@ int fail_cuda(const char *where, cudaError_t e);
         if (!(cond)) return b2s::fail(where, msg);                                      \
     } while (0)
 
-// Developer A/B switch for kernel variants (tools/raster_bench.py); 0 = the shipped default.
-static inline int tuning_variant() {
-    const char *e = getenv("B200SPLAT_TUNING_VARIANT");
-    return e ? atoi(e) : 0;
-}
+// Developer A/B switch for kernel variants (tools/raster_bench.py); 0 = the shipped default.  The
+// environment variable is read ONCE, when the library is loaded (capi.cu); the alternative
+// instances are only compiled into builds made with B200SPLAT_TUNING=1 (-DB2S_TUNING).
+extern const int g_tuning_variant;
+static inline int tuning_variant() { return g_tuning_variant; }
 
 static inline unsigned div_up(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
 

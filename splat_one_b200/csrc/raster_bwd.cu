@@ -56,66 +56,13 @@ __device__ __forceinline__ void warp_reduce_commit(const float *v, const unsigne
     if constexpr (OFF + CH < NV) warp_reduce_commit<NV, OFF + CH>(v, lane, commit);
 }
 
-// Branch-free commit for the quad kernels: the NV per-pair values are reduced in two chunks
-// (values 0..7 with an 8-wide reduce-scatter, which leaves value i in lanes 4i..4i+3, and the
-// remaining R = NV - 8 values with a P1-wide one, value 8+i in lanes (32/P1)·i ..), and every
-// value is handed to ONE lane chosen so that no lane gets two: chunk 0 commits from lanes 4i,
-// chunk 1 from lanes (32/P1)·i + 1.  Each lane resolves its destination array once, before
-// the loop over Gaussians; the per-pair commit is then a single predicated RED.
-template <int NV>
-struct GradSink {
-    static constexpr int N0 = NV < 8 ? NV : 8;
-    static constexpr int R = NV - N0;
-    static constexpr int P1 = next_pow2(R);
-    float *base;       // nullptr: this lane commits nothing
-    uint32_t stride;   // floats per Gaussian row of the destination array
-    bool from_chunk1;
-
-    template <int CDIM>
-    __device__ __forceinline__ void init(unsigned lane, uint32_t channels, float *v_colors, float *v_conics,
-                                         float *v_means2d, float *v_opacities, float *v_means2d_abs) {
-        int k = -1;
-        from_chunk1 = false;
-        if ((lane & 3) == 0) {
-            if ((int)(lane >> 2) < N0) k = (int)(lane >> 2);
-        } else if (R > 0 && (lane % (32 / P1)) == 1) {
-            const int i = (int)(lane / (32 / P1));
-            if (i < R) { k = 8 + i; from_chunk1 = true; }
-        }
-        base = nullptr;
-        stride = 0;
-        if (k < 0) return;
-        if (k < CDIM) {
-            if (k < (int)channels) { base = v_colors + k; stride = channels; }
-        } else if (k < CDIM + 3) { base = v_conics + (k - CDIM); stride = 3; }
-        else if (k < CDIM + 5) { base = v_means2d + (k - CDIM - 3); stride = 2; }
-        else if (k == CDIM + 5) { base = v_opacities; stride = 1; }
-        else { base = v_means2d_abs + (k - CDIM - 6); stride = 2; }
-    }
-
-    __device__ __forceinline__ void commit(const float (&v)[NV], unsigned lane, int32_t g) const {
-        float w0[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) w0[i] = (i < N0) ? v[i] : 0.f;
-        float val = warp_reduce_scatter<8>(w0, lane);
-        if (R > 0) {
-            float w1[P1];
-#pragma unroll
-            for (int i = 0; i < P1; ++i) w1[i] = (i < R) ? v[8 + i] : 0.f;
-            const float r1 = warp_reduce_scatter<P1>(w1, lane);
-            val = from_chunk1 ? r1 : val;
-        }
-        if (base != nullptr) atomicAdd(base + (size_t)g * stride, val);
-    }
-};
-
-// Shared-memory variant of the commit.  The butterfly above is a chain of 5 dependent SHFL
-// stages per pair (ncu: ~10 % of the kernel's stall samples are FADDs waiting on a shuffle).
-// Here every lane parks its NV partial values in shared memory (row (slot, k), 32 lanes wide,
-// rows padded to 36 floats so that the 128-bit row reads below are conflict-free); once
-// SLOTS = 32 / NV pairs are parked, lane l sums row l with eight LDS.128 and issues ONE RED:
-// no shuffles, ~26 instead of ~46 warp instructions per pair, and the sums of a flush are
-// independent of the compositing chain of the following pairs.
+// Commit of the quad kernels.  Every lane parks its NV partial values in shared memory (row (slot, k),
+// 32 lanes wide, rows padded to 36 floats so that the 128-bit row reads below are conflict-free); once
+// SLOTS = 32 / NV pairs are parked, lane l sums row l with eight LDS.128 and issues ONE RED: no
+// shuffles (a reduce-scatter butterfly is a chain of 5 dependent SHFL stages per pair: ~10 % of the
+// stall samples in ncu r1_d), and the sums of a flush are independent of the compositing chain of the
+// following pairs.  The parked values are the NEGATED gradients (the kernel accumulates with negated
+// opacity / colours, raster_quad.cuh); the sign is restored by the one subtraction of the flush.
 template <int NV>
 struct SmemSink {
     static constexpr int SLOTS = 32 / NV;
@@ -155,16 +102,17 @@ struct SmemSink {
             const float s2 = (e.x + e.y) + (e.z + e.w) + ((f.x + f.y) + (f.z + f.w));
             const float s3 = (g4.x + g4.y) + (g4.z + g4.w) + ((h.x + h.y) + (h.z + h.w));
             const int g = gid[my_slot];
-            if (base != nullptr) atomicAdd(base + (size_t)g * stride, (s0 + s1) + (s2 + s3));
+            if (base != nullptr) atomicAdd(base + (size_t)g * stride, -(s0 + s1) - (s2 + s3));
         }
         __syncwarp();
         cnt = 0;
     }
 
-    __device__ __forceinline__ void commit(const float (&v)[NV], unsigned lane, int32_t g) {
+    // nv: NEGATED per-lane partial gradients of one (tile, Gaussian) pair
+    __device__ __forceinline__ void commit(const float (&nv)[NV], unsigned lane, int32_t g) {
         float *row = buf + (cnt * NV) * ROW + lane;
 #pragma unroll
-        for (int k = 0; k < NV; ++k) row[k * ROW] = v[k];
+        for (int k = 0; k < NV; ++k) row[k * ROW] = nv[k];
         if (lane == 0) gid[cnt] = g;
         if (++cnt == SLOTS) flush(lane);
     }
@@ -339,13 +287,13 @@ static void launch_bwd(uint32_t C, uint64_t n_isects, uint32_t channels, const f
 
 
 // ---------------------------------------------------------------------------------------
-// quad kernels: warp-per-tile (or per half tile), 8x8 quads, packed fp32x2 (raster_quad.cuh).
+// quad kernels: warp-per-tile, 8x8 quads, packed fp32x2 (raster_quad.cuh).
 // Per (tile, Gaussian): each lane folds its pixels into CDIM colour sums and, per column
 // half (dx is shared by the pixels of a half), the moments
 //   W0 = sum v_sigma,  W1 = sum v_sigma·dy,  W2 = sum v_sigma·dy²
-// converts them to the 9 gradient values, and ONE reduce-scatter butterfly + one RED per
-// value commits them.  Everything is accumulated NEGATED (the record carries -opacity and
-// -colour, raster_quad.cuh) and the sign is restored once per pair.
+// converts them to the 9 gradient values and parks them in shared memory (SmemSink).
+// Everything is accumulated NEGATED (the record carries -opacity and -colour, raster_quad.cuh)
+// and the sign is restored once, in the flush.
 // ---------------------------------------------------------------------------------------
 struct BwdAcc {
     float2 nW0, nW1, nW2;  // negated moments of one column half, one entry per pixel row pair
@@ -354,7 +302,10 @@ struct BwdAcc {
 // One Gaussian against one quad.  State per pixel: T, ntb = -(T_final (v_alpha_out - bg·v_c) -
 // sum_k buffer_k v_c_k), which folds the reference's per-channel `buffer`
 // (CS/rasterize_to_pixels_bwd.cu:203-241): v_alpha only ever needs that dot product.
-template <int CDIM, bool ABS, bool SIGN>
+// SLOW: pair flagged kNonPD (raster_quad.cuh) — the `sigma < 0` rejection and the 0.999 clamp of alpha
+// (with its `opac·vis <= 0.999` gradient gate, :221) are applied literally; for every other pair neither
+// can fire: alpha = opac·vis itself, and v_sigma = -alpha·v_alpha needs no gate.
+template <int CDIM, bool ABS, bool SLOW>
 __device__ __forceinline__ bool bwd_quad(float2 &T2, float2 &ntb2, const float2 (&v_c2)[CDIM], const int32_t (&binf)[2],
                                          float2 (&nvacc2)[CDIM], BwdAcc &acc, float2 &abs2x, float2 &abs2y,
                                          const float2 dy2, const float2 ndy2, const float dx, const float hA,
@@ -363,9 +314,9 @@ __device__ __forceinline__ bool bwd_quad(float2 &T2, float2 &ntb2, const float2 
     const float2 u2 = __ffma2_rn(bc2(hC), dy2, bc2(B));
     const float2 ns2 = __ffma2_rn(ndy2, u2, bc2(nA));  // -sigma'
     const float2 nov2 = __fmul2_rn(bc2(nopac), make_float2(ex2_approx(ns2.x), ex2_approx(ns2.y)));  // -opac·vis
-    const float nal0 = fmaxf(-kAlphaMax, nov2.x), nal1 = fmaxf(-kAlphaMax, nov2.y);  // -alpha
+    const float nal0 = SLOW ? fmaxf(-kAlphaMax, nov2.x) : nov2.x, nal1 = SLOW ? fmaxf(-kAlphaMax, nov2.y) : nov2.y;  // -alpha
     bool ok0 = (nal0 <= -kAlphaMin) && (idx <= binf[0]), ok1 = (nal1 <= -kAlphaMin) && (idx <= binf[1]);
-    if (SIGN) { ok0 = ok0 && !(ns2.x > 0.f); ok1 = ok1 && !(ns2.y > 0.f); }
+    if (SLOW) { ok0 = ok0 && !(ns2.x > 0.f); ok1 = ok1 && !(ns2.y > 0.f); }
     // a rejected pixel runs with alpha = 0: ra = 1, fac = 0, v_sigma = 0
     const float2 nae2 = make_float2(ok0 ? nal0 : 0.f, ok1 ? nal1 : 0.f);
     const float2 om2 = __fadd2_rn(nae2, bc2(1.f));
@@ -380,9 +331,14 @@ __device__ __forceinline__ bool bwd_quad(float2 &T2, float2 &ntb2, const float2 
     }
     const float2 nv_alpha2 = __ffma2_rn(T2, ncv2, __fmul2_rn(ra2, ntb2));  // -v_alpha
     ntb2 = __ffma2_rn(nfac2, ncv2, ntb2);
-    float2 nvs2 = __fmul2_rn(nov2, nv_alpha2);  // ov·v_alpha = -v_sigma
-    nvs2.x = (ok0 && nov2.x >= -kAlphaMax) ? nvs2.x : 0.f;
-    nvs2.y = (ok1 && nov2.y >= -kAlphaMax) ? nvs2.y : 0.f;
+    float2 nvs2;  // ov·v_alpha = -v_sigma
+    if (SLOW) {
+        nvs2 = __fmul2_rn(nov2, nv_alpha2);
+        nvs2.x = (ok0 && nov2.x >= -kAlphaMax) ? nvs2.x : 0.f;
+        nvs2.y = (ok1 && nov2.y >= -kAlphaMax) ? nvs2.y : 0.f;
+    } else {
+        nvs2 = __fmul2_rn(nae2, nv_alpha2);  // alpha is unclamped and already 0 for a rejected pixel
+    }
     const float2 nwy2 = __fmul2_rn(nvs2, dy2);
     acc.nW0 = __fadd2_rn(acc.nW0, nvs2);
     acc.nW1 = __fadd2_rn(acc.nW1, nwy2);
@@ -397,36 +353,37 @@ __device__ __forceinline__ bool bwd_quad(float2 &T2, float2 &ntb2, const float2 
     return ok0 || ok1;
 }
 
-template <int CDIM, bool ABS, int NQ, int MINB, int JOINT, int SINK, int ASYNC>
-__global__ void __launch_bounds__(32 * (4 / NQ), MINB)
+// `quad_masks` (optional): the per-pair quad masks stored by the forward kernel; when given, staging is
+// a byte load instead of the exact rectangle test of quad_mask.
+template <int CDIM, bool ABS, int MINB>
+__global__ void __launch_bounds__(32, MINB)
 raster_bwd_quad_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channels, const float4 *__restrict__ rec,
                        const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks, uint32_t W,
                        uint32_t H, uint32_t tile_width, uint32_t tile_height,
                        const int32_t *__restrict__ tile_offsets, const int32_t *__restrict__ flatten_ids,
+                       const uint8_t *__restrict__ quad_masks,
                        const float *__restrict__ render_alphas, const int32_t *__restrict__ last_ids,
                        const float *__restrict__ v_render_colors, const float *__restrict__ v_render_alphas,
                        float *__restrict__ v_means2d_abs, float *__restrict__ v_means2d, float *__restrict__ v_conics,
                        float *__restrict__ v_colors, float *__restrict__ v_opacities) {
     constexpr int NV = CDIM + 6 + (ABS ? 2 : 0);
-    constexpr int NW = 4 / NQ;    // warps per CTA; each works on its own (no block-level sync)
-    constexpr int NQY = NQ / 2;   // quad rows per warp
-    __shared__ float4 s_rec_all[NW][32 * 3];
-    __shared__ int4 s_im_all[NW][32];  // {sorted index, quad mask, Gaussian row, -}
+    constexpr int NQ = 4;         // one warp owns the whole tile
+    constexpr int NQY = NQ / 2;   // quad rows
+    __shared__ float4 s_rec[32 * 3];
+    __shared__ int4 s_im[32];  // {sorted index, quad mask, Gaussian row, -}
     using SSink = SmemSink<NV>;
-    __shared__ __align__(16) float s_red_all[SINK ? NW : 1][SINK ? SSink::FLOATS : 4];
-    __shared__ int s_gid_all[SINK ? NW : 1][SINK ? SSink::SLOTS : 1];
-    __shared__ float4 s_pre_all[ASYNC ? NW : 1][ASYNC ? 32 * 3 : 1];  // records of the batch in flight
-    const unsigned lane = threadIdx.x & 31, sub = threadIdx.x >> 5;
-    float4 *s_rec = s_rec_all[sub];
-    int4 *s_im = s_im_all[sub];
-    const float4 *s_pre = s_pre_all[ASYNC ? sub : 0] + (ASYNC ? 3 * lane : 0);
+    __shared__ __align__(16) float s_red[SSink::FLOATS];
+    __shared__ int s_gid[SSink::SLOTS];
+    __shared__ float4 s_pre_all[32 * 3];  // records of the batch in flight
+    const unsigned lane = threadIdx.x & 31;
+    const float4 *s_pre = s_pre_all + 3 * lane;
     const uint32_t pre_addr = (uint32_t)__cvta_generic_to_shared(s_pre);
     const uint32_t tile_lin = blockIdx.x;
     if (masks != nullptr && !masks[tile_lin]) return;
     const int32_t range_start = tile_offsets[tile_lin];
     const int32_t range_end = (tile_lin == n_tiles_total - 1) ? (int32_t)n_isects : tile_offsets[tile_lin + 1];
     if (range_end <= range_start) return;
-    const QuadTile tc = quad_tile<NQ>(tile_lin, tile_width, tile_height, lane, sub);
+    const QuadTile tc = quad_tile<NQ>(tile_lin, tile_width, tile_height, lane, 0);
     const size_t cam_pix = (size_t)tc.cam * H * W;
 
     float2 T2[NQ], ntb2[NQ], v_c2[NQ][CDIM];
@@ -476,19 +433,17 @@ raster_bwd_quad_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t chann
     }
     const float pxa = tc.px, pxb = tc.px + 8.f;
 
-    GradSink<NV> sink;
     SSink ssink;
-    if (SINK) ssink.template init<CDIM>(lane, channels, v_colors, v_conics, v_means2d, v_opacities, v_means2d_abs,
-                                        s_red_all[SINK ? sub : 0], s_gid_all[SINK ? sub : 0]);
-    else sink.template init<CDIM>(lane, channels, v_colors, v_conics, v_means2d, v_opacities, v_means2d_abs);
+    ssink.template init<CDIM>(lane, channels, v_colors, v_conics, v_means2d, v_opacities, v_means2d_abs, s_red, s_gid);
 
-    // record prefetch one batch ahead (ASYNC: straight into shared memory), sorted id two ahead
-    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
+    // record (and stored quad mask) prefetch one batch ahead, the record straight into shared memory;
+    // sorted id two batches ahead
     int32_t my_idx = hi0 - (int32_t)lane, my_g = 0, g_next = 0;
+    uint32_t qm_next = 0;
     if (my_idx >= range_start) {
         my_g = flatten_ids[my_idx];
-        if (ASYNC) prefetch_record(pre_addr, rec, my_g);
-        else { r0 = __ldg(rec + 3 * (size_t)my_g); r1 = __ldg(rec + 3 * (size_t)my_g + 1); r2 = __ldg(rec + 3 * (size_t)my_g + 2); }
+        prefetch_record(pre_addr, rec, my_g);
+        if (quad_masks != nullptr) qm_next = quad_masks[my_idx];
     }
     if (my_idx - 32 >= range_start) g_next = flatten_ids[my_idx - 32];
     uint32_t act = 0;  // warp-uniform: quads with a pixel whose last contributor is inside the batches seen so far
@@ -498,10 +453,13 @@ raster_bwd_quad_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t chann
         for (int q = 0; q < NQ; ++q)
             if (!(act >> q & 1) && __any_sync(0xffffffffu, max(binf[q][0], binf[q][1]) >= lo)) act |= 1u << q;
         uint32_t my_mask = 0;
-        if (ASYNC) cp_async_wait_all();
+        float4 r0, r1, r2;
+        cp_async_wait_all();
         if (my_idx >= range_start) {
-            if (ASYNC) { r0 = s_pre[0]; r1 = s_pre[1]; r2 = s_pre[2]; }
-            my_mask = quad_mask<NQ>(r0.x, r0.y, r0.z, r0.w, r1.x, r2.z, tc.ox, tc.oy, W, H);
+            r0 = s_pre[0]; r1 = s_pre[1]; r2 = s_pre[2];
+            my_mask = quad_masks != nullptr
+                          ? unpack_quad_mask((uint8_t)qm_next)
+                          : quad_mask<NQ>(r0.x, r0.y, r0.z, r0.w, r1.x, r2.z, r1.y, tc.ox, tc.oy, W, H);
             if ((my_mask & act) == 0) my_mask = 0; else my_mask &= (act | kNonPD);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, my_mask != 0);
@@ -517,8 +475,8 @@ raster_bwd_quad_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t chann
         my_idx = hi - 32 - (int32_t)lane;
         if (my_idx >= range_start) {
             my_g = g_next;
-            if (ASYNC) prefetch_record(pre_addr, rec, my_g);
-            else { r0 = __ldg(rec + 3 * (size_t)my_g); r1 = __ldg(rec + 3 * (size_t)my_g + 1); r2 = __ldg(rec + 3 * (size_t)my_g + 2); }
+            prefetch_record(pre_addr, rec, my_g);
+            if (quad_masks != nullptr) qm_next = quad_masks[my_idx];
         }
         if (my_idx - 32 >= range_start) g_next = flatten_ids[my_idx - 32];
         for (int t = 0; t < n; ++t) {
@@ -543,20 +501,14 @@ raster_bwd_quad_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t chann
             acc[0].nW0 = acc[0].nW1 = acc[0].nW2 = acc[1].nW0 = acc[1].nW1 = acc[1].nW2 = make_float2(0.f, 0.f);
             float2 abs2x = make_float2(0.f, 0.f), abs2y = abs2x;
             bool hit = false;
-#define B2S_BQ(SIGN_, q_)                                                                                            \
-    hit |= bwd_quad<CDIM, ABS, SIGN_>(T2[q_], ntb2[q_], v_c2[q_], binf[q_], nvacc2, acc[(q_) & 1], abs2x, abs2y,        \
+#define B2S_BQ(SLOW_, q_)                                                                                            \
+    hit |= bwd_quad<CDIM, ABS, SLOW_>(T2[q_], ntb2[q_], v_c2[q_], binf[q_], nvacc2, acc[(q_) & 1], abs2x, abs2y,        \
                                       dy2[(q_) >> 1], ndy2[(q_) >> 1], ((q_) & 1) ? dxb : dxa, hA, cb,                 \
                                       ((q_) & 1) ? nAb : nAa, ((q_) & 1) ? Bb : Ba, hC, nopac, ncol, idx)
             if (m & kNonPD) {
 #pragma unroll
                 for (int q = 0; q < NQ; ++q)
                     if (m >> q & 1) B2S_BQ(true, q);  // warp-uniform
-            } else if (JOINT == 0) {
-#pragma unroll
-                for (int q = 0; q < NQ; ++q)
-                    if (m >> q & 1) B2S_BQ(false, q);  // warp-uniform
-            } else if (JOINT == 2 && NQ == 4 && (m & 0xFu) == 0xFu) {
-                B2S_BQ(false, 0); B2S_BQ(false, 1); B2S_BQ(false, 2); B2S_BQ(false, 3);
             } else {
                 // both quads of a quad row in one basic block when both are reached (ILP 2)
 #pragma unroll
@@ -568,55 +520,55 @@ raster_bwd_quad_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t chann
                 }
             }
 #undef B2S_BQ
-            if (SINK != 2 && !__any_sync(0xffffffffu, hit)) continue;  // SINK 2: commit unconditionally
-            // negated moments -> gradients (conic entries in the record are scaled by log2 e)
-            float v[NV];
+            if (!__any_sync(0xffffffffu, hit)) continue;
+            // negated moments -> NEGATED gradients (conic entries in the record are scaled by log2 e);
+            // the flush restores the sign
+            float nv[NV];
 #pragma unroll
-            for (int k = 0; k < CDIM; ++k) v[k] = -(nvacc2[k].x + nvacc2[k].y);
-            const float W0a = -(acc[0].nW0.x + acc[0].nW0.y), W0b = -(acc[1].nW0.x + acc[1].nW0.y);
-            const float W1a = -(acc[0].nW1.x + acc[0].nW1.y), W1b = -(acc[1].nW1.x + acc[1].nW1.y);
-            const float W2s = -((acc[0].nW2.x + acc[0].nW2.y) + (acc[1].nW2.x + acc[1].nW2.y));
-            const float ua = dxa * W0a, ub = dxb * W0b;
-            const float S1x = ua + ub, S1y = W1a + W1b;
-            v[CDIM + 0] = 0.5f * fmaf(dxa, ua, dxb * ub);                 // 1/2 sum v_sigma dx²
-            v[CDIM + 1] = fmaf(dxa, W1a, dxb * W1b);                      // sum v_sigma dx dy
-            v[CDIM + 2] = 0.5f * W2s;                                     // 1/2 sum v_sigma dy²
-            v[CDIM + 3] = kInvLog2e * fmaf(2.f * hA, S1x, cb * S1y);      // sum v_sigma (a dx + b dy)
-            v[CDIM + 4] = kInvLog2e * fmaf(cb, S1x, 2.f * hC * S1y);      // sum v_sigma (b dx + c dy)
-            v[CDIM + 5] = (W0a + W0b) * rcp_approx(nopac);                // sum vis·v_alpha = -S0 / opac
+            for (int k = 0; k < CDIM; ++k) nv[k] = nvacc2[k].x + nvacc2[k].y;
+            const float nW0a = acc[0].nW0.x + acc[0].nW0.y, nW0b = acc[1].nW0.x + acc[1].nW0.y;
+            const float nW1a = acc[0].nW1.x + acc[0].nW1.y, nW1b = acc[1].nW1.x + acc[1].nW1.y;
+            const float nW2s = (acc[0].nW2.x + acc[0].nW2.y) + (acc[1].nW2.x + acc[1].nW2.y);
+            const float nua = dxa * nW0a, nub = dxb * nW0b;
+            const float nS1x = nua + nub, nS1y = nW1a + nW1b;
+            nv[CDIM + 0] = 0.5f * fmaf(dxa, nua, dxb * nub);               // 1/2 sum v_sigma dx²
+            nv[CDIM + 1] = fmaf(dxa, nW1a, dxb * nW1b);                    // sum v_sigma dx dy
+            nv[CDIM + 2] = 0.5f * nW2s;                                    // 1/2 sum v_sigma dy²
+            nv[CDIM + 3] = kInvLog2e * fmaf(2.f * hA, nS1x, cb * nS1y);    // sum v_sigma (a dx + b dy)
+            nv[CDIM + 4] = kInvLog2e * fmaf(cb, nS1x, 2.f * hC * nS1y);    // sum v_sigma (b dx + c dy)
+            nv[CDIM + 5] = (nW0a + nW0b) * rcp_approx(nopac);              // sum vis·v_alpha = -S0 / opac
             if (ABS) {
-                v[CDIM + 6] = kInvLog2e * (abs2x.x + abs2x.y);
-                v[CDIM + 7] = kInvLog2e * (abs2y.x + abs2y.y);
+                nv[CDIM + 6] = -kInvLog2e * (abs2x.x + abs2x.y);
+                nv[CDIM + 7] = -kInvLog2e * (abs2y.x + abs2y.y);
             }
-            if (SINK) ssink.commit(v, lane, im.z);
-            else sink.commit(v, lane, im.z);
+            ssink.commit(nv, lane, im.z);
         }
     }
-    if (SINK) ssink.finish(lane);
+    ssink.finish(lane);
 }
 
 template <int CDIM, bool ABS>
 static void launch_bwd_quad(uint32_t C, uint64_t n_isects, uint32_t channels, const float4 *rec,
                             const float *backgrounds, const uint8_t *masks, uint32_t W, uint32_t H,
                             uint32_t tile_width, uint32_t tile_height, const int32_t *tile_offsets,
-                            const int32_t *flatten_ids, const float *render_alphas, const int32_t *last_ids,
-                            const float *v_render_colors, const float *v_render_alphas, float *v_means2d_abs,
-                            float *v_means2d, float *v_conics, float *v_colors, float *v_opacities, cudaStream_t st) {
+                            const int32_t *flatten_ids, const uint8_t *quad_masks, const float *render_alphas,
+                            const int32_t *last_ids, const float *v_render_colors, const float *v_render_alphas,
+                            float *v_means2d_abs, float *v_means2d, float *v_conics, float *v_colors,
+                            float *v_opacities, cudaStream_t st) {
     const uint32_t total = C * tile_width * tile_height;
-#define B2S_BWDQ(NQ_, MINB_, J_, S_, A_)                                                                             \
-    raster_bwd_quad_kernel<CDIM, ABS, NQ_, MINB_, J_, S_, A_><<<total, 32 * (4 / NQ_), 0, st>>>(                      \
+#define B2S_BWDQ(MINB_)                                                                                              \
+    raster_bwd_quad_kernel<CDIM, ABS, MINB_><<<total, 32, 0, st>>>(                                                   \
         total, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, \
-        render_alphas, last_ids, v_render_colors, v_render_alphas, v_means2d_abs, v_means2d, v_conics, v_colors,     \
-        v_opacities)
+        quad_masks, render_alphas, last_ids, v_render_colors, v_render_alphas, v_means2d_abs, v_means2d, v_conics,    \
+        v_colors, v_opacities)
+#ifdef B2S_TUNING
     switch (tuning_variant()) {
-        case 1: B2S_BWDQ(4, 16, 1, 0, 0); break;   // butterfly commit, register prefetch (r1_c default)
-        case 2: B2S_BWDQ(2, 10, 1, 1, 1); break;   // two warps per tile (upper / lower half), 96 registers
-        case 6: B2S_BWDQ(2, 12, 1, 1, 1); break;   // same, 80 registers
-        case 3: B2S_BWDQ(4, 16, 1, 1, 0); break;   // shared-memory commit, register prefetch
-        case 4: B2S_BWDQ(4, 16, 1, 2, 1); break;   // as default, without the per-pair hit vote
-        case 5: B2S_BWDQ(4, 18, 1, 1, 1); break;   // same, 112 registers
-        default: B2S_BWDQ(4, 16, 1, 1, 1); break;  // shared-memory commit + cp.async prefetch: 0.552 ms vs 0.613 (variant 1)
+        case 1: B2S_BWDQ(18); return;   // 112 registers
+        case 2: B2S_BWDQ(20); return;   // 96 registers
+        default: break;
     }
+#endif
+    B2S_BWDQ(16);
 #undef B2S_BWDQ
 }
 
@@ -629,7 +581,7 @@ extern "C" int b200splat_rasterize_bwd(uint32_t C, uint32_t n_gauss, uint64_t n_
                                        const float *opacities, const float *backgrounds, const uint8_t *masks,
                                        uint32_t W, uint32_t H, uint32_t tile_size, uint32_t tile_width,
                                        uint32_t tile_height, const int32_t *tile_offsets, const int32_t *flatten_ids,
-                                       const void *records,
+                                       const void *records, const uint8_t *quad_masks,
                                        const float *render_alphas, const int32_t *last_ids,
                                        const float *v_render_colors, const float *v_render_alphas,
                                        float *v_means2d_abs, float *v_means2d, float *v_conics, float *v_colors,
@@ -648,11 +600,11 @@ extern "C" int b200splat_rasterize_bwd(uint32_t C, uint32_t n_gauss, uint64_t n_
     case D:                                                                                                            \
         if (ab)                                                                                                        \
             launch_bwd_quad<D, true>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height,      \
-                                   tile_offsets, flatten_ids, render_alphas, last_ids, v_render_colors,                \
+                                   tile_offsets, flatten_ids, quad_masks, render_alphas, last_ids, v_render_colors,    \
                                    v_render_alphas, v_means2d_abs, v_means2d, v_conics, v_colors, v_opacities, st2);   \
         else                                                                                                           \
             launch_bwd_quad<D, false>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height,     \
-                                    tile_offsets, flatten_ids, render_alphas, last_ids, v_render_colors,               \
+                                    tile_offsets, flatten_ids, quad_masks, render_alphas, last_ids, v_render_colors,   \
                                     v_render_alphas, v_means2d_abs, v_means2d, v_conics, v_colors, v_opacities, st2);  \
         break;
         switch (channels) { B2S_BWD2(1) B2S_BWD2(2) B2S_BWD2(3) B2S_BWD2(4) }

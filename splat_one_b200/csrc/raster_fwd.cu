@@ -152,19 +152,19 @@ static int launch_fwd(uint32_t C, uint64_t n_isects, uint32_t channels, const fl
 // quad kernels: warp-per-tile (or per half tile), 8x8 quads, packed fp32x2 (raster_quad.cuh)
 // ---------------------------------------------------------------------------------------
 // One Gaussian against one quad: the lane's two pixels (rows v and v + 4 of the quad).
-// SIGN: the conic is not positive definite, so sigma may be negative and is tested like the
-// reference does (CS/rasterize_to_pixels_fwd.cu:147); for a positive definite conic the
-// test can never fire and is compiled out.
-template <int CDIM, bool SIGN>
+// SLOW: the pair is flagged kNonPD (raster_quad.cuh): sigma may be negative and is tested like the
+// reference does (CS/rasterize_to_pixels_fwd.cu:147), and alpha may reach the 0.999 clamp (:146).
+// For every other pair neither rule can fire and both are compiled out.
+template <int CDIM, bool SLOW>
 __device__ __forceinline__ void fwd_quad(float2 &T2, float2 (&pix2)[CDIM], int32_t (&cur)[2], const float2 dy2,
                                          const float2 ndy2, const float nA, const float B, const float hC,
                                          const float nopac, const float (&ncol)[4], const int32_t idx) {
     const float2 u2 = __ffma2_rn(bc2(hC), dy2, bc2(B));
     const float2 ns2 = __ffma2_rn(ndy2, u2, bc2(nA));  // -sigma'
     const float2 nov2 = __fmul2_rn(bc2(nopac), make_float2(ex2_approx(ns2.x), ex2_approx(ns2.y)));
-    const float nal0 = fmaxf(-kAlphaMax, nov2.x), nal1 = fmaxf(-kAlphaMax, nov2.y);  // -alpha
+    const float nal0 = SLOW ? fmaxf(-kAlphaMax, nov2.x) : nov2.x, nal1 = SLOW ? fmaxf(-kAlphaMax, nov2.y) : nov2.y;  // -alpha
     bool ok0 = nal0 <= -kAlphaMin, ok1 = nal1 <= -kAlphaMin;
-    if (SIGN) { ok0 = ok0 && !(ns2.x > 0.f); ok1 = ok1 && !(ns2.y > 0.f); }
+    if (SLOW) { ok0 = ok0 && !(ns2.x > 0.f); ok1 = ok1 && !(ns2.y > 0.f); }
     const float2 nae2 = make_float2(ok0 ? nal0 : 0.f, ok1 ? nal1 : 0.f);
     const float2 next_T2 = __fmul2_rn(T2, __fadd2_rn(nae2, bc2(1.f)));  // == T exactly when rejected
     // exclusive stop; also fires for a dead pixel (T < 0), which therefore composites nothing
@@ -179,26 +179,26 @@ __device__ __forceinline__ void fwd_quad(float2 &T2, float2 (&pix2)[CDIM], int32
     T2.y = st1 ? fminf(T2.y, -T2.y) : next_T2.y;
 }
 
-template <int CDIM, int NQ, int MINB, int JOINT, int ASYNC>
-__global__ void __launch_bounds__(32 * (4 / NQ), MINB)
+// `quad_masks` (optional, [n_isects] bytes): the geometric quad mask of every pair this kernel stages is
+// stored for the backward kernel (raster_quad.cuh pack_quad_mask).
+template <int CDIM, int MINB>
+__global__ void __launch_bounds__(32, MINB)
 raster_fwd_quad_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t channels, const float4 *__restrict__ rec,
                        const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks, uint32_t W,
                        uint32_t H, uint32_t tile_width, uint32_t tile_height,
                        const int32_t *__restrict__ tile_offsets, const int32_t *__restrict__ flatten_ids,
                        float *__restrict__ render_colors, float *__restrict__ render_alphas,
-                       int32_t *__restrict__ last_ids) {
-    constexpr int NW = 4 / NQ;    // warps per CTA; each works on its own (no block-level sync)
-    constexpr int NQY = NQ / 2;   // quad rows per warp
-    __shared__ float4 s_rec_all[NW][32 * 3];
-    __shared__ int2 s_im_all[NW][32];  // {sorted index, quad mask}
-    __shared__ float4 s_pre_all[ASYNC ? NW : 1][ASYNC ? 32 * 3 : 1];  // records of the batch in flight
-    const unsigned lane = threadIdx.x & 31, sub = threadIdx.x >> 5;
-    float4 *s_rec = s_rec_all[sub];
-    int2 *s_im = s_im_all[sub];
-    const float4 *s_pre = s_pre_all[ASYNC ? sub : 0] + (ASYNC ? 3 * lane : 0);
+                       int32_t *__restrict__ last_ids, uint8_t *__restrict__ quad_masks) {
+    constexpr int NQ = 4;         // one warp owns the whole tile
+    constexpr int NQY = NQ / 2;   // quad rows
+    __shared__ float4 s_rec[32 * 3];
+    __shared__ int2 s_im[32];     // {sorted index, quad mask}
+    __shared__ float4 s_pre_all[32 * 3];  // records of the batch in flight
+    const unsigned lane = threadIdx.x & 31;
+    const float4 *s_pre = s_pre_all + 3 * lane;
     const uint32_t pre_addr = (uint32_t)__cvta_generic_to_shared(s_pre);
     const uint32_t tile_lin = blockIdx.x;
-    const QuadTile tc = quad_tile<NQ>(tile_lin, tile_width, tile_height, lane, sub);
+    const QuadTile tc = quad_tile<NQ>(tile_lin, tile_width, tile_height, lane, 0);
     if (backgrounds != nullptr) backgrounds += (size_t)tc.cam * channels;
     const size_t cam_pix = (size_t)tc.cam * H * W;
 
@@ -247,22 +247,19 @@ raster_fwd_quad_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t chann
     }
     const float pxa = tc.px, pxb = tc.px + 8.f;
 
-    // prefetch of this lane's record: one batch ahead for the record (ASYNC: straight into shared
-    // memory), two batches ahead for the sorted id it is addressed by
-    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
+    // prefetch of this lane's record: one batch ahead straight into shared memory (cp.async), two
+    // batches ahead for the sorted id it is addressed by
     int32_t my_idx = range_start + (int32_t)lane, g_next = 0;
-    if (my_idx < range_end) {
-        const int32_t g = flatten_ids[my_idx];
-        if (ASYNC) prefetch_record(pre_addr, rec, g);
-        else { r0 = __ldg(rec + 3 * (size_t)g); r1 = __ldg(rec + 3 * (size_t)g + 1); r2 = __ldg(rec + 3 * (size_t)g + 2); }
-    }
+    if (my_idx < range_end) prefetch_record(pre_addr, rec, flatten_ids[my_idx]);
     if (my_idx + 32 < range_end) g_next = flatten_ids[my_idx + 32];
     for (int32_t base = range_start; base < range_end && live != 0; base += 32) {
         uint32_t my_mask = 0;
-        if (ASYNC) cp_async_wait_all();
+        float4 r0, r1, r2;
+        cp_async_wait_all();
         if (my_idx < range_end) {
-            if (ASYNC) { r0 = s_pre[0]; r1 = s_pre[1]; r2 = s_pre[2]; }
-            my_mask = quad_mask<NQ>(r0.x, r0.y, r0.z, r0.w, r1.x, r2.z, tc.ox, tc.oy, W, H);
+            r0 = s_pre[0]; r1 = s_pre[1]; r2 = s_pre[2];
+            my_mask = quad_mask<NQ>(r0.x, r0.y, r0.z, r0.w, r1.x, r2.z, r1.y, tc.ox, tc.oy, W, H);
+            if (quad_masks != nullptr) quad_masks[my_idx] = pack_quad_mask(my_mask);
             if ((my_mask & live) == 0) my_mask = 0; else my_mask &= (live | kNonPD);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, my_mask != 0);
@@ -277,10 +274,7 @@ raster_fwd_quad_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t chann
         __syncwarp();
         // prefetch the next batch while this one is composited
         my_idx = base + 32 + (int32_t)lane;
-        if (my_idx < range_end) {
-            if (ASYNC) prefetch_record(pre_addr, rec, g_next);
-            else { r0 = __ldg(rec + 3 * (size_t)g_next); r1 = __ldg(rec + 3 * (size_t)g_next + 1); r2 = __ldg(rec + 3 * (size_t)g_next + 2); }
-        }
+        if (my_idx < range_end) prefetch_record(pre_addr, rec, g_next);
         if (my_idx + 32 < range_end) g_next = flatten_ids[my_idx + 32];
         for (int t = 0; t < n; ++t) {
             const float4 a = s_rec[3 * t], b4 = s_rec[3 * t + 1], c4 = s_rec[3 * t + 2];
@@ -297,30 +291,17 @@ raster_fwd_quad_kernel(uint32_t n_tiles_total, uint64_t n_isects, uint32_t chann
                 ndy2[qy] = __fadd2_rn(pyc2[qy], bc2(c4.z));   // p_y - g_y
                 dy2[qy] = __fadd2_rn(npyc2[qy], bc2(a.y));    // g_y - p_y
             }
-#define B2S_FQ(SIGN_, q_)                                                                                            \
-    fwd_quad<CDIM, SIGN_>(T2[q_], pix2[q_], cur[q_], dy2[(q_) >> 1], ndy2[(q_) >> 1], ((q_) & 1) ? nAb : nAa,          \
+#define B2S_FQ(SLOW_, q_)                                                                                            \
+    fwd_quad<CDIM, SLOW_>(T2[q_], pix2[q_], cur[q_], dy2[(q_) >> 1], ndy2[(q_) >> 1], ((q_) & 1) ? nAb : nAa,          \
                           ((q_) & 1) ? Bb : Ba, hC, nopac, ncol, idx)
             if (m & kNonPD) {
 #pragma unroll
                 for (int q = 0; q < NQ; ++q)
                     if (m >> q & 1) B2S_FQ(true, q);  // warp-uniform
-            } else if (JOINT == 0) {
+            } else {
 #pragma unroll
                 for (int q = 0; q < NQ; ++q)
                     if (m >> q & 1) B2S_FQ(false, q);  // warp-uniform
-            } else if (JOINT == 2 && NQ == 4 && (m & 0xFu) == 0xFu) {
-                // all four quads: one basic block, four independent dependency chains
-                B2S_FQ(false, 0); B2S_FQ(false, 1); B2S_FQ(false, 2); B2S_FQ(false, 3);
-            } else {
-                // the two quads of a quad row in ONE basic block when both are reached, so the
-                // scheduler interleaves their (independent) chains: ILP 2 instead of 1
-#pragma unroll
-                for (int h = 0; h < NQY; ++h) {
-                    const uint32_t mm = (m >> (2 * h)) & 3u;
-                    if (mm == 3u) { B2S_FQ(false, 2 * h); B2S_FQ(false, 2 * h + 1); }
-                    else if (mm == 1u) B2S_FQ(false, 2 * h);
-                    else if (mm == 2u) B2S_FQ(false, 2 * h + 1);
-                }
             }
 #undef B2S_FQ
         }
@@ -357,21 +338,21 @@ static void launch_fwd_quad(uint32_t C, uint64_t n_isects, uint32_t channels, co
                             const float *backgrounds, const uint8_t *masks, uint32_t W, uint32_t H,
                             uint32_t tile_width, uint32_t tile_height, const int32_t *tile_offsets,
                             const int32_t *flatten_ids, float *render_colors, float *render_alphas, int32_t *last_ids,
-                            cudaStream_t st) {
+                            uint8_t *quad_masks, cudaStream_t st) {
     const uint32_t total = C * tile_width * tile_height;
-#define B2S_FWDQ(NQ_, MINB_, J_, A_)                                                                                \
-    raster_fwd_quad_kernel<CDIM, NQ_, MINB_, J_, A_><<<total, 32 * (4 / NQ_), 0, st>>>(                              \
-        total, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, \
-        render_colors, render_alphas, last_ids)
+#define B2S_FWDQ(MINB_)                                                                                              \
+    raster_fwd_quad_kernel<CDIM, MINB_><<<total, 32, 0, st>>>(total, n_isects, channels, rec, backgrounds, masks, W,  \
+                                                               H, tile_width, tile_height, tile_offsets, flatten_ids, \
+                                                               render_colors, render_alphas, last_ids, quad_masks)
+#ifdef B2S_TUNING
     switch (tuning_variant()) {
-        case 1: B2S_FWDQ(4, 16, 0, 0); break;
-        case 2: B2S_FWDQ(2, 12, 0, 1); break;   // two warps per tile
-        case 6: B2S_FWDQ(2, 16, 0, 1); break;
-        case 3: B2S_FWDQ(4, 20, 0, 0); break;   // register prefetch of the records (r1_c default)
-        case 4: B2S_FWDQ(4, 20, 1, 0); break;   // joint quads measured slower here (0.416 vs 0.383 ms)
-        case 5: B2S_FWDQ(4, 24, 0, 1); break;   // cp.async record prefetch, 80 registers
-        default: B2S_FWDQ(4, 20, 0, 1); break;  // cp.async record prefetch: 0.362 ms vs 0.372 (fwd + pack, config B)
+        case 1: B2S_FWDQ(16); return;
+        case 2: B2S_FWDQ(24); return;
+        case 3: B2S_FWDQ(18); return;
+        default: break;
     }
+#endif
+    B2S_FWDQ(20);
 #undef B2S_FWDQ
 }
 
@@ -403,7 +384,7 @@ extern "C" int b200splat_rasterize_fwd(uint32_t C, uint32_t n_gauss, uint64_t n_
                                        const float *opacities, const float *backgrounds, const uint8_t *masks,
                                        uint32_t W, uint32_t H, uint32_t tile_size, uint32_t tile_width,
                                        uint32_t tile_height, const int32_t *tile_offsets, const int32_t *flatten_ids,
-                                       const void *records,
+                                       const void *records, uint8_t *quad_masks,
                                        float *render_colors, float *render_alphas, int32_t *last_ids, void *stream) {
     const char *where = "b200splat_rasterize_fwd";
     (void)n_gauss;
@@ -417,10 +398,10 @@ extern "C" int b200splat_rasterize_fwd(uint32_t C, uint32_t n_gauss, uint64_t n_
         const float4 *rec = reinterpret_cast<const float4 *>(records);
         cudaStream_t st2 = (cudaStream_t)stream;
         switch (channels) {
-            case 1: launch_fwd_quad<1>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids, st2); break;
-            case 2: launch_fwd_quad<2>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids, st2); break;
-            case 3: launch_fwd_quad<3>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids, st2); break;
-            default: launch_fwd_quad<4>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids, st2); break;
+            case 1: launch_fwd_quad<1>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids, quad_masks, st2); break;
+            case 2: launch_fwd_quad<2>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids, quad_masks, st2); break;
+            case 3: launch_fwd_quad<3>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids, quad_masks, st2); break;
+            default: launch_fwd_quad<4>(C, n_isects, channels, rec, backgrounds, masks, W, H, tile_width, tile_height, tile_offsets, flatten_ids, render_colors, render_alphas, last_ids, quad_masks, st2); break;
         }
         B2S_CHECK_LAUNCH(where);
         return 0;

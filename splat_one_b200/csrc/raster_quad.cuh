@@ -79,15 +79,26 @@ __device__ __forceinline__ float rect_qmin(float hA, float b, float hC, float ih
     return qmin;
 }
 
-constexpr uint32_t kNonPD = 0x80000000u;  // mask flag: conic not positive definite (sigma may be < 0)
+// mask flag: this pair takes the slow compositing path, which applies the reference's two rarely-active
+// rules literally — `sigma < 0` rejection (conic not positive definite) and the `min(0.999, .)` clamp of
+// alpha (only reachable when opacity > 0.998: alpha = opacity·2^(-sigma') <= opacity otherwise, and
+// ex2.approx is within 2 ulp).  Every other pair runs code with both compiled out.
+constexpr uint32_t kNonPD = 0x80000000u;
+constexpr float kClampFreeOpacity = 0.998f;
+
+// one byte per listed (tile, Gaussian) pair, written by the forward kernel for every pair it stages and
+// read back by the backward kernel instead of re-running quad_mask: bits 0-3 = reachable quads
+// (geometry only), bit 7 = slow path
+__device__ __forceinline__ uint8_t pack_quad_mask(uint32_t m) { return (uint8_t)((m & 0xFu) | ((m & kNonPD) ? 0x80u : 0u)); }
+__device__ __forceinline__ uint32_t unpack_quad_mask(uint8_t b) { return (uint32_t)(b & 0xFu) | ((b & 0x80u) ? kNonPD : 0u); }
 
 // Which of the NQ 8x8 quads of the region at pixel origin (ox, oy) can this Gaussian reach
 // with alpha >= 1/255 at some pixel centre?  Quad q sits at (ox + 8 (q & 1), oy + 8 (q >> 1)).
 // Conservative: answers "yes" whenever unsure (non positive-definite conic, NaNs); never
 // "yes" for a quad outside the image.  Bit 31 flags a non positive-definite conic.
 template <int NQ>
-__device__ __forceinline__ uint32_t quad_mask(float gx, float gy, float hA, float b, float hC, float tau, uint32_t ox,
-                                              uint32_t oy, uint32_t W, uint32_t H) {
+__device__ __forceinline__ uint32_t quad_mask(float gx, float gy, float hA, float b, float hC, float tau, float nopac,
+                                              uint32_t ox, uint32_t oy, uint32_t W, uint32_t H) {
     const bool pd = (hA > 0.f) && (hC > 0.f) && (4.f * hA * hC - b * b > 0.f);
     const float ihC = -0.5f * b / hC, ihA = -0.5f * b / hA;
     uint32_t m = 0;
@@ -105,7 +116,7 @@ __device__ __forceinline__ uint32_t quad_mask(float gx, float gy, float hA, floa
         const bool drop = pd && (qmin - (0.03f + 2e-6f * mag) > tau);  // NaN-safe: keeps on NaN
         if (!drop) m |= 1u << q;
     }
-    if (m != 0 && !pd) m |= kNonPD;
+    if (m != 0 && (!pd || !(-nopac <= kClampFreeOpacity))) m |= kNonPD;  // NaN opacity: slow path too
     return m;
 }
 

@@ -1196,26 +1196,29 @@ class _RasterizeToPixels(torch.autograd.Function):
             last_ids.zero_()
         # warp-per-tile fast path (tile_size 16, <= 4 channels): one packed 48-byte record per
         # Gaussian, shared by the forward and the backward kernel
-        records = None
+        records = quad_masks = None
         rec_bytes = 0 if _FORCE_GENERIC_RASTER else lib.b200splat_rasterize_records_bytes(n_gauss, channels, tile_size)
         if rec_bytes and n_isects:
             records = torch.empty((rec_bytes // 4,), device=dev, dtype=torch.float32)
             native("rasterize_pack", lib, dev, n_gauss, channels, _ptr(means2d_a), _ptr(conics), _ptr(colors),
                    _ptr(opacities), _ptr(records))
+            if any(ctx.needs_input_grad[:5]):
+                # one byte per list entry: the forward's quad culling decisions, reused by the backward
+                quad_masks = torch.empty((n_isects,), device=dev, dtype=torch.uint8)
         if render_colors.numel():
             native("rasterize_fwd", lib, dev, C, n_gauss, n_isects, channels, _ptr(means2d_a), _ptr(conics), _ptr(colors), _ptr(opacities),
                     _ptr(backgrounds), _ptr(masks), width, height, tile_size, tile_width, tile_height,
-                    _ptr(isect_offsets), _ptr(flatten_ids), _ptr(records), _ptr(render_colors), _ptr(render_alphas),
-                    _ptr(last_ids))
+                    _ptr(isect_offsets), _ptr(flatten_ids), _ptr(records), _ptr(quad_masks), _ptr(render_colors),
+                    _ptr(render_alphas), _ptr(last_ids))
         ctx.save_for_backward(means2d, conics, colors, opacities, backgrounds, masks, isect_offsets, flatten_ids,
-                              render_alphas, last_ids, records)
+                              render_alphas, last_ids, records, quad_masks)
         ctx.width, ctx.height, ctx.tile_size, ctx.absgrad = width, height, tile_size, absgrad
         return render_colors, render_alphas
 
     @staticmethod
     def backward(ctx, v_render_colors: Tensor, v_render_alphas: Tensor):
         (means2d, conics, colors, opacities, backgrounds, masks, isect_offsets, flatten_ids, render_alphas,
-         last_ids, records) = ctx.saved_tensors
+         last_ids, records, quad_masks) = ctx.saved_tensors
         lib = get_lib()
         dev = means2d.device
         C, tile_height, tile_width = isect_offsets.shape
@@ -1237,8 +1240,8 @@ class _RasterizeToPixels(torch.autograd.Function):
         if n_isects and render_alphas.numel():
             native("rasterize_bwd", lib, dev, C, n_gauss, n_isects, channels, _ptr(means2d_a), _ptr(conics), _ptr(colors), _ptr(opacities),
                     _ptr(backgrounds), _ptr(masks), ctx.width, ctx.height, ctx.tile_size, tile_width, tile_height,
-                    _ptr(isect_offsets), _ptr(flatten_ids), _ptr(records), _ptr(render_alphas), _ptr(last_ids),
-                    _ptr(v_render_colors), _ptr(v_render_alphas), _ptr(v_means2d_abs), _ptr(v_means2d),
+                    _ptr(isect_offsets), _ptr(flatten_ids), _ptr(records), _ptr(quad_masks), _ptr(render_alphas),
+                    _ptr(last_ids), _ptr(v_render_colors), _ptr(v_render_alphas), _ptr(v_means2d_abs), _ptr(v_means2d),
                     _ptr(v_conics), _ptr(v_colors), _ptr(v_opacities))
         if ctx.absgrad:
             means2d.absgrad = v_means2d_abs  # G/cuda/_wrapper.py:1005-1006

@@ -45,7 +45,7 @@ def test_validation_errors_are_reported_without_a_gpu():
     with pytest.raises(_lib.B200SplatError):
         _lib.check(rc, lib)
     rc = lib.b200splat_rasterize_fwd(1, 1, 1, 700, None, None, None, None, None, None, 16, 16, 16, 1, 1, None, None,
-                                     None, None, None, None, None)
+                                     None, None, None, None, None, None)
     assert rc != 0 and b"channels" in lib.b200splat_last_error()
     rc = lib.b200splat_projection_fwd(1, 1, None, None, None, None, None, None, 8, 8, 0.3, 0.01, 1e10, 0.0, 9,
                                       None, None, None, None, None, None)
