@@ -32,9 +32,10 @@ N_GAUSS = 1_000_000
 WIDTH, HEIGHT = 1920, 1080
 SH_DEGREE = 3
 WORKLOAD = "configB: 1M Gaussians, SH3, 1920x1080 pinhole, packed=False, fwd+bwd"
-# bounded CPU sample: same scene generator at 1/16 of the pixels and Gaussians (same
-# depth complexity per pixel), so a CPU step takes seconds instead of minutes
-CPU_SAMPLE = dict(n=N_GAUSS // 16, width=WIDTH // 4, height=HEIGHT // 4)
+# CPU arm: the FULL config B (a step of the oracle port takes a few seconds on the host cores);
+# what is bounded is the number of steps (CPU_BUDGET_S of wall clock per run)
+CPU_SAMPLE = dict(n=N_GAUSS, width=WIDTH, height=HEIGHT)
+CPU_BUDGET_S = 200.0
 
 
 def _peaks():
@@ -158,8 +159,10 @@ def cpu_reference_step(scene, params, cot):
     return cot, meta
 
 
-def cpu_baseline(steps: int, warmup: int):
-    """Time the oracle port on the host cores. Returns (Mpix/s, ms/step, cores, sample str)."""
+def cpu_baseline(steps: int, warmup: int, budget_s: float = CPU_BUDGET_S):
+    """Time the oracle port on the host cores, on the same scene and sizes as the GPU arm (config B).
+    `steps` / `warmup` are honoured as long as the run fits `budget_s` of wall clock (the first step is
+    timed to decide).  Returns (Mpix/s, ms/step, cores, sample str, steps done, warm-ups done)."""
     from oracle import raster_ref as RC
     from splat_one_b200 import synthetic
 
@@ -169,29 +172,33 @@ def cpu_baseline(steps: int, warmup: int):
     scene = synthetic.pinhole_scene(CPU_SAMPLE["n"], CPU_SAMPLE["width"], CPU_SAMPLE["height"], seed=42,
                                     sh_degree=SH_DEGREE)
     params = [scene[k].clone().requires_grad_() for k in ("means", "quats", "scales", "opacities", "sh")]
-    cot = None
-    for _ in range(warmup):
+    t_start = time.perf_counter()
+    cot, _ = cpu_reference_step(scene, params, None)  # first warm-up (builds the cotangents), timed for the budget
+    t_first = time.perf_counter() - t_start
+    fit = max(1, int((budget_s - t_first) / max(t_first, 1e-3)))
+    warm_done = 1 + max(0, min(warmup - 1, fit - 1))
+    for _ in range(warm_done - 1):
         cot, _ = cpu_reference_step(scene, params, cot)
+    steps = max(1, min(steps, fit - (warm_done - 1)))
     t0 = time.perf_counter()
     for _ in range(steps):
         cot, meta = cpu_reference_step(scene, params, cot)
     dt = (time.perf_counter() - t0) / steps
     mpix = CPU_SAMPLE["width"] * CPU_SAMPLE["height"] / dt / 1e6
-    sample = (f"{CPU_SAMPLE['n']} Gaussians @ {CPU_SAMPLE['width']}x{CPU_SAMPLE['height']} (1/16 of config B, same "
-              f"density; n_isects={meta['flatten_ids'].numel()}), oracle port: torch-CPU projection/SH/autograd + "
-              f"numpy isect + C raster fwd/bwd, {steps} steps")
-    return mpix, dt * 1e3, cores, sample
+    sample = (f"full config B: {CPU_SAMPLE['n']} Gaussians @ {CPU_SAMPLE['width']}x{CPU_SAMPLE['height']} "
+              f"(n_isects={meta['flatten_ids'].numel()}), oracle port: torch-CPU projection/SH/autograd + "
+              f"numpy isect + C raster fwd/bwd, {steps} steps after {warm_done} warm-ups")
+    return mpix, dt * 1e3, cores, sample, steps, warm_done
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 5))
-    mpix, ms, cores, sample = cpu_baseline(steps, max(1, min(args.warmup, 1)))
+    mpix, ms, cores, sample, steps, warm = cpu_baseline(args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": "rendered Mpix/s fwd+bwd", "value": mpix, "unit": "Mpix/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": ms,
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
         "cpu_baseline": {"value": mpix, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample},
@@ -241,6 +248,149 @@ def train_step_report(S, scene, dev, reps: int = 30, warm: int = 5):
                     "-> backward; config B scene, random target image"}
 
 
+
+def reference_cuda_leg(S, scene, dev, ms_ours: float, reps: int = 20, warm: int = 5):
+    """Extra, labelled leg (outside the timed region, never on the product path): the reference's OWN
+    CUDA kernels — oracle/_ref, the fork's gsplat extension built for sm_100a by oracle/build_ref.py —
+    chained the way G/rendering.py chains them (raw pybind calls: without the reference's Python and
+    autograd overhead, which favours the reference), on the same scene, same GPU, same run.
+    None when oracle/_ref was not built."""
+    try:
+        from oracle import ref_cuda
+    except Exception:
+        return None
+    R = ref_cuda.load()
+    if R is None:
+        return {"unavailable": "oracle/_ref/gsplat_ref_csrc.so not built (python oracle/build_ref.py)"}
+    P = {k: scene[k].to(dev) for k in ("means", "quats", "scales", "opacities", "sh")}
+    P["viewmats"], P["Ks"] = scene["viewmats"][:1].to(dev), scene["Ks"][:1].to(dev)
+    g = torch.Generator().manual_seed(1000)
+    vc = torch.randn(1, HEIGHT, WIDTH, 3, generator=g).to(dev)
+    va = torch.randn(1, HEIGHT, WIDTH, 1, generator=g).to(dev)
+    for _ in range(warm):
+        ref = ref_cuda.reference_chain(R, P, WIDTH, HEIGHT, "pinhole", vc, va)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        ref = ref_cuda.reference_chain(R, P, WIDTH, HEIGHT, "pinhole", vc, va)
+    b.record()
+    torch.cuda.synchronize()
+    ms_ref = a.elapsed_time(b) / reps
+    # parity of this very run (the asserting version lives in tests/test_gpu_fullsize_parity.py)
+    A = [P[k].clone().requires_grad_() for k in ("means", "quats", "scales", "opacities", "sh")]
+    rc, ra, _ = S.rasterization(*A, P["viewmats"], P["Ks"], WIDTH, HEIGHT, sh_degree=SH_DEGREE, packed=False)
+    torch.autograd.backward([rc, ra], [vc, va])
+    err = (rc.detach() - ref["image"]).abs()
+    gerr = {k: float((p.grad - ref["grads"][k]).abs().max() / (ref["grads"][k].abs().max() + 1e-30))
+            for k, p in zip(("means", "quats", "scales", "opacities", "sh"), A)}
+    return {"ms_per_step": ms_ref, "Mpix_per_s": HEIGHT * WIDTH / (ms_ref * 1e-3) / 1e6, "steps": reps,
+            "speedup_of_this_library": ms_ref / ms_ours, "image_max_abs_err": float(err.max()),
+            "image_frac_outside_1e-4": float((err > 1e-4).float().mean()), "grad_max_rel_err": gerr,
+            "what": "reference CUDA (oracle/_ref, sm_100a build of the fork's kernels) chained as G/rendering.py does, "
+                    "raw pybind calls, same scene / GPU / run; device-resident like `value`"}
+
+
+def dp_parity_check(S, dist, world, rank, dev):
+    """Outside the timed region, N > 1: gradients of the camera-sharded step (each rank one camera,
+    colour-cotangent all-gather + arena all-reduce) against the SAME batch rendered by one process
+    (C = N cameras on this GPU), 40 k Gaussians at 320x240.  Returns the max over ranks and parameters of
+    max|dp - batch| / max|batch|."""
+    from splat_one_b200 import synthetic
+    from splat_one_b200.distributed import GradArena, camera_parallel
+
+    W_, H_, N_ = 320, 240, 40000
+    sc = synthetic.pinhole_scene(N_, W_, H_, seed=7, n_cameras=world)
+    names = ("means", "quats", "scales", "opacities", "sh")
+    g = torch.Generator().manual_seed(3)
+    vc_all = torch.randn(world, H_, W_, 3, generator=g).to(dev)
+    va_all = torch.randn(world, H_, W_, 1, generator=g).to(dev)
+
+    def grads(cams, dp):
+        P = [sc[k].to(dev).requires_grad_() for k in names]
+        rc, ra, _ = S.rasterization(*P, sc["viewmats"][cams].to(dev), sc["Ks"][cams].to(dev), W_, H_,
+                                    sh_degree=SH_DEGREE, packed=False)
+        if dp:
+            arena = GradArena(P)
+            with arena.sink(), camera_parallel() as cp:
+                torch.autograd.backward([rc, ra], [vc_all[cams], va_all[cams]])
+            arena.gather_from_params()
+            arena.all_reduce(skip_ptrs=cp.reduced_ptrs)
+            arena.scatter_to_params()
+        else:
+            torch.autograd.backward([rc, ra], [vc_all[cams], va_all[cams]])
+        return [p.grad.detach().clone() for p in P]
+
+    g_dp, g_ref = grads([rank], True), grads(list(range(world)), False)
+    worst = max(float((a - b).abs().max() / (b.abs().max() + 1e-30)) for a, b in zip(g_dp, g_ref))
+    t = torch.tensor([worst], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item()
+
+
+def extra_config(S, dist, name, world, rank, dev, steps: int = 10, warm: int = 3):
+    """The other multi-GPU configs of BASELINE.json as extra keys (not the headline): config C = 3 M
+    Gaussians, a batch of `world` 1080p cameras (one per rank), dense gradient exchange; config E = 6 M
+    Gaussians, 3840x2160, packed + sparse gradients, exchanged as (gaussian_ids, rows) with the dense
+    fallback (splat_one_b200.distributed.allreduce_mixed_gradients)."""
+    from splat_one_b200 import synthetic
+    from splat_one_b200.distributed import GradArena, allreduce_mixed_gradients, camera_parallel
+
+    if name == "C":
+        n, W_, H_, kw = 3_000_000, 1920, 1080, dict(packed=False)
+    else:
+        n, W_, H_, kw = 6_000_000, 3840, 2160, dict(packed=True, sparse_grad=True)
+    sc = synthetic.pinhole_scene(n, W_, H_, seed=43 if name == "C" else 45, n_cameras=world)
+    names = ("means", "quats", "scales", "opacities", "sh")
+    P = [sc[k].to(dev).requires_grad_() for k in names]
+    vm, Ks = sc["viewmats"][rank::world].to(dev), sc["Ks"][rank::world].to(dev)
+    g = torch.Generator().manual_seed(2000 + rank)
+    vc = torch.randn(1, H_, W_, 3, generator=g).to(dev)
+    va = torch.randn(1, H_, W_, 1, generator=g).to(dev)
+    arena = GradArena(P) if (world > 1 and name == "C") else None
+    counts = []
+
+    def step():
+        for p in P:
+            p.grad = None
+        rc, ra, meta = S.rasterization(*P, vm, Ks, W_, H_, sh_degree=SH_DEGREE, **kw)
+        if arena is not None:
+            with arena.sink(), camera_parallel() as cp:
+                torch.autograd.backward([rc, ra], [vc, va])
+            arena.gather_from_params()
+            arena.all_reduce(skip_ptrs=cp.reduced_ptrs)
+        else:
+            torch.autograd.backward([rc, ra], [vc, va])
+            if world > 1:
+                allreduce_mixed_gradients(P)
+        return meta
+
+    for _ in range(warm):
+        meta = step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        meta = step()
+    b.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item() / steps
+    out = {"ms_per_step": ms, "Mpix_per_s": world * H_ * W_ / (ms * 1e-3) / 1e6, "steps": steps, "warmup": warm,
+           "n_gaussians": n, "image": f"{W_}x{H_}", "cameras": world, "n_isects_rank0": int(meta["flatten_ids"].numel()),
+           "mode": "unpacked, dense gradients: cotangent all-gather + arena all-reduce" if name == "C" else
+                   "packed, sparse gradients: (gaussian_ids, rows) all-gather with dense fallback above 0.4 visible"}
+    del P, sc
+    torch.cuda.empty_cache()
+    return out
+
+
 # A/B switch: overlapped gradient exchange (camera_parallel(defer=True) + finish()).  Measured at N = 2:
 # 1.731 ms/step against 1.701 for the plain order (the collectives and the colour backward compete for
 # HBM), so the plain order stays the default; not measured at N = 8.
@@ -278,7 +428,7 @@ def run_gpu(args):
     vc, va = vc_host.to(dev), va_host.to(dev)
     arena = GradArena(params) if world > 1 else None
 
-    def step():
+    def step(defer=DEFER):
         for p in params:
             p.grad = None
         rc, ra, meta = S.rasterization(*params, vm, Ks, WIDTH, HEIGHT, sh_degree=SH_DEGREE, packed=False)
@@ -286,14 +436,14 @@ def run_gpu(args):
         if arena is not None:
             # SH / quats / scales gradients are produced inside the arena; the SH gradient comes
             # out already summed over ranks (colour-cotangent all-gather, distributed.py)
-            with arena.sink(), camera_parallel(defer=DEFER) as cp:
+            with arena.sink(), camera_parallel(defer=defer) as cp:
                 torch.autograd.backward([rc, ra], [vc, va])
             skip = cp.reduced_ptrs
         else:
             torch.autograd.backward([rc, ra], [vc, va])
         if arena is not None:
             prof = wrapper.profiler
-            if DEFER:
+            if defer:
                 # all-gather overlapped the projection backward; the arena all-reduce overlaps the colour
                 # backward kernel (splat_one_b200/distributed.py camera_parallel.finish)
                 if prof.enabled:
@@ -348,6 +498,22 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = t.item() / args.steps
+    # A/B of the other exchange order (N > 1, outside `value`): a few steps with the overlapped exchange
+    # when the timed loop used the plain one and vice versa
+    ms_other = None
+    if world > 1:
+        n_ab = max(min(args.steps, 30), 5)
+        for _ in range(3):
+            step(not DEFER)
+        barrier()
+        e0.record()
+        for _ in range(n_ab):
+            step(not DEFER)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_other = t.item() / n_ab
     launches = wrapper.profiler.launches()
     timed_stages = wrapper.profiler.summary_ms()
     # full stage table: a few more steps with every native call bracketed (not part of `value`)
@@ -435,13 +601,15 @@ def run_gpu(args):
     cot_free[0].record(torch.cuda.current_stream(dev))
     cot_free[1].record(torch.cuda.current_stream(dev))
     prefetch(0)
+    # headline e2e: the step's RESULT — the rendered image and alpha, plus the gradient norm — goes back
+    # to pinned host memory every step
     for _ in range(2):
-        e2e_step()
+        e2e_step(True)
     e2e_drain()
     barrier()
     e0.record()
     for _ in range(args.steps):
-        e2e_step()
+        e2e_step(True)
     e2e_drain()
     e1.record()
     barrier()
@@ -450,23 +618,33 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = t.item() / args.steps
     h2d = vm_host.numel() * 4 + K_host.numel() * 4 + vc_host.numel() * 4 + va_host.numel() * 4
-    d2h = 4
-    # the same loop with the rendered image + alpha copied back to the host every step (viewer-style)
-    n_img = max(args.steps // 2, 1)
-    e2e_step(True)
+    d2h = out_c_host.numel() * 4 + out_a_host.numel() * 4 + 4
+    # the same loop reading back only the gradient norm (what a trainer reads per step)
+    n_small = max(args.steps // 2, 1)
+    e2e_step(False)
     e2e_drain()
     barrier()
     e0.record()
-    for _ in range(n_img):
-        e2e_step(True)
+    for _ in range(n_small):
+        e2e_step(False)
     e2e_drain()
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_img_ms = t.item() / n_img
-    d2h_img = out_c_host.numel() * 4 + out_a_host.numel() * 4 + 4
+    e2e_small_ms = t.item() / n_small
+
+    # ---- extra legs, all outside the timed regions -------------------------------------------
+    dp_parity = dp_parity_check(S, dist, world, rank, dev) if world > 1 else None
+    extras = {}
+    if not args.no_extra_configs:
+        # free the config-B scene first: config E needs several GB
+        for name in ("C", "E"):
+            try:
+                extras[name] = extra_config(S, dist, name, world, rank, dev)
+            except Exception as ex:  # never lose the headline line to an extra
+                extras[name] = {"error": repr(ex)[:200]}
 
     if rank == 0:
         peak, peak_src = _peaks()
@@ -521,12 +699,13 @@ def run_gpu(args):
         stage_report = {k: {"avg_ms": round(v["avg_ms"], 4),
                             "GBps": round(alg_bytes.get(k, 0) / (v["avg_ms"] * 1e-3) / 1e9, 1) if v["avg_ms"] > 0 else None}
                         for k, v in stages.items()}
-        train = None
+        train = ref_cuda_leg = None
         if world == 1:
             train = train_step_report(S, scene, dev)
+            ref_cuda_leg = reference_cuda_leg(S, scene, dev, ms_step)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            mpix, ms, cores, sample = cpu_baseline(2, 1)
+            mpix, ms, cores, sample, _, _ = cpu_baseline(3, 1, budget_s=40.0)
             cpu = {"value": mpix, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample}
         line = {
             "metric": "rendered Mpix/s fwd+bwd", "value": world * C_local * HEIGHT * WIDTH / (ms_step * 1e-3) / 1e6,
@@ -541,18 +720,24 @@ def run_gpu(args):
             "e2e": {"value": world * C_local * HEIGHT * WIDTH / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s",
                     "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "every step: camera + cotangent images H2D from pinned memory (cotangents prefetched one "
-                            "step ahead on an H2D stream), rasterization()+backward, result (gradient norm) D2H; "
+                            "step ahead on an H2D stream), rasterization()+backward, and the step's result — rendered "
+                            "image + alpha (D2H stream) and the gradient norm — copied to pinned host memory; "
                             "Gaussians stay resident (model state)",
-                    "with_image_d2h": {"value": world * C_local * HEIGHT * WIDTH / (e2e_img_ms * 1e-3) / 1e6,
-                                       "ms_per_step": e2e_img_ms, "d2h_bytes_per_step": d2h_img,
-                                       "what": "same, plus the rendered image + alpha copied to pinned host memory "
-                                               "every step on a D2H stream (viewer-style)"}},
+                    "grad_norm_only": {"value": world * C_local * HEIGHT * WIDTH / (e2e_small_ms * 1e-3) / 1e6,
+                                       "ms_per_step": e2e_small_ms, "d2h_bytes_per_step": 4,
+                                       "what": "same, reading back only the gradient norm (trainer-style)"}},
             "gpu_launches": launches,
             "roofline": roof,
             "raster_stages": raster,
             "stages": stage_report,
             "train_step": train,
             "cpu_baseline": cpu,
+            "reference_cuda": ref_cuda_leg,
+            "dp_parity_max_rel": dp_parity,
+            "exchange_order": {"timed": "deferred (overlapped)" if DEFER else "plain",
+                               "ms_per_step_other_order": ms_other} if world > 1 else None,
+            "config_C": extras.get("C"),
+            "config_E": extras.get("E"),
         }
         print(json.dumps(line))
     if world > 1:
@@ -566,6 +751,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the config C / E extra keys")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -30,10 +30,16 @@ class camera_parallel:
     `backward()` already global.  `reduced_ptrs` lists the parameters (by data_ptr) this
     happened for; `GradArena.all_reduce(skip_ptrs=...)` then leaves them out."""
 
-    def __init__(self, group=None, defer: bool = False):
+    def __init__(self, group=None, defer: bool = False, n_cameras_global: Optional[int] = None):
+        """`n_cameras_global`: size of the global camera batch when it is NOT a multiple of the world
+        size (shards then differ by one camera, `shard_cameras(..., allow_uneven=True)`); leave None for
+        equal shards.  `defer=True` needs the gradient sink of the arena to be active around `backward()`
+        and `p.grad is None` for the SH parameters (`zero_grad(set_to_none=True)`); where that does not
+        hold the colour stage silently uses the immediate order."""
         self.group = group if group is not None else dist.group.WORLD
         self.reduced_ptrs = set()
         self.defer = defer
+        self.n_cameras_global = n_cameras_global
         self._deferred = []  # (means parameter, finish(all_cameras) -> v_means) of the colour stages
 
     def __enter__(self):
@@ -45,6 +51,8 @@ class camera_parallel:
             wrapper._CAMERA_PARALLEL["reduced"] = self.reduced_ptrs
             if self.defer:
                 wrapper._CAMERA_PARALLEL["deferred"] = self._deferred
+            if self.n_cameras_global is not None:
+                wrapper._CAMERA_PARALLEL["n_cameras_global"] = int(self.n_cameras_global)
         return self
 
     def __exit__(self, *exc):
@@ -89,10 +97,16 @@ class camera_parallel:
 
 
 def shard_cameras(viewmats: Tensor, Ks: Tensor, rank: Optional[int] = None,
-                  world_size: Optional[int] = None) -> Tuple[Tensor, Tensor, Tensor]:
-    """Cameras owned by `rank`: indices rank, rank+W, ...  Returns (viewmats, Ks, global ids)."""
+                  world_size: Optional[int] = None, allow_uneven: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
+    """Cameras owned by `rank`: indices rank, rank+W, ...  Returns (viewmats, Ks, global ids).
+    The colour-cotangent exchange of `camera_parallel` all-gathers equal blocks: a global batch that
+    is not a multiple of the world size must be announced (`allow_uneven=True` here and
+    `camera_parallel(n_cameras_global=C)`), otherwise it is an error."""
     rank = dist.get_rank() if rank is None else rank
     world_size = dist.get_world_size() if world_size is None else world_size
+    if viewmats.shape[0] % world_size != 0 and not allow_uneven:
+        raise ValueError(f"{viewmats.shape[0]} cameras do not divide over {world_size} ranks: pass allow_uneven=True "
+                         f"and camera_parallel(n_cameras_global={viewmats.shape[0]})")
     ids = torch.arange(rank, viewmats.shape[0], world_size, device=viewmats.device)
     return viewmats[ids].contiguous(), Ks[ids].contiguous(), ids
 
@@ -198,3 +212,83 @@ def rasterization_dp(render_fn, params: Dict[str, Tensor], viewmats: Tensor, Ks:
     rc, ra, meta = render_fn(params["means"], params["quats"], params["scales"], params["opacities"],
                              params["colors"], vm, k, width, height, **kwargs)
     return rc, ra, meta, ids
+
+
+def sparse_allreduce(grads: Sequence[Tensor], group=None, dense_threshold: float = 0.4,
+                     counts_out: Optional[list] = None) -> List[Tensor]:
+    """SUM over ranks of sparse per-Gaussian gradients (packed mode with `sparse_grad=True`, config E).
+
+    `grads`: sparse COO tensors of this rank that share ONE index vector — the `gaussian_ids` of the
+    packed projection, [1, nnz] — with value rows [nnz, d_i] (the layout of the reference's sparse
+    gradients, G/cuda/_wrapper.py:1163-1203).  Ranks exchange `(gaussian_ids, value rows)` with ONE
+    padded all-gather (8 + 4·sum(d_i) bytes per visible Gaussian and rank) and every rank returns the
+    concatenation as un-coalesced COO tensors: identical on all ranks, and equal to the all-reduced dense
+    gradient once coalesced.  When the visible fraction sum_r(nnz_r) / N exceeds `dense_threshold` the
+    rows are scattered into dense tensors and all-reduced instead (the gathered rows would then outweigh
+    the dense payload); the result is dense in that case.  Outside a process group: returned unchanged."""
+    grads = list(grads)
+    if not grads or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return grads
+    W = dist.get_world_size(group)
+    g0 = grads[0]
+    assert all(g.is_sparse and g.shape[0] == g0.shape[0] for g in grads), "sparse COO gradients over the same rows"
+    ids = g0._indices()[0].contiguous()
+    nnz, n_rows, dev = ids.numel(), g0.shape[0], ids.device
+    for g in grads[1:]:
+        assert g._indices().shape == g0._indices().shape, "gradients must share gaussian_ids"
+    widths = [g._values().numel() // max(nnz, 1) if nnz else int(torch.tensor(g.shape[1:]).prod()) for g in grads]
+    counts = torch.empty(W, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, torch.tensor([nnz], dtype=torch.int64, device=dev), group=group)
+    counts = counts.tolist()  # one small host sync, like the n_isects / nnz read-backs of the path
+    if counts_out is not None:
+        counts_out[:] = counts
+    total = sum(counts)
+    if total > dense_threshold * n_rows:
+        out = []
+        for g in grads:
+            d = torch.zeros(g.shape, dtype=g.dtype, device=dev)
+            if nnz:
+                d.index_add_(0, ids, g._values())
+            dist.all_reduce(d, op=dist.ReduceOp.SUM, group=group)
+            out.append(d)
+        return out
+    m = max(counts)
+    D = sum(widths)
+    ids_pad = torch.zeros(m, dtype=torch.int64, device=dev)
+    rows_pad = torch.zeros((m, D), dtype=torch.float32, device=dev)
+    if nnz:
+        ids_pad[:nnz] = ids
+        rows_pad[:nnz] = torch.cat([g._values().reshape(nnz, -1) for g in grads], dim=1)
+    ids_all = torch.empty(W * m, dtype=torch.int64, device=dev)
+    rows_all = torch.empty((W * m, D), dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(ids_all, ids_pad, group=group)
+    dist.all_gather_into_tensor(rows_all, rows_pad, group=group)
+    keep = torch.cat([torch.arange(r * m, r * m + c, device=dev) for r, c in enumerate(counts)]) if total else \
+        torch.zeros(0, dtype=torch.int64, device=dev)
+    ids_cat, rows_cat = ids_all[keep], rows_all[keep]
+    out, o = [], 0
+    for g, w in zip(grads, widths):
+        vals = rows_cat[:, o:o + w].reshape((total,) + tuple(g.shape[1:])).contiguous()
+        out.append(torch.sparse_coo_tensor(ids_cat[None], vals, size=g.shape, is_coalesced=False))
+        o += w
+    return out
+
+
+def allreduce_mixed_gradients(params: Sequence[Tensor], arena: Optional[GradArena] = None, group=None,
+                              dense_threshold: float = 0.4, skip_ptrs=()) -> None:
+    """Gradient exchange of a camera-sharded step whose parameters carry a MIX of dense and sparse
+    gradients (packed mode, `sparse_grad=True`): the sparse ones (sharing `gaussian_ids`) go through
+    `sparse_allreduce`, the dense ones through the flat arena.  `p.grad` of every parameter holds the
+    global sum afterwards (sparse stays sparse below the threshold)."""
+    params = list(params)
+    sparse = [p for p in params if p.grad is not None and p.grad.is_sparse]
+    dense = [p for p in params if p.grad is not None and not p.grad.is_sparse]
+    if sparse:
+        for p, g in zip(sparse, sparse_allreduce([p.grad for p in sparse], group=group, dense_threshold=dense_threshold)):
+            p.grad = g
+    if dense:
+        if arena is None or [id(p) for p in arena.params] != [id(p) for p in dense]:
+            arena = GradArena(dense)
+        arena.gather_from_params()
+        arena.all_reduce(group=group, skip_ptrs=skip_ptrs)
+        arena.scatter_to_params()

@@ -219,8 +219,30 @@ class gradient_sink:
 
 
 # camera-parallel mode (set by splat_one_b200.distributed.camera_parallel): process group + the
-# data_ptr()s of parameters whose gradient came out of the backward already summed over ranks
+# data_ptr()s of parameters whose gradient came out of the backward already summed over ranks.
+# Like _GRAD_SINK this is process-wide, not thread-local, on purpose: autograd runs the backward
+# nodes on its own engine threads, which do not see the caller's thread-local state.  One training
+# loop per process (one process per GPU) is the supported use; the viewer thread of splat_one only
+# runs no-grad forwards and never reads either registry.
 _CAMERA_PARALLEL: dict = {}
+
+
+def _leaf_sources(t: Tensor):
+    """The leaf tensors a gradient handed to `t` ends up in, when that is known to be a plain
+    pass-through: `t` itself if it is a leaf, or the operands of a `torch.cat` of leaves (the
+    `torch.cat([sh0, shN], 1)` of gsplat_trainer.py:474).  None otherwise."""
+    if t.is_leaf:
+        return [t]
+    fn = t.grad_fn
+    if fn is not None and type(fn).__name__.startswith("CatBackward"):
+        leaves = []
+        for nxt, _ in fn.next_functions:
+            v = getattr(nxt, "variable", None)
+            if v is None:
+                return None
+            leaves.append(v)
+        return leaves
+    return None
 
 
 def _grad_out(like: Tensor) -> Tensor:
@@ -361,16 +383,33 @@ def _camera_parallel_colour_bwd(cp, means, campos, colors, v_colors, C, outs, v_
 
     W, r = dist.get_world_size(cp), dist.get_rank(cp)
     N = means.shape[0]
+    # every rank contributes a block of Cm camera slots.  Equal shards (the default, checked by
+    # distributed.shard_cameras) have Cm == C; with `n_cameras_global` given to camera_parallel, shards
+    # may differ by one camera (ids rank, rank + W, ...): short ranks pad with zero cotangents, which
+    # add nothing to the sums.
+    Cg = _CAMERA_PARALLEL.get("n_cameras_global")
+    Cm = C if Cg is None else (Cg + W - 1) // W
+    assert Cg is None or C == len(range(r, Cg, W)), (C, Cg, r, W)
     g_local = torch.where(colors > 0, v_colors, torch.zeros_like(v_colors))  # [C,N,3], zero where invisible
-    g_all = torch.empty((W * C, N, 3), device=means.device, dtype=torch.float32)
-    campos_all = torch.empty((W * C, 3), device=means.device, dtype=torch.float32)
+    campos_c = campos.contiguous()
+    if Cm != C:
+        g_local = torch.cat([g_local, g_local.new_zeros((Cm - C, N, 3))])
+        campos_c = torch.cat([campos_c, campos_c.new_zeros((Cm - C, 3))])
+    g_all = torch.empty((W * Cm, N, 3), device=means.device, dtype=torch.float32)
+    campos_all = torch.empty((W * Cm, 3), device=means.device, dtype=torch.float32)
     deferred = _CAMERA_PARALLEL.get("deferred")
+    if deferred is not None:
+        # deferred mode returns gradient tensors that are only filled in finish(): that is only sound
+        # when they ARE the arena views (gradient sink active) and nothing has to be added to them
+        sink_ok = all(o is None or any(o.data_ptr() == d.data_ptr() for d in _GRAD_SINK.values()) for o in outs)
+        fresh = all(lf.grad is None for lf in _CAMERA_PARALLEL.get("leaves", ()))
+        if not (sink_ok and fresh):
+            deferred = None
     if deferred is None:
         dist.all_gather_into_tensor(g_all, g_local, group=cp)
-        dist.all_gather_into_tensor(campos_all, campos.contiguous(), group=cp)
-        run(campos_all, g_all, outs, v_means, r * C, (r + 1) * C, W * C)
+        dist.all_gather_into_tensor(campos_all, campos_c, group=cp)
+        run(campos_all, g_all, outs, v_means, r * Cm, r * Cm + C, W * Cm)
         return v_means
-    campos_c = campos.contiguous()
     works = [dist.all_gather_into_tensor(g_all, g_local, group=cp, async_op=True),
              dist.all_gather_into_tensor(campos_all, campos_c, group=cp, async_op=True)]
     # the kernel writes through fresh aliases: autograd adopts the returned gradient tensors without
@@ -382,8 +421,8 @@ def _camera_parallel_colour_bwd(cp, means, campos, colors, v_colors, C, outs, v_
         for w in works:
             w.wait()
         vm = torch.empty_like(means) if want_means else None
-        lo, hi = (0, W * C) if all_cameras else (r * C, (r + 1) * C)
-        run(campos_all, g_all, alias, vm, lo, hi, W * C)
+        lo, hi = (0, W * Cm) if all_cameras else (r * Cm, r * Cm + C)
+        run(campos_all, g_all, alias, vm, lo, hi, W * Cm)
         return vm
 
     deferred.append((means, finish))
@@ -422,6 +461,9 @@ class _ShViewColors(torch.autograd.Function):
                    _ptr(coeffs), _ptr(radii), _ptr(colors))
         ctx.save_for_backward(means, campos, coeffs, radii, colors)
         ctx.sh_degree = sh_degree
+        # where the coefficient gradient ends up (camera-parallel exchange: only when that is a known
+        # set of leaves can the gradient be declared "already summed over ranks")
+        ctx.coeff_leaves = _leaf_sources(coeffs)
         return colors
 
     @staticmethod
@@ -435,7 +477,7 @@ class _ShViewColors(torch.autograd.Function):
         v_means = torch.empty_like(means) if ctx.needs_input_grad[1] else None
         v_colors = v_colors.contiguous()
         cp = _CAMERA_PARALLEL.get("group", None) if _CAMERA_PARALLEL else None
-        if cp is not None and not per_view and N:
+        if cp is not None and not per_view and N and ctx.coeff_leaves is not None:
             # camera-parallel exchange (splat_one_b200/distributed.py): the coefficient gradient
             # of camera c is the outer product B(dir_c) x v_rgb_c, so ranks all-gather their masked
             # colour cotangents (3 floats per Gaussian and camera) and every rank evaluates the
@@ -444,8 +486,12 @@ class _ShViewColors(torch.autograd.Function):
                 native("sh_colors_bwd", lib, means.device, WC, N, K, ctx.sh_degree, 0, _ptr(means), _ptr(campos_all),
                        _ptr(coeffs), None, None, _ptr(g_all), _ptr(v_out[0]), _ptr(v_means_out), lo, hi)
 
+            _CAMERA_PARALLEL["leaves"] = ctx.coeff_leaves
             v_means = _camera_parallel_colour_bwd(cp, means, campos, colors, v_colors, C, (v_coeffs,), v_means, run)
-            _CAMERA_PARALLEL["reduced"].add(coeffs.data_ptr())
+            # the gradient is global: mark the LEAVES it flows into (the table itself, or sh0 / shN behind
+            # a torch.cat), never the data_ptr of a temporary
+            for lf in ctx.coeff_leaves:
+                _CAMERA_PARALLEL["reduced"].add(lf.data_ptr())
         elif N:
             native("sh_colors_bwd", lib, means.device, C, N, K, ctx.sh_degree, per_view, _ptr(means), _ptr(campos),
                    _ptr(coeffs), _ptr(radii), _ptr(colors), _ptr(v_colors), _ptr(v_coeffs),
@@ -490,6 +536,9 @@ class _ShViewColorsStaged(torch.autograd.Function):
                    _ptr(rest), _ptr(radii), _ptr(colors))
         ctx.save_for_backward(means, campos, sh0, rest, radii, colors)
         ctx.sh_degree = sh_degree
+        ctx.coeff_leaves = None
+        if (sh0 is None or sh0.is_leaf) and rest.is_leaf:
+            ctx.coeff_leaves = [rest] if sh0 is None else [sh0, rest]
         return colors
 
     @staticmethod
@@ -503,7 +552,7 @@ class _ShViewColorsStaged(torch.autograd.Function):
         v_means = torch.empty_like(means) if ctx.needs_input_grad[1] else None
         v_colors = v_colors.contiguous()
         cp = _CAMERA_PARALLEL.get("group", None) if _CAMERA_PARALLEL else None
-        if cp is not None and N:
+        if cp is not None and N and ctx.coeff_leaves is not None:
             # camera-parallel exchange, as in _ShViewColors.backward
             outs = (v_sh0, v_rest) if sh0 is not None else (None, v_rest)
 
@@ -512,10 +561,10 @@ class _ShViewColorsStaged(torch.autograd.Function):
                        _ptr(campos_all), _ptr(sh0), _ptr(rest), None, None, _ptr(g_all), _ptr(v_out[0]), _ptr(v_out[1]),
                        _ptr(v_means_out), lo, hi)
 
+            _CAMERA_PARALLEL["leaves"] = ctx.coeff_leaves
             v_means = _camera_parallel_colour_bwd(cp, means, campos, colors, v_colors, C, outs, v_means, run)
-            _CAMERA_PARALLEL["reduced"].add(rest.data_ptr())
-            if sh0 is not None:
-                _CAMERA_PARALLEL["reduced"].add(sh0.data_ptr())
+            for lf in ctx.coeff_leaves:
+                _CAMERA_PARALLEL["reduced"].add(lf.data_ptr())
         elif N:
             native("sh_colors_staged_bwd", lib, means.device, C, N, K, ctx.sh_degree, _ptr(means), _ptr(campos),
                    _ptr(sh0), _ptr(rest), _ptr(radii), _ptr(colors), _ptr(v_colors), _ptr(v_sh0), _ptr(v_rest),

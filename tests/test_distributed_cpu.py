@@ -187,3 +187,73 @@ def _async_worker(rank, world, port, out_dir):
 def test_arena_async_all_reduce_returns_one_work_per_run(tmp_path):
     mp.spawn(_async_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "ok")
+
+
+def _worker_sparse(rank, world, port, out_dir):
+    """sparse_allreduce / allreduce_mixed_gradients: the (gaussian_ids, rows) exchange of packed mode
+    with sparse gradients == the dense all-reduce, below and above the dense-fallback threshold, with
+    ragged and empty shards."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from splat_one_b200.distributed import allreduce_mixed_gradients, sparse_allreduce
+
+        N = 1000
+        res = {}
+        for case, nnz_of in (("sparse", lambda r: 37 + 11 * r), ("ragged_empty", lambda r: 0 if r == 1 else 55),
+                             ("dense_fallback", lambda r: 400 + 50 * r)):
+            g = torch.Generator().manual_seed(100 + rank)
+            nnz = nnz_of(rank)
+            ids = torch.randperm(N, generator=g)[:nnz].sort().values
+            vq, vs = torch.randn(nnz, 4, generator=g), torch.randn(nnz, 3, generator=g)
+            gq = torch.sparse_coo_tensor(ids[None], vq, size=(N, 4), is_coalesced=True)
+            gs = torch.sparse_coo_tensor(ids[None], vs, size=(N, 3), is_coalesced=True)
+            counts = []
+            oq, os_ = sparse_allreduce([gq, gs], dense_threshold=0.4, counts_out=counts)
+            assert counts == [nnz_of(r) for r in range(world)]
+            assert oq.is_sparse == (case != "dense_fallback")
+            dq, ds = gq.to_dense(), gs.to_dense()
+            dist.all_reduce(dq)
+            dist.all_reduce(ds)
+            res[case] = ((oq.to_dense() if oq.is_sparse else oq) - dq).abs().max().item(), \
+                        ((os_.to_dense() if os_.is_sparse else os_) - ds).abs().max().item()
+        # mixed dense + sparse parameter gradients through one call
+        g = torch.Generator().manual_seed(7 + rank)
+        P = [torch.zeros(N, 3, requires_grad=True), torch.zeros(N, 4, requires_grad=True), torch.zeros(N, requires_grad=True)]
+        ids = torch.randperm(N, generator=g)[:20].sort().values
+        P[0].grad = torch.randn(N, 3, generator=g)
+        P[1].grad = torch.sparse_coo_tensor(ids[None], torch.randn(20, 4, generator=g), size=(N, 4), is_coalesced=True)
+        P[2].grad = torch.randn(N, generator=g)
+        want = []
+        for p in P:
+            d = p.grad.to_dense().clone() if p.grad.is_sparse else p.grad.clone()
+            dist.all_reduce(d)
+            want.append(d)
+        allreduce_mixed_gradients(P)
+        res["mixed"] = tuple(((p.grad.to_dense() if p.grad.is_sparse else p.grad) - w).abs().max().item()
+                             for p, w in zip(P, want))
+        assert P[1].grad.is_sparse
+        if rank == 0:
+            torch.save(res, os.path.join(out_dir, "sparse.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_sparse_gradient_exchange_equals_dense_allreduce(tmp_path):
+    world = 2
+    mp.spawn(_worker_sparse, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    res = torch.load(os.path.join(tmp_path, "sparse.pt"))
+    for case, errs in res.items():
+        assert max(errs) <= 1e-6, (case, errs)
+
+
+def test_uneven_camera_shards_must_be_announced():
+    from splat_one_b200.distributed import shard_cameras
+
+    vm, Ks = torch.eye(4).repeat(5, 1, 1), torch.eye(3).repeat(5, 1, 1)
+    with pytest.raises(ValueError):
+        shard_cameras(vm, Ks, rank=0, world_size=2)
+    a = shard_cameras(vm, Ks, rank=0, world_size=2, allow_uneven=True)[2].tolist()
+    b = shard_cameras(vm, Ks, rank=1, world_size=2, allow_uneven=True)[2].tolist()
+    assert a == [0, 2, 4] and b == [1, 3]
