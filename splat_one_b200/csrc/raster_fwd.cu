@@ -175,8 +175,8 @@ __device__ __forceinline__ void fwd_quad(float2 &T2, float2 (&pix2)[CDIM], int32
     for (int k = 0; k < CDIM; ++k) pix2[k] = __ffma2_rn(bc2(ncol[k]), nvis2, pix2[k]);
     cur[0] = (nac2.x < 0.f) ? idx : cur[0];
     cur[1] = (nac2.y < 0.f) ? idx : cur[1];
-    T2.x = st0 ? fminf(T2.x, -T2.x) : next_T2.x;  // -|T|
-    T2.y = st1 ? fminf(T2.y, -T2.y) : next_T2.y;
+    T2.x = st0 ? -fabsf(T2.x) : next_T2.x;  // -|T| (operand modifiers of one FSEL)
+    T2.y = st1 ? -fabsf(T2.y) : next_T2.y;
 }
 
 // `quad_masks` (optional, [n_isects] bytes): the geometric quad mask of every pair this kernel stages is
