@@ -291,6 +291,34 @@ def reference_cuda_leg(S, scene, dev, ms_ours: float, reps: int = 20, warm: int 
                     "raw pybind calls, same scene / GPU / run; device-resident like `value`"}
 
 
+# N > 1: which gradient exchange the timed loop uses.  "peer" (default) = this library's own kernels over
+# NVLink peer memory (splat_one_b200.distributed.PeerExchange, csrc/peer.cu), falling back to "nccl" (all-gather
+# + all-reduce library collectives) if the platform cannot map symmetric memory; the other one is A/B-timed.
+EXCHANGE = os.environ.get("B200SPLAT_DP_EXCHANGE", "peer")
+
+
+def make_peer(n_gaussians, cams_per_rank, params, world, note=None):
+    """PeerExchange sized for `params`, or None (with the reason in note["error"]) where unavailable."""
+    if world <= 1 or EXCHANGE == "nccl":
+        return None
+    from splat_one_b200.distributed import PeerExchange, arena_layout
+
+    try:
+        return PeerExchange(n_gaussians, cams_per_rank, arena_floats=arena_layout(params)[1],
+                            use_multicast={"1": True, "0": False}.get(os.environ.get("B200SPLAT_DP_MULTICAST", "")))
+    except Exception as e:  # no peer mapping on this platform: the NCCL exchange is used and the line says so
+        if note is not None:
+            note["error"] = f"{type(e).__name__}: {e}"[:300]
+        return None
+
+
+def exchange_kind(peer):
+    if peer is None:
+        return "nccl: all-gather of colour cotangents + all-reduce of the arena"
+    return ("peer kernels over NVLink symmetric memory: cotangents read in place by the colour backward + two-shot "
+            + ("multimem (switch-reduced)" if peer.multicast_base else "peer load/store") + " arena all-reduce")
+
+
 def dp_parity_check(S, dist, world, rank, dev):
     """Outside the timed region, N > 1: gradients of the camera-sharded step (each rank one camera,
     colour-cotangent all-gather + arena all-reduce) against the SAME batch rendered by one process
@@ -311,8 +339,9 @@ def dp_parity_check(S, dist, world, rank, dev):
         rc, ra, _ = S.rasterization(*P, sc["viewmats"][cams].to(dev), sc["Ks"][cams].to(dev), W_, H_,
                                     sh_degree=SH_DEGREE, packed=False)
         if dp:
-            arena = GradArena(P)
-            with arena.sink(), camera_parallel() as cp:
+            peer = make_peer(N_, 1, P, world)
+            arena = GradArena(P, peer=peer)
+            with arena.sink(), camera_parallel(peer=peer) as cp:
                 torch.autograd.backward([rc, ra], [vc_all[cams], va_all[cams]])
             arena.gather_from_params()
             arena.all_reduce(skip_ptrs=cp.reduced_ptrs)
@@ -347,7 +376,8 @@ def extra_config(S, dist, name, world, rank, dev, steps: int = 10, warm: int = 3
     g = torch.Generator().manual_seed(2000 + rank)
     vc = torch.randn(1, H_, W_, 3, generator=g).to(dev)
     va = torch.randn(1, H_, W_, 1, generator=g).to(dev)
-    arena = GradArena(P) if (world > 1 and name == "C") else None
+    peer = make_peer(n, 1, P, world) if name == "C" else None
+    arena = GradArena(P, peer=peer) if (world > 1 and name == "C") else None
     counts = []
 
     def step():
@@ -355,7 +385,7 @@ def extra_config(S, dist, name, world, rank, dev, steps: int = 10, warm: int = 3
             p.grad = None
         rc, ra, meta = S.rasterization(*P, vm, Ks, W_, H_, sh_degree=SH_DEGREE, **kw)
         if arena is not None:
-            with arena.sink(), camera_parallel() as cp:
+            with arena.sink(), camera_parallel(peer=peer) as cp:
                 torch.autograd.backward([rc, ra], [vc, va])
             arena.gather_from_params()
             arena.all_reduce(skip_ptrs=cp.reduced_ptrs)
@@ -384,9 +414,9 @@ def extra_config(S, dist, name, world, rank, dev, steps: int = 10, warm: int = 3
     ms = t.item() / steps
     out = {"ms_per_step": ms, "Mpix_per_s": world * H_ * W_ / (ms * 1e-3) / 1e6, "steps": steps, "warmup": warm,
            "n_gaussians": n, "image": f"{W_}x{H_}", "cameras": world, "n_isects_rank0": int(meta["flatten_ids"].numel()),
-           "mode": "unpacked, dense gradients: cotangent all-gather + arena all-reduce" if name == "C" else
+           "mode": ("unpacked, dense gradients; exchange = " + exchange_kind(peer)) if name == "C" else
                    "packed, sparse gradients: (gaussian_ids, rows) all-gather with dense fallback above 0.4 visible"}
-    del P, sc
+    del P, sc, arena, peer
     torch.cuda.empty_cache()
     return out
 
@@ -411,6 +441,9 @@ def run_gpu(args):
         raise SystemExit("bench.py needs a GPU (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # host side of a rank next to its GPU (pinned buffers are allocated below): matters for e2e at N = 8
+    from splat_one_b200.distributed import bind_host_to_gpu
+    host_cpus = bind_host_to_gpu(local_rank) if os.environ.get("B200SPLAT_NO_BIND", "0") != "1" else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -426,17 +459,22 @@ def run_gpu(args):
     vc_host = torch.randn(C_local, HEIGHT, WIDTH, 3, generator=g).pin_memory()
     va_host = torch.randn(C_local, HEIGHT, WIDTH, 1, generator=g).pin_memory()
     vc, va = vc_host.to(dev), va_host.to(dev)
-    arena = GradArena(params) if world > 1 else None
+    peer_note = {}
+    peer = make_peer(N_GAUSS, C_local, params, world, peer_note)
+    arena_nccl = GradArena(params) if world > 1 else None
+    arena_peer = GradArena(params, peer=peer) if peer is not None else None
 
-    def step(defer=DEFER):
+    def step(defer=DEFER, use_peer=True):
         for p in params:
             p.grad = None
         rc, ra, meta = S.rasterization(*params, vm, Ks, WIDTH, HEIGHT, sh_degree=SH_DEGREE, packed=False)
         skip = ()
+        px = peer if use_peer else None
+        arena = arena_peer if px is not None else arena_nccl
         if arena is not None:
             # SH / quats / scales gradients are produced inside the arena; the SH gradient comes
-            # out already summed over ranks (colour-cotangent all-gather, distributed.py)
-            with arena.sink(), camera_parallel(defer=defer) as cp:
+            # out already summed over ranks (colour-cotangent exchange, distributed.py)
+            with arena.sink(), camera_parallel(defer=defer, peer=px) as cp:
                 torch.autograd.backward([rc, ra], [vc, va])
             skip = cp.reduced_ptrs
         else:
@@ -498,22 +536,28 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = t.item() / args.steps
-    # A/B of the other exchange order (N > 1, outside `value`): a few steps with the overlapped exchange
-    # when the timed loop used the plain one and vice versa
-    ms_other = None
+    # A/B of the other exchanges (N > 1, outside `value`): a few steps each with the NCCL collectives in
+    # plain order and in the overlapped (deferred) order
+    ms_ab = {}
     if world > 1:
         n_ab = max(min(args.steps, 30), 5)
-        for _ in range(3):
-            step(not DEFER)
-        barrier()
-        e0.record()
-        for _ in range(n_ab):
-            step(not DEFER)
-        e1.record()
-        barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_other = t.item() / n_ab
+        for label, kw in (("peer_plain", dict(defer=False, use_peer=True)), ("peer_overlapped", dict(defer=True, use_peer=True)),
+                          ("nccl_plain", dict(defer=False, use_peer=False)), ("nccl_deferred", dict(defer=True, use_peer=False))):
+            if kw["use_peer"] == (peer is not None) and kw["defer"] == DEFER:
+                continue  # that is the timed loop itself
+            if kw["use_peer"] and peer is None:
+                continue
+            for _ in range(3):
+                step(**kw)
+            barrier()
+            e0.record()
+            for _ in range(n_ab):
+                step(**kw)
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_ab[label] = t.item() / n_ab
     launches = wrapper.profiler.launches()
     timed_stages = wrapper.profiler.summary_ms()
     # full stage table: a few more steps with every native call bracketed (not part of `value`)
@@ -580,8 +624,10 @@ def run_gpu(args):
         prefetch(i ^ 1)  # cotangents of the NEXT step
         main.wait_event(cot_ready[i])
         vc_d, va_d = cot[i]
+        px = peer
+        arena = arena_peer if px is not None else arena_nccl
         if arena is not None:
-            with arena.sink(), camera_parallel(defer=DEFER) as cp:
+            with arena.sink(), camera_parallel(defer=DEFER, peer=px) as cp:
                 torch.autograd.backward([rc_, ra_], [vc_d, va_d])
             if DEFER:
                 cp.finish(arena)
@@ -715,7 +761,10 @@ def run_gpu(args):
                        "visible_pairs": V, "n_isects": I, "tiles_per_visible_gaussian": round(I / max(V, 1), 3),
                        "listed_pairs_per_pixel": round(I * 256 / max(P, 1), 1),
                        "l2_policy": "per-step working set ~1 GB > 126 MB L2",
-                       "parallelism": f"camera-sharded dp{world}" + (" + all-gather of colour cotangents (12 MB/rank) + NCCL allreduce of 44 MB grads" if world > 1 else "")},
+                       "parallelism": f"camera-sharded dp{world}" + (
+                           "; gradient exchange (12 MB/rank colour cotangents, 44 MB arena) = " + exchange_kind(peer)
+                           + (", colour backward overlapped with projection backward + all-reduce" if DEFER else "")
+                           if world > 1 else "")},
             "clocks": clocks,
             "e2e": {"value": world * C_local * HEIGHT * WIDTH / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s",
                     "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -734,8 +783,11 @@ def run_gpu(args):
             "cpu_baseline": cpu,
             "reference_cuda": ref_cuda_leg,
             "dp_parity_max_rel": dp_parity,
-            "exchange_order": {"timed": "deferred (overlapped)" if DEFER else "plain",
-                               "ms_per_step_other_order": ms_other} if world > 1 else None,
+            "host_binding": (f"{len(host_cpus)} cores nearest to the GPU (NVML affinity)" if host_cpus else "none"),
+            "exchange": {"timed": ("peer" if peer is not None else "nccl") + ("_overlapped" if DEFER else "_plain"),
+                         "multicast": bool(peer is not None and peer.multicast_base),
+                         "peer_unavailable": peer_note.get("error"),
+                         "ms_per_step_other": ms_ab} if world > 1 else None,
             "config_C": extras.get("C"),
             "config_E": extras.get("E"),
         }

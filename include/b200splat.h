@@ -489,6 +489,54 @@ B200SPLAT_API int b200splat_sh_colors_staged_bwd(
     float *v_sh0, float *v_rest, float *v_means,
     uint32_t means_cam_begin, uint32_t means_cam_end, void *stream);
 
+/* ------------------------------------------------------------------------------------
+ * e   camera-parallel peer exchange (no counterpart in the reference, whose
+ *     multi-GPU mode is Gaussian-sharded: G/rendering.py:397-478).  The colour backward of C =
+ *     W * cams_per_block cameras reads the pre-masked colour cotangents and camera centres of camera
+ *     block b IN PLACE from the memory of rank b over NVLink: peer_bases is a DEVICE array of W base
+ *     addresses mapped into this process (torch symmetric memory: buffer_ptrs_dev); block b lives at
+ *     peer_bases[b] + offset_bytes = { campos [cams_per_block][3] fp32, padding up to hdr_floats
+ *     floats, v_colors [cams_per_block][N][3] fp32 }.  The caller orders the peers' writes before this
+ *     call (symmetric-memory barrier on the same stream).  Otherwise as the non-peer calls with
+ *     radii == colors == NULL: coefficient gradient summed over all C cameras, direction gradient over
+ *     cameras [means_cam_begin, means_cam_end).
+ * ---------------------------------------------------------------------------------- */
+B200SPLAT_API int b200splat_sh_colors_bwd_peer(
+    uint32_t C, uint32_t N, uint32_t K, uint32_t degrees_to_use,
+    const float *means, const float *coeffs,
+    const void *peer_bases, uint64_t offset_bytes, uint32_t cams_per_block, uint32_t hdr_floats,
+    float *v_coeffs, float *v_means,
+    uint32_t means_cam_begin, uint32_t means_cam_end, void *stream);
+
+B200SPLAT_API int b200splat_sh_colors_staged_bwd_peer(
+    uint32_t C, uint32_t N, uint32_t K, uint32_t degrees_to_use,
+    const float *means, const float *sh0, const float *rest,
+    const void *peer_bases, uint64_t offset_bytes, uint32_t cams_per_block, uint32_t hdr_floats,
+    float *v_sh0, float *v_rest, float *v_means,
+    uint32_t means_cam_begin, uint32_t means_cam_end, void *stream);
+
+/* The exchange itself, as kernels over the same symmetric buffers (csrc/peer.cu).  flag_bases /
+ * peer_bases: DEVICE arrays of W mapped base addresses (one symmetric buffer per rank, the same
+ * offsets valid in each); the flag region (b200splat_peer_flag_bytes(W) bytes at flag_offset_bytes,
+ * zero-initialised once by the caller) carries the release/acquire handshakes.  All ranks must issue
+ * the same sequence of these calls.
+ *   publish:   campos [C,3] and the cotangents masked by colors > 0 ([C,N,3]) -> this rank's block
+ *              (layout above; camera slots C..cams_per_block-1 are zero-filled);
+ *   barrier:   returns (in stream order) once every rank has reached it: the peers' blocks are readable;
+ *   allreduce: in-place SUM over ranks of n_floats fp32 at offset_bytes of every rank's buffer, two-shot
+ *              (rank r reduces and re-broadcasts slice r).  multicast_base != 0: the NVSwitch multicast
+ *              alias of the W buffers (multimem.ld_reduce / multimem.st); 0: plain peer loads and stores. */
+B200SPLAT_API size_t b200splat_peer_flag_bytes(uint32_t world);
+B200SPLAT_API int b200splat_peer_publish_cotangents(
+    uint32_t C, uint32_t N, uint32_t cams_per_block, uint32_t hdr_floats,
+    const float *campos, const float *colors, const float *v_colors, float *block, void *stream);
+B200SPLAT_API int b200splat_peer_barrier(
+    uint32_t world, uint32_t rank, const void *flag_bases, uint64_t flag_offset_bytes, void *stream);
+B200SPLAT_API int b200splat_peer_allreduce_f32(
+    uint32_t world, uint32_t rank, const void *peer_bases, uint64_t multicast_base,
+    uint64_t offset_bytes, uint64_t n_floats, const void *flag_bases, uint64_t flag_offset_bytes,
+    void *stream);
+
 /* viewmats = inverse(camtoworlds) [C,4,4] (gsplat_trainer.py:483), adjugate in double, no
  * host synchronisation (torch.linalg.inv syncs to report singular inputs). */
 B200SPLAT_API int b200splat_invert_4x4(uint32_t C, const float *mats, float *out, void *stream);

@@ -17,7 +17,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("B200SPLAT_LIB", _PKG / "libb200splat.so"))
 
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 _P = c_void_p
 _U32 = c_uint32
@@ -88,6 +88,13 @@ SIGNATURES = {
     "b200splat_compute_relocation": (_I, [_U32, _P, _P, _P, _P, _I, _P, _P, _P]),
     "b200splat_sh_colors_staged_smem_bytes": (c_size_t, [_U32, _I]),
     "b200splat_sh_colors_staged_fwd": (_I, [_U32, _U32, _U32, _U32, _P, _P, _P, _P, _P, _P, _P]),
+    "b200splat_sh_colors_bwd_peer": (_I, [_U32, _U32, _U32, _U32, _P, _P, _P, _U64, _U32, _U32, _P, _P, _U32, _U32, _P]),
+    "b200splat_sh_colors_staged_bwd_peer": (_I, [_U32, _U32, _U32, _U32, _P, _P, _P, _P, _U64, _U32, _U32, _P, _P, _P,
+                                                 _U32, _U32, _P]),
+    "b200splat_peer_flag_bytes": (c_size_t, [_U32]),
+    "b200splat_peer_publish_cotangents": (_I, [_U32, _U32, _U32, _U32, _P, _P, _P, _P, _P]),
+    "b200splat_peer_barrier": (_I, [_U32, _U32, _P, _U64, _P]),
+    "b200splat_peer_allreduce_f32": (_I, [_U32, _U32, _P, _U64, _U64, _U64, _P, _U64, _P]),
     "b200splat_sh_colors_staged_bwd": (_I, [_U32, _U32, _U32, _U32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _U32, _U32,
                                             _P]),
     "b200splat_invert_4x4": (_I, [_U32, _P, _P, _P]),

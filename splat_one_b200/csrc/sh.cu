@@ -242,14 +242,51 @@ sh_colors_fwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, int per_v
     colors[3 * e] = r; colors[3 * e + 1] = g; colors[3 * e + 2] = b;
 }
 
+// Where the colour cotangents and the camera centres of camera c come from in the colour backward:
+// one local pair of arrays, or — camera-parallel peer exchange (splat_one_b200/distributed.py) — the
+// symmetric buffers of the ranks, read IN PLACE over NVLink: block b = c / cams_per_block lives at
+// bases[b] + offset_bytes and holds {campos [cams_per_block][3], padding to hdr_floats,
+// v_colors [cams_per_block][N][3]} (pre-masked: zero where invisible or clamped).  The all-gather of
+// the plain exchange becomes the kernel's own loads, overlapped with its gradient writes.
+struct CamSource {
+    const float *v_colors;
+    const float *campos;
+    const unsigned long long *bases;  // device array, one base address per rank; nullptr: local arrays
+    unsigned long long offset_bytes;
+    uint32_t cams_per_block;
+    uint32_t hdr_floats;
+};
+
+__device__ __forceinline__ const float *cam_block(const CamSource &s, uint32_t c, uint32_t &local) {
+    const uint32_t b = c / s.cams_per_block;
+    local = c - b * s.cams_per_block;
+    return reinterpret_cast<const float *>(s.bases[b] + s.offset_bytes);
+}
+// row base of camera c's cotangents ([N,3])
+__device__ __forceinline__ const float *cam_cotangents(const CamSource &s, uint32_t c, uint32_t N) {
+    if (s.bases == nullptr) return s.v_colors + (size_t)c * N * 3;
+    uint32_t l;
+    const float *blk = cam_block(s, c, l);
+    return blk + s.hdr_floats + (size_t)l * N * 3;
+}
+__device__ __forceinline__ const float *cam_centre(const CamSource &s, uint32_t c) {
+    if (s.bases == nullptr) return s.campos + 3 * (size_t)c;
+    uint32_t l;
+    const float *blk = cam_block(s, c, l);
+    return blk + 3 * l;
+}
+// CB = cameras whose cotangents are fetched together (loads in flight per thread): 1 for local arrays,
+// kPeerCamBatch when they are NVLink loads
+constexpr int kPeerCamBatch = 4;
+
 // One thread per Gaussian, loop over cameras: v_coeffs (shared table) and v_means are
 // written once, without atomics.  The clamp passes gradient where the clamped colour > 0.
-template <int NB>
+template <int NB, int CB>
 __global__ void __launch_bounds__(kThreads)
 sh_colors_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, int per_view, const float *__restrict__ means,
-                     const float *__restrict__ campos, const float *__restrict__ coeffs,
+                     const CamSource src, const float *__restrict__ coeffs,
                      const int32_t *__restrict__ radii, const float *__restrict__ colors,
-                     const float *__restrict__ v_colors, float *__restrict__ v_coeffs, float *__restrict__ v_means,
+                     float *__restrict__ v_coeffs, float *__restrict__ v_means,
                      uint32_t means_cam_begin, uint32_t means_cam_end) {
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
@@ -272,11 +309,26 @@ sh_colors_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, int per_v
             for (uint32_t k = NB * 3; k < K * 3; k++) vrow[k] = 0.f;
         }
     };
-    for (uint32_t c = 0; c < C; ++c) {
+    for (uint32_t c0 = 0; c0 < C; c0 += CB) {
+      // the cotangents of CB cameras are requested before any is consumed: with the peer exchange
+      // they are NVLink loads (microseconds of latency)
+      float vin[CB][3];
+#pragma unroll
+      for (int jc = 0; jc < CB; ++jc) {
+          vin[jc][0] = vin[jc][1] = vin[jc][2] = 0.f;
+          if (c0 + jc < C) {
+              const float *vrow = cam_cotangents(src, c0 + jc, N) + 3 * (size_t)n;
+              vin[jc][0] = vrow[0]; vin[jc][1] = vrow[1]; vin[jc][2] = vrow[2];
+          }
+      }
+#pragma unroll
+      for (int jc = 0; jc < CB; ++jc) {
+        const uint32_t c = c0 + jc;
+        if (c >= C) break;
         const uint64_t e = (uint64_t)c * N + n;
         // radii == NULL / colors == NULL: v_colors is PRE-MASKED (zero where the Gaussian is
         // invisible or the colour was clamped) — the layout the camera-parallel exchange gathers
-        float vr = v_colors[3 * e], vg = v_colors[3 * e + 1], vb = v_colors[3 * e + 2];
+        float vr = vin[jc][0], vg = vin[jc][1], vb = vin[jc][2];
         if (colors != nullptr) {
             vr = colors[3 * e] > 0.f ? vr : 0.f;
             vg = colors[3 * e + 1] > 0.f ? vg : 0.f;
@@ -286,7 +338,8 @@ sh_colors_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, int per_v
         if (visible) {
             float x = 0.f, y = 0.f, z = 0.f, inorm = 0.f;
             if (NB > 1) {
-                const float dx = mx - campos[3 * c], dy = my - campos[3 * c + 1], dz = mz - campos[3 * c + 2];
+                const float *cp = cam_centre(src, c);
+                const float dx = mx - cp[0], dy = my - cp[1], dz = mz - cp[2];
                 inorm = rsqrtf(dx * dx + dy * dy + dz * dz);
                 x = dx * inorm; y = dy * inorm; z = dz * inorm;
             }
@@ -315,6 +368,7 @@ sh_colors_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, int per_v
 #pragma unroll
             for (int k = 0; k < NB * 3; k++) vc[k] = 0.f;
         }
+      }
     }
     if (!per_view) flush(v_coeffs + (uint64_t)n * K * 3);
     if (v_means != nullptr) { v_means[3 * n] = vmx; v_means[3 * n + 1] = vmy; v_means[3 * n + 2] = vmz; }
@@ -603,12 +657,12 @@ sh_colors_staged_fwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, co
 // CFS: the coefficient rows stay in shared memory (a second buffer) and are read from there
 // inside the basis loop instead of living in 3 (NB-1) registers: 140 -> ~96 registers, 12 -> 20
 // warps per SM.  Only for odd row lengths (scalar row reads are conflict-free then).
-template <int NB, bool SPLIT, bool CFS>
+template <int NB, bool SPLIT, bool CFS, int CB>
 __global__ void __launch_bounds__(32 * kStageWarps, CFS ? 5 : 1)
 sh_colors_staged_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, const float *__restrict__ means,
-                            const float *__restrict__ campos, const float *__restrict__ sh0,
+                            const CamSource src, const float *__restrict__ sh0,
                             const float *__restrict__ rest, const int32_t *__restrict__ radii,
-                            const float *__restrict__ colors, const float *__restrict__ v_colors,
+                            const float *__restrict__ colors,
                             float *__restrict__ v_sh0, float *__restrict__ v_rest, float *__restrict__ v_means,
                             uint32_t means_cam_begin, uint32_t means_cam_end) {
     constexpr int K0 = SPLIT ? 1 : 0;
@@ -646,9 +700,22 @@ sh_colors_staged_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, co
     for (int k = 0; k < NFA; k++) vc[k] = 0.f;
     float vmx = 0.f, vmy = 0.f, vmz = 0.f;
     const float mx = __ldg(means + 3 * (size_t)n), my = __ldg(means + 3 * (size_t)n + 1), mz = __ldg(means + 3 * (size_t)n + 2);
-    for (uint32_t c = 0; c < C && mine; ++c) {
+    for (uint32_t c0 = 0; c0 < C && mine; c0 += CB) {
+      float vin[CB][3];
+#pragma unroll
+      for (int jc = 0; jc < CB; ++jc) {
+          vin[jc][0] = vin[jc][1] = vin[jc][2] = 0.f;
+          if (c0 + jc < C) {
+              const float *vrow = cam_cotangents(src, c0 + jc, N) + 3 * (size_t)n;
+              vin[jc][0] = vrow[0]; vin[jc][1] = vrow[1]; vin[jc][2] = vrow[2];
+          }
+      }
+#pragma unroll
+      for (int jc = 0; jc < CB; ++jc) {
+        const uint32_t c = c0 + jc;
+        if (c >= C) break;
         const uint64_t e = (uint64_t)c * N + n;
-        float vr = v_colors[3 * e], vg = v_colors[3 * e + 1], vb = v_colors[3 * e + 2];
+        float vr = vin[jc][0], vg = vin[jc][1], vb = vin[jc][2];
         if (colors != nullptr) {
             vr = colors[3 * e] > 0.f ? vr : 0.f;
             vg = colors[3 * e + 1] > 0.f ? vg : 0.f;
@@ -658,7 +725,8 @@ sh_colors_staged_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, co
         if (!visible) continue;
         float x = 0.f, y = 0.f, z = 0.f, inorm = 0.f;
         if (NB > 1) {
-            const float dx = mx - campos[3 * c], dy = my - campos[3 * c + 1], dz = mz - campos[3 * c + 2];
+            const float *cp = cam_centre(src, c);
+            const float dx = mx - cp[0], dy = my - cp[1], dz = mz - cp[2];
             inorm = rsqrtf(dx * dx + dy * dy + dz * dz);
             x = dx * inorm; y = dy * inorm; z = dz * inorm;
         }
@@ -681,6 +749,7 @@ sh_colors_staged_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, co
                 vc[j] += B * vr; vc[j + 1] += B * vg; vc[j + 2] += B * vb;
             });
         }
+      }
     }
     if (R > 0) {
         if (mine) {
@@ -769,18 +838,20 @@ extern "C" int b200splat_sh_colors_fwd(uint32_t C, uint32_t N, uint32_t K, uint3
     return 0;
 }
 
-extern "C" int b200splat_sh_colors_bwd(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, int per_view,
-                                       const float *means, const float *campos, const float *coeffs,
-                                       const int32_t *radii, const float *colors, const float *v_colors,
-                                       float *v_coeffs, float *v_means, uint32_t means_cam_begin,
-                                       uint32_t means_cam_end, void *stream) {
-    const char *where = "b200splat_sh_colors_bwd";
-    B2S_REQUIRE(deg <= 4, where, "degrees_to_use must be <= 4");
-    B2S_REQUIRE((deg + 1) * (deg + 1) <= K, where, "K too small for degrees_to_use");
-    if (N == 0) return 0;
+static int launch_colors_bwd(const char *where, uint32_t C, uint32_t N, uint32_t K, uint32_t deg, int per_view,
+                             const float *means, const CamSource &src, const float *coeffs, const int32_t *radii,
+                             const float *colors, float *v_coeffs, float *v_means, uint32_t means_cam_begin,
+                             uint32_t means_cam_end, cudaStream_t st) {
     const unsigned grid = div_up(N, kThreads);
-    cudaStream_t st = (cudaStream_t)stream;
-#define B2S_SHC(NBV) sh_colors_bwd_kernel<NBV><<<grid, kThreads, 0, st>>>(C, N, K, deg, per_view, means, campos, coeffs, radii, colors, v_colors, v_coeffs, v_means, means_cam_begin, means_cam_end)
+#define B2S_SHC(NBV)                                                                                                  \
+    do {                                                                                                              \
+        if (src.bases != nullptr)                                                                                     \
+            sh_colors_bwd_kernel<NBV, kPeerCamBatch><<<grid, kThreads, 0, st>>>(                                      \
+                C, N, K, deg, per_view, means, src, coeffs, radii, colors, v_coeffs, v_means, means_cam_begin, means_cam_end); \
+        else                                                                                                          \
+            sh_colors_bwd_kernel<NBV, 1><<<grid, kThreads, 0, st>>>(                                                  \
+                C, N, K, deg, per_view, means, src, coeffs, radii, colors, v_coeffs, v_means, means_cam_begin, means_cam_end); \
+    } while (0)
     switch (deg) {
         case 0: B2S_SHC(1); break;
         case 1: B2S_SHC(4); break;
@@ -791,6 +862,40 @@ extern "C" int b200splat_sh_colors_bwd(uint32_t C, uint32_t N, uint32_t K, uint3
 #undef B2S_SHC
     B2S_CHECK_LAUNCH(where);
     return 0;
+}
+
+extern "C" int b200splat_sh_colors_bwd(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, int per_view,
+                                       const float *means, const float *campos, const float *coeffs,
+                                       const int32_t *radii, const float *colors, const float *v_colors,
+                                       float *v_coeffs, float *v_means, uint32_t means_cam_begin,
+                                       uint32_t means_cam_end, void *stream) {
+    const char *where = "b200splat_sh_colors_bwd";
+    B2S_REQUIRE(deg <= 4, where, "degrees_to_use must be <= 4");
+    B2S_REQUIRE((deg + 1) * (deg + 1) <= K, where, "K too small for degrees_to_use");
+    if (N == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const CamSource src{v_colors, campos, nullptr, 0ull, 1u, 0u};
+    return launch_colors_bwd(where, C, N, K, deg, per_view, means, src, coeffs, radii, colors, v_coeffs, v_means,
+                             means_cam_begin, means_cam_end, st);
+}
+
+// camera-parallel peer exchange: campos / v_colors of camera block b are read from peer_bases[b] + offset_bytes
+// (device array of per-rank base addresses, e.g. the buffer_ptrs_dev of a torch symmetric-memory handle)
+extern "C" int b200splat_sh_colors_bwd_peer(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, const float *means,
+                                            const float *coeffs, const void *peer_bases, uint64_t offset_bytes,
+                                            uint32_t cams_per_block, uint32_t hdr_floats, float *v_coeffs,
+                                            float *v_means, uint32_t means_cam_begin, uint32_t means_cam_end,
+                                            void *stream) {
+    const char *where = "b200splat_sh_colors_bwd_peer";
+    B2S_REQUIRE(deg <= 4, where, "degrees_to_use must be <= 4");
+    B2S_REQUIRE((deg + 1) * (deg + 1) <= K, where, "K too small for degrees_to_use");
+    B2S_REQUIRE(peer_bases != nullptr && cams_per_block > 0 && hdr_floats >= 3 * cams_per_block, where,
+                "peer table, cameras per block and header size are required");
+    if (N == 0) return 0;
+    const CamSource src{nullptr, nullptr, reinterpret_cast<const unsigned long long *>(peer_bases), offset_bytes,
+                        cams_per_block, hdr_floats};
+    return launch_colors_bwd(where, C, N, K, deg, 0, means, src, coeffs, nullptr, nullptr, v_coeffs, v_means,
+                             means_cam_begin, means_cam_end, (cudaStream_t)stream);
 }
 
 static int packed_fwd_impl(const char *where, uint32_t nnz, uint32_t C, uint32_t N, uint32_t K, uint32_t deg,
@@ -868,24 +973,24 @@ static int launch_staged_fwd(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, c
     return 0;
 }
 
-template <bool SPLIT>
-static int launch_staged_bwd(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, const float *means, const float *campos,
+template <bool SPLIT, int CB>
+static int launch_staged_bwd_cb(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, const float *means, const CamSource &src,
                              const float *sh0, const float *rest, const int32_t *radii, const float *colors,
-                             const float *v_colors, float *v_sh0, float *v_rest, float *v_means, uint32_t cb,
+                             float *v_sh0, float *v_rest, float *v_means, uint32_t cb,
                              uint32_t ce, size_t smem, cudaStream_t st) {
     const unsigned grid = div_up(N, 32 * kStageWarps);
     const uint32_t R = (K - (SPLIT ? 1 : 0)) * 3;
-    const bool cfs = stage_row_stride(R) == R && 2 * smem <= 48 * 1024 && tuning_variant() != 7;
+    const bool cfs = stage_row_stride(R) == R && 2 * smem <= 48 * 1024;
 #define B2S_SHS(NBV)                                                                                                 \
     do {                                                                                                             \
         if (cfs) {                                                                                                   \
-            sh_colors_staged_bwd_kernel<NBV, SPLIT, true><<<grid, 32 * kStageWarps, 2 * smem, st>>>(                 \
-                C, N, K, deg, means, campos, sh0, rest, radii, colors, v_colors, v_sh0, v_rest, v_means, cb, ce);    \
+            sh_colors_staged_bwd_kernel<NBV, SPLIT, true, CB><<<grid, 32 * kStageWarps, 2 * smem, st>>>(                 \
+                C, N, K, deg, means, src, sh0, rest, radii, colors, v_sh0, v_rest, v_means, cb, ce);                 \
         } else {                                                                                                     \
-            auto kern = sh_colors_staged_bwd_kernel<NBV, SPLIT, false>;                                              \
+            auto kern = sh_colors_staged_bwd_kernel<NBV, SPLIT, false, CB>;                                              \
             if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            kern<<<grid, 32 * kStageWarps, smem, st>>>(C, N, K, deg, means, campos, sh0, rest, radii, colors,        \
-                                                       v_colors, v_sh0, v_rest, v_means, cb, ce);                    \
+            kern<<<grid, 32 * kStageWarps, smem, st>>>(C, N, K, deg, means, src, sh0, rest, radii, colors,           \
+                                                       v_sh0, v_rest, v_means, cb, ce);                              \
         }                                                                                                            \
     } while (0)
     switch (deg) {
@@ -897,6 +1002,18 @@ static int launch_staged_bwd(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, c
     }
 #undef B2S_SHS
     return 0;
+}
+
+template <bool SPLIT>
+static int launch_staged_bwd(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, const float *means, const CamSource &src,
+                             const float *sh0, const float *rest, const int32_t *radii, const float *colors,
+                             float *v_sh0, float *v_rest, float *v_means, uint32_t cb,
+                             uint32_t ce, size_t smem, cudaStream_t st) {
+    if (src.bases != nullptr)
+        return launch_staged_bwd_cb<SPLIT, kPeerCamBatch>(C, N, K, deg, means, src, sh0, rest, radii, colors, v_sh0, v_rest,
+                                                          v_means, cb, ce, smem, st);
+    return launch_staged_bwd_cb<SPLIT, 1>(C, N, K, deg, means, src, sh0, rest, radii, colors, v_sh0, v_rest, v_means, cb,
+                                          ce, smem, st);
 }
 
 extern "C" int b200splat_sh_colors_staged_fwd(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, const float *means,
@@ -929,12 +1046,40 @@ extern "C" int b200splat_sh_colors_staged_bwd(uint32_t C, uint32_t N, uint32_t K
     const size_t smem = b200splat_sh_colors_staged_smem_bytes(K, sh0 != nullptr);
     B2S_REQUIRE(smem <= 200 * 1024, where, "K too large for the staged colour kernels");
     cudaStream_t st = (cudaStream_t)stream;
+    const CamSource src{v_colors, campos, nullptr, 0ull, 1u, 0u};
     if (sh0 != nullptr)
-        launch_staged_bwd<true>(C, N, K, deg, means, campos, sh0, rest, radii, colors, v_colors, v_sh0, v_rest, v_means,
+        launch_staged_bwd<true>(C, N, K, deg, means, src, sh0, rest, radii, colors, v_sh0, v_rest, v_means,
                                 means_cam_begin, means_cam_end, smem, st);
     else
-        launch_staged_bwd<false>(C, N, K, deg, means, campos, sh0, rest, radii, colors, v_colors, v_sh0, v_rest,
+        launch_staged_bwd<false>(C, N, K, deg, means, src, sh0, rest, radii, colors, v_sh0, v_rest,
                                  v_means, means_cam_begin, means_cam_end, smem, st);
+    B2S_CHECK_LAUNCH(where);
+    return 0;
+}
+
+extern "C" int b200splat_sh_colors_staged_bwd_peer(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, const float *means,
+                                                   const float *sh0, const float *rest, const void *peer_bases,
+                                                   uint64_t offset_bytes, uint32_t cams_per_block, uint32_t hdr_floats,
+                                                   float *v_sh0, float *v_rest, float *v_means,
+                                                   uint32_t means_cam_begin, uint32_t means_cam_end, void *stream) {
+    const char *where = "b200splat_sh_colors_staged_bwd_peer";
+    B2S_REQUIRE(deg <= 4, where, "degrees_to_use must be <= 4");
+    B2S_REQUIRE((deg + 1) * (deg + 1) <= K, where, "K too small for degrees_to_use");
+    B2S_REQUIRE(peer_bases != nullptr && cams_per_block > 0 && hdr_floats >= 3 * cams_per_block, where,
+                "peer table, cameras per block and header size are required");
+    if (N == 0) return 0;
+    B2S_REQUIRE((sh0 != nullptr) == (v_sh0 != nullptr), where, "sh0 and v_sh0 go together");
+    const size_t smem = b200splat_sh_colors_staged_smem_bytes(K, sh0 != nullptr);
+    B2S_REQUIRE(smem <= 200 * 1024, where, "K too large for the staged colour kernels");
+    cudaStream_t st = (cudaStream_t)stream;
+    const CamSource src{nullptr, nullptr, reinterpret_cast<const unsigned long long *>(peer_bases), offset_bytes,
+                        cams_per_block, hdr_floats};
+    if (sh0 != nullptr)
+        launch_staged_bwd<true>(C, N, K, deg, means, src, sh0, rest, nullptr, nullptr, v_sh0, v_rest, v_means,
+                                means_cam_begin, means_cam_end, smem, st);
+    else
+        launch_staged_bwd<false>(C, N, K, deg, means, src, sh0, rest, nullptr, nullptr, v_sh0, v_rest, v_means,
+                                 means_cam_begin, means_cam_end, smem, st);
     B2S_CHECK_LAUNCH(where);
     return 0;
 }

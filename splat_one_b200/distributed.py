@@ -30,8 +30,13 @@ class camera_parallel:
     `backward()` already global.  `reduced_ptrs` lists the parameters (by data_ptr) this
     happened for; `GradArena.all_reduce(skip_ptrs=...)` then leaves them out."""
 
-    def __init__(self, group=None, defer: bool = False, n_cameras_global: Optional[int] = None):
-        """`n_cameras_global`: size of the global camera batch when it is NOT a multiple of the world
+    def __init__(self, group=None, defer: bool = False, n_cameras_global: Optional[int] = None,
+                 peer: Optional["PeerExchange"] = None):
+        """`peer`: a `PeerExchange` — the colour cotangents are then published into this rank's symmetric
+        buffer and the colour backward kernel reads the other ranks' blocks IN PLACE over NVLink (no
+        all-gather, no gathered copy).  With `defer=True` that kernel runs on a side stream, overlapped with the
+        projection backward and the arena all-reduce, and `finish()` joins it.
+        `n_cameras_global`: size of the global camera batch when it is NOT a multiple of the world
         size (shards then differ by one camera, `shard_cameras(..., allow_uneven=True)`); leave None for
         equal shards.  `defer=True` needs the gradient sink of the arena to be active around `backward()`
         and `p.grad is None` for the SH parameters (`zero_grad(set_to_none=True)`); where that does not
@@ -40,6 +45,7 @@ class camera_parallel:
         self.reduced_ptrs = set()
         self.defer = defer
         self.n_cameras_global = n_cameras_global
+        self.peer = peer
         self._deferred = []  # (means parameter, finish(all_cameras) -> v_means) of the colour stages
 
     def __enter__(self):
@@ -53,6 +59,8 @@ class camera_parallel:
                 wrapper._CAMERA_PARALLEL["deferred"] = self._deferred
             if self.n_cameras_global is not None:
                 wrapper._CAMERA_PARALLEL["n_cameras_global"] = int(self.n_cameras_global)
+            if self.peer is not None:
+                wrapper._CAMERA_PARALLEL["peer"] = self.peer
         return self
 
     def __exit__(self, *exc):
@@ -96,6 +104,33 @@ class camera_parallel:
                 m.grad = vm if m.grad is None else m.grad + vm
 
 
+def bind_host_to_gpu(device_index: int) -> Optional[List[int]]:
+    """Pin the calling process to the CPU cores closest to GPU `device_index` (NVML's ideal CPU set: the
+    cores of the NUMA node the GPU's PCIe root hangs off).  Call it BEFORE allocating pinned host buffers:
+    page-locked memory is placed on the node of the thread that allocates it, and with eight ranks per host
+    the per-step image traffic (33 MB each way per rank at 1080p) otherwise crosses the socket interconnect
+    for half of the GPUs.  Returns the CPU list, or None where NVML / the affinity call is unavailable
+    (containers with a fixed cpuset): nothing is changed then."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def shard_cameras(viewmats: Tensor, Ks: Tensor, rank: Optional[int] = None,
                   world_size: Optional[int] = None, allow_uneven: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
     """Cameras owned by `rank`: indices rank, rank+W, ...  Returns (viewmats, Ks, global ids).
@@ -111,20 +146,121 @@ def shard_cameras(viewmats: Tensor, Ks: Tensor, rank: Optional[int] = None,
     return viewmats[ids].contiguous(), Ks[ids].contiguous(), ids
 
 
+def arena_layout(params: Sequence[Tensor]) -> Tuple[List[int], int]:
+    """Offsets (in floats) of the parameters' gradient segments in a flat arena, and its length;
+    every segment starts on a 16-byte boundary."""
+    offs, n = [], 0
+    for p in params:
+        assert p.dtype == torch.float32, "arena holds fp32 gradients"
+        offs.append(n)
+        n += (p.numel() + 3) // 4 * 4
+    return offs, n
+
+
+class PeerExchange:
+    """Symmetric (peer-mapped) device memory for the camera-parallel gradient exchange, and the two
+    exchanges as this library's own kernels over it (csrc/peer.cu) instead of NCCL collectives:
+
+    * colour cotangents: each rank PUBLISHES its masked cotangents and camera centres into its own
+      block; after a flag barrier the colour backward kernel of every rank reads all W blocks in place
+      over NVLink (`b200splat_sh_colors*_bwd_peer`) — the all-gather and its W-fold buffer disappear
+      into the consumer's loads.  Two slots alternate between steps, so one barrier per step suffices
+      (a slot is rewritten only after the barrier of the following step, which every rank reaches after
+      its reads of that slot);
+    * arena: `GradArena(params, peer=this)` places the flat gradient arena in the same buffer and
+      all-reduces it with the two-shot kernel (`b200splat_peer_allreduce_f32`; switch-side reduction
+      through the multicast mapping when the fabric offers one).
+
+    Layout of the buffer (floats): [ flags | slot 0 | slot 1 | arena ], slot = {campos [Cm,3], pad to
+    hdr, cotangents [Cm,N,3]}.  Construction is COLLECTIVE over `group` (symmetric allocation +
+    rendezvous, `torch.distributed._symmetric_memory` is only the allocator/handle exchange).  Raises
+    if the platform cannot map peer memory; callers fall back to the NCCL path (`camera_parallel()`
+    without `peer`, `GradArena(params)`)."""
+
+    def __init__(self, n_gaussians: int, cams_per_rank: int = 1, group=None, arena_floats: int = 0,
+                 device: Optional[torch.device] = None, use_multicast: Optional[bool] = None):
+        import torch.distributed._symmetric_memory as symm
+
+        from ._lib import get_lib
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.N, self.Cm = int(n_gaussians), int(cams_per_rank)
+        self.hdr, self.slot_floats, self.flag_floats, self.total_floats = self.layout(
+            self.N, self.Cm, self.world, get_lib().b200splat_peer_flag_bytes(self.world))
+        self.arena_floats = (int(arena_floats) + 3) // 4 * 4
+        self.slot_off = [self.flag_floats, self.flag_floats + self.slot_floats]
+        self.arena_off = self.flag_floats + 2 * self.slot_floats
+        device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.buf = symm.empty(self.total_floats + self.arena_floats, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, self.group)
+        self.bases_dev = int(self.handle.buffer_ptrs_dev)
+        mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+        # switch-side reduction pays from 4 ranks on (at 2 the multicast path also routes a rank's own copy
+        # through the switch: measured 0.157 vs 0.093 ms for 44 MB, tools/peer_bench.py)
+        self.multicast_available = mc != 0
+        if use_multicast is None:
+            use_multicast = self.world >= 4
+        self.multicast_base = mc if use_multicast else 0
+        self._k = 0
+        # the zeroed flags must be in place everywhere before the first handshake
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)
+
+    @staticmethod
+    def layout(n_gaussians: int, cams_per_rank: int, world: int, flag_bytes: int) -> Tuple[int, int, int, int]:
+        """(hdr_floats, slot_floats, flag_floats, floats before the arena)."""
+        hdr = (3 * cams_per_rank + 3) // 4 * 4
+        slot = (hdr + 3 * cams_per_rank * n_gaussians + 3) // 4 * 4
+        flags = (flag_bytes // 4 + 3) // 4 * 4
+        return hdr, slot, flags, flags + 2 * slot
+
+    def fits(self, n_gaussians: int, cams_per_rank: int) -> bool:
+        return n_gaussians == self.N and cams_per_rank == self.Cm
+
+    def next_slot(self) -> int:
+        self._k += 1
+        return self._k & 1
+
+    def slot_view(self, slot: int) -> Tensor:
+        o = self.slot_off[slot]
+        return self.buf[o:o + self.slot_floats]
+
+    def arena_view(self, n: int) -> Tensor:
+        assert n <= self.arena_floats, f"PeerExchange was built with arena_floats={self.arena_floats} < {n}"
+        return self.buf[self.arena_off:self.arena_off + n]
+
+    def barrier(self) -> None:
+        """Stream-ordered meeting of all ranks (one-warp kernel, flags in the symmetric buffers)."""
+        from .wrapper import get_lib, native
+
+        native("peer_barrier", get_lib(), self.buf.device, self.world, self.rank, self.bases_dev, 0)
+
+    def all_reduce_(self, offset_floats: int, n_floats: int) -> None:
+        """In-place SUM over ranks of buf[offset : offset + n] (a multiple of 4 floats, 16-byte aligned)."""
+        from .wrapper import get_lib, native
+
+        native("peer_allreduce_f32", get_lib(), self.buf.device, self.world, self.rank, self.bases_dev,
+               self.multicast_base, 4 * offset_floats, n_floats, self.bases_dev, 0)
+
+
 class GradArena:
     """Flat, 16-byte-segment-aligned fp32 buffer holding the gradients of a fixed list of
-    parameters, so a step needs exactly one all-reduce launch."""
+    parameters, so a step needs exactly one all-reduce launch.  With `peer` (a `PeerExchange` built
+    with `arena_floats >= arena_layout(params)[1]`) the arena lives in symmetric memory and
+    `all_reduce` is this library's two-shot kernel over NVLink instead of the NCCL collective."""
 
-    def __init__(self, params: Sequence[Tensor]):
+    def __init__(self, params: Sequence[Tensor], peer: Optional[PeerExchange] = None):
         self.params = list(params)
-        offs, n = [], 0
-        for p in self.params:
-            assert p.dtype == torch.float32, "arena holds fp32 gradients"
-            offs.append(n)
-            n += (p.numel() + 3) // 4 * 4  # keep every segment 16-byte aligned
-        self.offsets = offs
-        self.flat = torch.zeros(n, dtype=torch.float32, device=self.params[0].device)
-        self.views = [self.flat[o:o + p.numel()].view_as(p) for o, p in zip(offs, self.params)]
+        self.offsets, n = arena_layout(self.params)
+        self.peer = peer
+        if peer is not None:
+            self.flat = peer.arena_view(n)
+            self.flat.zero_()
+        else:
+            self.flat = torch.zeros(n, dtype=torch.float32, device=self.params[0].device)
+        self.views = [self.flat[o:o + p.numel()].view_as(p) for o, p in zip(self.offsets, self.params)]
 
     @property
     def nbytes(self) -> int:
@@ -173,6 +309,17 @@ class GradArena:
                 start = o
         if start is not None:
             runs.append((start, self.flat.numel()))
+        if self.peer is not None and (group is None or group is self.peer.group):
+            W = self.peer.world
+            for a, b in runs:
+                self.peer.all_reduce_(self.peer.arena_off + a, b - a)  # current stream; nothing to wait for
+                if average:
+                    self.flat[a:b].div_(W)
+            if average:
+                for p, v in zip(self.params, self.views):
+                    if p.data_ptr() in skip_ptrs:
+                        v.div_(W)
+            return [] if async_op else None
         works = []
         for a, b in runs:
             works.append(dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=group, async_op=async_op))

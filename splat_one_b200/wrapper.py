@@ -57,6 +57,8 @@ class _Profiler:
         "quat_scale_to_covar_preci_bwd": 1, "world_to_cam_fwd": 1, "world_to_cam_bwd": 1, "proj_fwd": 1, "proj_bwd": 1,
         "selective_adam_update": 1, "compute_relocation": 1, "sh_colors_staged_fwd": 1, "sh_colors_staged_bwd": 1,
         "splat_activations_fwd": 1, "splat_activations_bwd": 1, "l1_ssim_fwd": 2, "l1_ssim_bwd": 1,
+        "peer_publish_cotangents": 1, "peer_barrier": 1, "peer_allreduce_f32": 1, "sh_colors_bwd_peer": 1,
+        "sh_colors_staged_bwd_peer": 1,
     }
 
     def __init__(self):
@@ -371,8 +373,11 @@ def camera_centers(viewmats: Tensor) -> Tensor:
     return out
 
 
-def _camera_parallel_colour_bwd(cp, means, campos, colors, v_colors, C, outs, v_means, run):
-    """The colour-cotangent exchange of the camera-parallel mode.  Immediate mode: all-gather, then
+def _camera_parallel_colour_bwd(cp, means, campos, colors, v_colors, C, outs, v_means, run, run_peer=None):
+    """The colour-cotangent exchange of the camera-parallel mode.  Peer mode (`camera_parallel(peer=
+    PeerExchange)`): the masked cotangents are published into this rank's symmetric block, a flag
+    barrier orders the ranks, and the kernel (`run_peer`) reads all W blocks in place over NVLink.
+    Immediate mode: all-gather, then
     the kernel (`run`) sums the coefficient gradient over ALL cameras and the direction gradient over
     this rank's cameras; returns v_means.  Deferred mode (`camera_parallel(defer=True)`): the
     all-gather is only STARTED here (async) and the kernel launch is handed to
@@ -390,6 +395,45 @@ def _camera_parallel_colour_bwd(cp, means, campos, colors, v_colors, C, outs, v_
     Cg = _CAMERA_PARALLEL.get("n_cameras_global")
     Cm = C if Cg is None else (Cg + W - 1) // W
     assert Cg is None or C == len(range(r, Cg, W)), (C, Cg, r, W)
+    deferred = _CAMERA_PARALLEL.get("deferred")
+    if deferred is not None:
+        # deferred mode returns gradient tensors that are only filled later: that is only sound
+        # when they ARE the arena views (gradient sink active) and nothing has to be added to them
+        sink_ok = all(o is None or any(o.data_ptr() == d.data_ptr() for d in _GRAD_SINK.values()) for o in outs)
+        fresh = all(lf.grad is None for lf in _CAMERA_PARALLEL.get("leaves", ()))
+        if not (sink_ok and fresh):
+            deferred = None
+    peer = _CAMERA_PARALLEL.get("peer")
+    if peer is not None and run_peer is not None and peer.fits(N, Cm) and peer.group is cp:
+        slot = peer.next_slot()
+        native("peer_publish_cotangents", get_lib(), means.device, C, N, Cm, peer.hdr, _ptr(campos.contiguous()),
+               _ptr(colors), _ptr(v_colors), _ptr(peer.slot_view(slot)))
+        peer.barrier()
+        if deferred is None:
+            run_peer(peer.bases_dev, 4 * peer.slot_off[slot], Cm, peer.hdr, outs, v_means, r * Cm, r * Cm + C, W * Cm)
+            return v_means
+        # overlapped: the colour kernel (NVLink reads of the peers' cotangents + the SH gradient write) runs on a
+        # side stream next to the projection backward and the arena all-reduce of the main stream; its direction
+        # gradient is summed over ALL cameras (already global) and added in camera_parallel.finish()
+        main, side = torch.cuda.current_stream(means.device), _side_stream(means.device)
+        alias = tuple(None if o is None else o.detach() for o in outs)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            vm = torch.empty_like(means) if v_means is not None else None
+            run_peer(peer.bases_dev, 4 * peer.slot_off[slot], Cm, peer.hdr, alias, vm, 0, W * Cm, W * Cm)
+            done = torch.cuda.Event()
+            done.record(side)
+
+        def join(all_cameras: bool, _keep=(colors, v_colors)):
+            assert all_cameras, "the overlapped peer exchange always sums the direction gradient over all cameras"
+            cur = torch.cuda.current_stream(means.device)
+            cur.wait_event(done)
+            if vm is not None:
+                vm.record_stream(cur)
+            return vm
+
+        deferred.append((means, join))
+        return None
     g_local = torch.where(colors > 0, v_colors, torch.zeros_like(v_colors))  # [C,N,3], zero where invisible
     campos_c = campos.contiguous()
     if Cm != C:
@@ -397,14 +441,6 @@ def _camera_parallel_colour_bwd(cp, means, campos, colors, v_colors, C, outs, v_
         campos_c = torch.cat([campos_c, campos_c.new_zeros((Cm - C, 3))])
     g_all = torch.empty((W * Cm, N, 3), device=means.device, dtype=torch.float32)
     campos_all = torch.empty((W * Cm, 3), device=means.device, dtype=torch.float32)
-    deferred = _CAMERA_PARALLEL.get("deferred")
-    if deferred is not None:
-        # deferred mode returns gradient tensors that are only filled in finish(): that is only sound
-        # when they ARE the arena views (gradient sink active) and nothing has to be added to them
-        sink_ok = all(o is None or any(o.data_ptr() == d.data_ptr() for d in _GRAD_SINK.values()) for o in outs)
-        fresh = all(lf.grad is None for lf in _CAMERA_PARALLEL.get("leaves", ()))
-        if not (sink_ok and fresh):
-            deferred = None
     if deferred is None:
         dist.all_gather_into_tensor(g_all, g_local, group=cp)
         dist.all_gather_into_tensor(campos_all, campos_c, group=cp)
@@ -486,8 +522,13 @@ class _ShViewColors(torch.autograd.Function):
                 native("sh_colors_bwd", lib, means.device, WC, N, K, ctx.sh_degree, 0, _ptr(means), _ptr(campos_all),
                        _ptr(coeffs), None, None, _ptr(g_all), _ptr(v_out[0]), _ptr(v_means_out), lo, hi)
 
+            def run_peer(bases, off_bytes, cams_per_block, hdr, v_out, v_means_out, lo, hi, WC):
+                native("sh_colors_bwd_peer", lib, means.device, WC, N, K, ctx.sh_degree, _ptr(means), _ptr(coeffs),
+                       bases, off_bytes, cams_per_block, hdr, _ptr(v_out[0]), _ptr(v_means_out), lo, hi)
+
             _CAMERA_PARALLEL["leaves"] = ctx.coeff_leaves
-            v_means = _camera_parallel_colour_bwd(cp, means, campos, colors, v_colors, C, (v_coeffs,), v_means, run)
+            v_means = _camera_parallel_colour_bwd(cp, means, campos, colors, v_colors, C, (v_coeffs,), v_means, run,
+                                                  run_peer)
             # the gradient is global: mark the LEAVES it flows into (the table itself, or sh0 / shN behind
             # a torch.cat), never the data_ptr of a temporary
             for lf in ctx.coeff_leaves:
@@ -561,8 +602,13 @@ class _ShViewColorsStaged(torch.autograd.Function):
                        _ptr(campos_all), _ptr(sh0), _ptr(rest), None, None, _ptr(g_all), _ptr(v_out[0]), _ptr(v_out[1]),
                        _ptr(v_means_out), lo, hi)
 
+            def run_peer(bases, off_bytes, cams_per_block, hdr, v_out, v_means_out, lo, hi, WC):
+                native("sh_colors_staged_bwd_peer", lib, means.device, WC, N, K, ctx.sh_degree, _ptr(means), _ptr(sh0),
+                       _ptr(rest), bases, off_bytes, cams_per_block, hdr, _ptr(v_out[0]), _ptr(v_out[1]),
+                       _ptr(v_means_out), lo, hi)
+
             _CAMERA_PARALLEL["leaves"] = ctx.coeff_leaves
-            v_means = _camera_parallel_colour_bwd(cp, means, campos, colors, v_colors, C, outs, v_means, run)
+            v_means = _camera_parallel_colour_bwd(cp, means, campos, colors, v_colors, C, outs, v_means, run, run_peer)
             for lf in ctx.coeff_leaves:
                 _CAMERA_PARALLEL["reduced"].add(lf.data_ptr())
         elif N:

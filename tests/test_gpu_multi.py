@@ -19,12 +19,13 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out_path, sh_mode, defer, n_cams, packed_sparse):
+def _worker(rank, world, port, out_path, sh_mode, defer, n_cams, packed_sparse, peer_mode=None):
     import torch.distributed as dist
 
     import splat_one_b200 as S
     from splat_one_b200 import synthetic
-    from splat_one_b200.distributed import GradArena, allreduce_mixed_gradients, camera_parallel, shard_cameras
+    from splat_one_b200.distributed import (GradArena, PeerExchange, allreduce_mixed_gradients, arena_layout, camera_parallel,
+                                            shard_cameras)
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
@@ -36,6 +37,7 @@ def _worker(rank, world, port, out_path, sh_mode, defer, n_cams, packed_sparse):
     vc_all = torch.randn(n_cams, H, W, 3, generator=g)
     va_all = torch.randn(n_cams, H, W, 1, generator=g)
     uneven = n_cams % world != 0
+    peer_box = {}
 
     def grads(cam_ids, dp):
         vm, Ks = scene["viewmats"][cam_ids].to(dev), scene["Ks"][cam_ids].to(dev)
@@ -60,8 +62,16 @@ def _worker(rank, world, port, out_path, sh_mode, defer, n_cams, packed_sparse):
             allreduce_mixed_gradients(P, dense_threshold=packed_sparse)
             assert P[1].grad.is_sparse == (packed_sparse > 1.0)
         elif dp:
-            arena = GradArena(P)
-            with arena.sink(), camera_parallel(defer=defer, n_cameras_global=n_cams if uneven else None) as cp:
+            peer = None
+            if peer_mode is not None:
+                # own kernels over NVLink peer memory (csrc/peer.cu): built once, reused by every step
+                if "x" not in peer_box:
+                    peer_box["x"] = PeerExchange(N, (n_cams + world - 1) // world, arena_floats=arena_layout(P)[1],
+                                                 use_multicast=peer_mode == "multicast")
+                peer = peer_box["x"]
+            arena = GradArena(P, peer=peer)
+            with arena.sink(), camera_parallel(defer=defer, n_cameras_global=n_cams if uneven else None,
+                                               peer=peer) as cp:
                 torch.autograd.backward([rc, ra], [vc, va])
             if defer:  # all-reduce overlapped with the colour backward (camera_parallel.finish)
                 cp.finish(arena)
@@ -75,6 +85,9 @@ def _worker(rank, world, port, out_path, sh_mode, defer, n_cams, packed_sparse):
 
     mine = shard_cameras(scene["viewmats"], scene["Ks"], rank, world, allow_uneven=uneven)[2].tolist()
     g_dp = grads(mine, dp=True)
+    if peer_mode is not None:  # both cotangent slots and the self-resetting flags get reused
+        for _ in range(3):
+            g_dp = grads(mine, dp=True)
     g_ref = grads(list(range(n_cams)), dp=False)   # the whole batch on this GPU
     report = {}
     for n in g_ref:
@@ -97,6 +110,29 @@ CASES = [
     # packed + sparse_grad (config E's mode): sparse (ids, rows) exchange and its dense fallback
     ("table", False, 2, 10.0), ("table", False, 2, 0.0),
 ]
+
+
+PEER_CASES = [("table", 2, "p2p", False), ("split", 2, "p2p", False), ("cat", 2, "p2p", False), ("table", 3, "p2p", False),
+              ("split", 3, "multicast", False), ("table", 2, "multicast", False),
+              # overlapped: colour backward on a side stream next to projection backward + all-reduce
+              ("table", 2, "p2p", True), ("split", 3, "multicast", True), ("cat", 2, "p2p", True)]
+
+
+@pytest.mark.parametrize("sh_mode,n_cams,peer_mode,defer", PEER_CASES)
+def test_two_gpu_peer_exchange_matches_single_process_batch(tmp_path, sh_mode, n_cams, peer_mode, defer):
+    """The same parity bar with both exchanges done by this library's own kernels over NVLink peer memory
+    (`PeerExchange`: published cotangents read in place by the colour backward, two-shot arena all-reduce;
+    "multicast" uses the switch-side reduction when the fabric maps a multicast address, else it is the
+    peer load/store kernel again)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    out = str(tmp_path / "report.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out, sh_mode, defer, n_cams, None, peer_mode), nprocs=2, join=True)
+    for r, rep in enumerate(torch.load(out)):
+        for n, (max_rel, n_bad) in rep.items():
+            assert max_rel < 1e-3 and n_bad == 0, f"rank {r} grad {n}: max rel {max_rel:.2e}, rows outside 1e-3: {n_bad}"
 
 
 @pytest.mark.parametrize("sh_mode,defer,n_cams,packed_sparse", CASES)

@@ -120,3 +120,21 @@ def test_rasterization_split_sh_table_asserts():
     # CPU tensors take the concatenating route and then fail loudly at the first kernel
     with pytest.raises(RuntimeError, match="CUDA"):
         S.rasterization(**ok, colors=(torch.zeros(N, 1, 3), torch.zeros(N, 15, 3)), sh_degree=3)
+
+
+def test_peer_exchange_layout_is_16_byte_aligned_and_disjoint():
+    """Host-side layout of the symmetric buffer of the peer gradient exchange (flags | slot 0 | slot 1 |
+    arena): every region starts on a 16-byte boundary and holds what the kernels index."""
+    from splat_one_b200._lib import get_lib
+    from splat_one_b200.distributed import PeerExchange
+
+    lib = get_lib()
+    for world in (2, 3, 8):
+        fb = lib.b200splat_peer_flag_bytes(world)
+        assert fb >= (1 + 2 * 148) * world * 4
+        for n, cm in ((40000, 1), (1000003, 2), (7, 3)):
+            hdr, slot, flags, total = PeerExchange.layout(n, cm, world, fb)
+            assert hdr % 4 == 0 and hdr >= 3 * cm
+            assert slot % 4 == 0 and slot >= hdr + 3 * cm * n
+            assert flags % 4 == 0 and flags * 4 >= fb
+            assert total == flags + 2 * slot
