@@ -681,6 +681,29 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_small_ms = t.item() / n_small
 
+    # host-link probe (outside every timed region): the e2e payloads alone, all ranks at once, one direction
+    # at a time — what the host's PCIe path gives each rank when N ranks copy simultaneously
+    def link_probe(direction):
+        reps = 10
+        barrier()
+        e0.record()
+        for _ in range(reps):
+            if direction == "h2d":
+                cot[0][0].copy_(vc_host, non_blocking=True)
+                cot[0][1].copy_(va_host, non_blocking=True)
+            else:
+                out_c_host.copy_(vc, non_blocking=True)
+                out_a_host.copy_(va, non_blocking=True)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return (vc_host.numel() + va_host.numel()) * 4 * reps / (t.item() * 1e-3) / 1e9
+
+    host_link = {"h2d_GBps_per_rank": round(link_probe("h2d"), 2), "d2h_GBps_per_rank": round(link_probe("d2h"), 2),
+                 "what": f"33 MB pinned copies, {world} rank(s) at once, min over ranks"}
+
     # ---- extra legs, all outside the timed regions -------------------------------------------
     dp_parity = dp_parity_check(S, dist, world, rank, dev) if world > 1 else None
     extras = {}
@@ -783,6 +806,7 @@ def run_gpu(args):
             "cpu_baseline": cpu,
             "reference_cuda": ref_cuda_leg,
             "dp_parity_max_rel": dp_parity,
+            "host_link": host_link,
             "host_binding": (f"{len(host_cpus)} cores nearest to the GPU (NVML affinity)" if host_cpus else "none"),
             "exchange": {"timed": ("peer" if peer is not None else "nccl") + ("_overlapped" if DEFER else "_plain"),
                          "multicast": bool(peer is not None and peer.multicast_base),

@@ -89,6 +89,34 @@ B200SPLAT_API int b200splat_projection_bwd(
     float *v_means, float *v_covars, float *v_quats, float *v_scales, float *v_viewmats,
     void *stream);
 
+/* f3  DefaultStrategy._update_state     G/strategy/default.py:239-262 (running densification
+ *     statistics), folded into the projection backward: besides the gradients of a3, for every Gaussian n
+ *       state_grad2d[n] += sum_c [radii[c,n] > 0] * |(v_means2d[c,n].x * grad_scale_x, .y * grad_scale_y)|
+ *       state_count[n]  += sum_c [radii[c,n] > 0]
+ *       state_radii[n]   = max(state_radii[n], max_c radii[c,n] / max_wh)      (state_radii may be NULL)
+ *     with grad_scale = (W/2, H/2) * n_cameras and max_wh = max(W,H) as in :220-226, :258-261.
+ *     v_means2d is the cotangent this call receives, i.e. the `means2d.grad` the reference retains. */
+B200SPLAT_API int b200splat_projection_bwd_state(
+    uint32_t C, uint32_t N,
+    const float *means, const float *covars, const float *quats, const float *scales,
+    const float *viewmats, const float *Ks,
+    uint32_t image_width, uint32_t image_height, float eps2d, int camera_model,
+    const int32_t *radii, const float *conics, const float *compensations,
+    const float *v_means2d, const float *v_depths, const float *v_conics,
+    const float *v_compensations,
+    float *v_means, float *v_covars, float *v_quats, float *v_scales, float *v_viewmats,
+    float grad_scale_x, float grad_scale_y, float max_wh,
+    float *state_grad2d, float *state_count, float *state_radii, void *stream);
+
+/* The same update as one stand-alone kernel, for the cases the fused form does not cover: packed layout
+ * (gaussian_ids != NULL: grads [nnz,2], radii [nnz], atomics per visible pair) and `absgrad` statistics
+ * (grads = means2d.absgrad).  Unpacked: grads [C,N,2], radii [C,N], nnz ignored. */
+B200SPLAT_API int b200splat_strategy_update_state(
+    uint32_t C, uint32_t N, uint32_t nnz, const int64_t *gaussian_ids,
+    const float *grads, const int32_t *radii,
+    float grad_scale_x, float grad_scale_y, float max_wh,
+    float *state_grad2d, float *state_count, float *state_radii, void *stream);
+
 /* ------------------------------------------------------------------------------------
  * a4  fully_fused_projection_packed_fwd  CS/bindings.h:254-278, kernel
  *     CS/fully_fused_projection_packed_fwd.cu:20-267 (two launches + cumsum + .item()).

@@ -11,6 +11,7 @@ there is no CPU / PyTorch fallback.
 from .optimizers import SelectiveAdam
 from .rendering import rasterization
 from .step import l1_ssim_loss, rasterize_splats, splat_activations
+from .strategy import strategy_state_sink, update_state as update_strategy_state
 from .wrapper import (
     accumulate,
     compute_relocation,
@@ -45,6 +46,8 @@ __all__ = [
     "selective_adam_update",
     "compute_relocation",
     "SelectiveAdam",
+    "strategy_state_sink",
+    "update_strategy_state",
     "spherical_harmonics",
     "spherical_harmonics_table",
     "rasterize_splats",

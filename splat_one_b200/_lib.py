@@ -17,7 +17,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("B200SPLAT_LIB", _PKG / "libb200splat.so"))
 
-ABI_VERSION = 14
+ABI_VERSION = 15
 
 _P = c_void_p
 _U32 = c_uint32
@@ -35,6 +35,9 @@ SIGNATURES = {
     "b200splat_projection_fwd": (_I, _PROJ_COMMON + [_F, _F, _F, _F, _I, _P, _P, _P, _P, _P, _P]),
     "b200splat_projection_bwd": (
         _I, _PROJ_COMMON + [_F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "b200splat_projection_bwd_state": (
+        _I, _PROJ_COMMON + [_F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _P, _P, _P, _P]),
+    "b200splat_strategy_update_state": (_I, [_U32, _U32, _U32, _P, _P, _P, _F, _F, _F, _P, _P, _P, _P]),
     "b200splat_projection_packed_count": (_I, _PROJ_COMMON + [_F, _F, _F, _F, _I, _P, _P, _P]),
     "b200splat_projection_packed_fill": (
         _I, _PROJ_COMMON + [_F, _F, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

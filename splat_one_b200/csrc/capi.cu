@@ -25,7 +25,7 @@ int fail_cuda(const char *where, cudaError_t e) {
 
 }  // namespace b2s
 
-extern "C" int b200splat_abi_version(void) { return 14; }
+extern "C" int b200splat_abi_version(void) { return 15; }
 extern "C" const char *b200splat_last_error(void) { return b2s::last_error().c_str(); }
 extern "C" const char *b200splat_arch(void) { return "sm_100a"; }
 

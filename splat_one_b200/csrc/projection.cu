@@ -63,11 +63,25 @@ projection_fwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
     if (compensations != nullptr) compensations[idx] = o.comp;
 }
 
+// Running densification statistics of the reference's DefaultStrategy (G/strategy/default.py:239-262,
+// `_update_state`), folded into the projection backward: the kernel already visits
+// every (camera, Gaussian) pair with its 2-D mean cotangent and radius in registers, so
+//   grad2d[n] += sum_c [radius > 0] |(v_x sx, v_y sy)|,   count[n] += sum_c [radius > 0],
+//   radii[n]   = max(radii[n], max_c radius / max(W, H))
+// cost three read-modify-writes per Gaussian instead of ~10 ATen launches over [C,N] temporaries.
+struct DensifyState {
+    float *grad2d;     // nullptr: statistics off
+    float *count;
+    float *radii;      // nullable (refine_scale2d_stop_iter == 0)
+    float sx, sy;      // W/2 * n_cameras, H/2 * n_cameras
+    float max_wh;      // max(W, H): radii are divided exactly (IEEE), like the reference
+};
+
 // ---------------------------------------------------------------------------------------
 // a3: one thread per Gaussian, loop over cameras; no atomics on the parameter grads.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)   // (kThreads, 3) = 80 registers spills: 0.059 vs 0.055 ms
-projection_bwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, const float *__restrict__ covars,
+projection_bwd_kernel(const DensifyState dens, uint32_t C, uint32_t N, const float *__restrict__ means, const float *__restrict__ covars,
                       const float *__restrict__ quats, const float *__restrict__ scales,
                       const float *__restrict__ viewmats, const float *__restrict__ Ks, uint32_t W, uint32_t H,
                       float eps2d, int camera_model, const int32_t *__restrict__ radii,
@@ -88,9 +102,11 @@ projection_bwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
     }
     V3 v_mean = {0.f, 0.f, 0.f};
     M3 v_covar = m3_zero();
+    float d_grad = 0.f, d_count = 0.f, d_radius = 0.f;
     for (uint32_t cid = 0; cid < C; ++cid) {
         const uint64_t idx = (uint64_t)cid * N + gid;
-        const bool valid = in_range && radii[idx] > 0;
+        const int32_t radius = in_range ? radii[idx] : 0;
+        const bool valid = radius > 0;
         M3 v_R = m3_zero();
         V3 v_t = {0.f, 0.f, 0.f};
         if (valid) {
@@ -100,6 +116,12 @@ projection_bwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
                                      __ldcs(v_conics + 3 * idx + 2)};
             const float2 vm2 = __ldcs(reinterpret_cast<const float2 *>(v_means2d) + idx);
             const V2 v_mean2d = {vm2.x, vm2.y};
+            if (dens.grad2d != nullptr) {
+                const float gx = vm2.x * dens.sx, gy = vm2.y * dens.sy;
+                d_grad += sqrtf(gx * gx + gy * gy);
+                d_count += 1.f;
+                d_radius = fmaxf(d_radius, __fdiv_rn((float)radius, dens.max_wh));
+            }
             const float v_depth = __ldcs(v_depths + idx);
             float comp = 0.f, v_comp = 0.f;
             const bool has_comp = v_compensations != nullptr;
@@ -126,6 +148,11 @@ projection_bwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
         }
     }
     if (!in_range) return;
+    if (dens.grad2d != nullptr && d_count > 0.f) {
+        dens.grad2d[gid] += d_grad;
+        dens.count[gid] += d_count;
+        if (dens.radii != nullptr) dens.radii[gid] = fmaxf(dens.radii[gid], d_radius);
+    }
     v_means[3 * gid] = v_mean.x; v_means[3 * gid + 1] = v_mean.y; v_means[3 * gid + 2] = v_mean.z;
     if (v_covars != nullptr) {
         // flattened upper triangle (CS/fully_fused_projection_bwd.cu:221-231)
@@ -338,6 +365,26 @@ extern "C" int b200splat_projection_fwd(uint32_t C, uint32_t N, const float *mea
     return 0;
 }
 
+static int projection_bwd_impl(const char *where, const DensifyState &dens, uint32_t C, uint32_t N, const float *means,
+                               const float *covars, const float *quats, const float *scales, const float *viewmats,
+                               const float *Ks, uint32_t W, uint32_t H, float eps2d, int camera_model,
+                               const int32_t *radii, const float *conics, const float *compensations,
+                               const float *v_means2d, const float *v_depths, const float *v_conics,
+                               const float *v_compensations, float *v_means, float *v_covars, float *v_quats,
+                               float *v_scales, float *v_viewmats, void *stream) {
+    B2S_REQUIRE(camera_model >= 0 && camera_model <= 3, where, "unknown camera model");
+    B2S_REQUIRE(covars != nullptr || (quats != nullptr && scales != nullptr), where, "covars or (quats, scales) required");
+    B2S_REQUIRE(covars == nullptr || v_covars != nullptr, where, "v_covars required with covars");
+    B2S_REQUIRE(covars != nullptr || (v_quats != nullptr && v_scales != nullptr), where, "v_quats/v_scales required");
+    if (N == 0) return 0;
+    projection_bwd_kernel<<<div_up(N, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        dens, C, N, means, covars, quats, scales, viewmats, Ks, W, H, eps2d, camera_model, radii, conics,
+        compensations, v_means2d, v_depths, v_conics, v_compensations, v_means, v_covars, v_quats, v_scales,
+        v_viewmats);
+    B2S_CHECK_LAUNCH(where);
+    return 0;
+}
+
 extern "C" int b200splat_projection_bwd(uint32_t C, uint32_t N, const float *means, const float *covars,
                                         const float *quats, const float *scales, const float *viewmats,
                                         const float *Ks, uint32_t W, uint32_t H, float eps2d, int camera_model,
@@ -345,17 +392,27 @@ extern "C" int b200splat_projection_bwd(uint32_t C, uint32_t N, const float *mea
                                         const float *v_means2d, const float *v_depths, const float *v_conics,
                                         const float *v_compensations, float *v_means, float *v_covars,
                                         float *v_quats, float *v_scales, float *v_viewmats, void *stream) {
-    const char *where = "b200splat_projection_bwd";
-    B2S_REQUIRE(camera_model >= 0 && camera_model <= 3, where, "unknown camera model");
-    B2S_REQUIRE(covars != nullptr || (quats != nullptr && scales != nullptr), where, "covars or (quats, scales) required");
-    B2S_REQUIRE(covars == nullptr || v_covars != nullptr, where, "v_covars required with covars");
-    B2S_REQUIRE(covars != nullptr || (v_quats != nullptr && v_scales != nullptr), where, "v_quats/v_scales required");
-    if (N == 0) return 0;
-    projection_bwd_kernel<<<div_up(N, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-        C, N, means, covars, quats, scales, viewmats, Ks, W, H, eps2d, camera_model, radii, conics, compensations,
-        v_means2d, v_depths, v_conics, v_compensations, v_means, v_covars, v_quats, v_scales, v_viewmats);
-    B2S_CHECK_LAUNCH(where);
-    return 0;
+    const DensifyState off{nullptr, nullptr, nullptr, 0.f, 0.f, 0.f};
+    return projection_bwd_impl("b200splat_projection_bwd", off, C, N, means, covars, quats, scales, viewmats, Ks, W, H,
+                               eps2d, camera_model, radii, conics, compensations, v_means2d, v_depths, v_conics,
+                               v_compensations, v_means, v_covars, v_quats, v_scales, v_viewmats, stream);
+}
+
+extern "C" int b200splat_projection_bwd_state(uint32_t C, uint32_t N, const float *means, const float *covars,
+                                              const float *quats, const float *scales, const float *viewmats,
+                                              const float *Ks, uint32_t W, uint32_t H, float eps2d, int camera_model,
+                                              const int32_t *radii, const float *conics, const float *compensations,
+                                              const float *v_means2d, const float *v_depths, const float *v_conics,
+                                              const float *v_compensations, float *v_means, float *v_covars,
+                                              float *v_quats, float *v_scales, float *v_viewmats, float grad_scale_x,
+                                              float grad_scale_y, float max_wh, float *state_grad2d,
+                                              float *state_count, float *state_radii, void *stream) {
+    const char *where = "b200splat_projection_bwd_state";
+    B2S_REQUIRE(state_grad2d != nullptr && state_count != nullptr, where, "grad2d and count state arrays are required");
+    const DensifyState dens{state_grad2d, state_count, state_radii, grad_scale_x, grad_scale_y, max_wh};
+    return projection_bwd_impl(where, dens, C, N, means, covars, quats, scales, viewmats, Ks, W, H, eps2d, camera_model,
+                               radii, conics, compensations, v_means2d, v_depths, v_conics, v_compensations, v_means,
+                               v_covars, v_quats, v_scales, v_viewmats, stream);
 }
 
 extern "C" int b200splat_projection_packed_count(uint32_t C, uint32_t N, const float *means, const float *covars,

@@ -82,12 +82,44 @@ class camera_parallel:
         every rank, i.e. it is already global and is added AFTER the all-reduce.  Reduced gradients
         live in the arena views (`arena.scatter_to_params()` re-attaches them)."""
         arena.gather_from_params()
+        W = dist.get_world_size(self.group)
+        if arena.peer is not None and self._deferred and all(getattr(fin, "local", False) for _, fin in self._deferred):
+            # peer exchange, overlapped: the colour kernel of each deferred node is already running on a side
+            # stream (NVLink reads of the peers' cotangents; direction gradient of THIS rank's cameras only).
+            #   high-priority stream: all-reduce of everything but the means segment  || colour kernel
+            #   main stream:          join, means += local direction gradient, all-reduce of the means segment
+            from .wrapper import _side_stream
+
+            dev = arena.flat.device
+            main, hp = torch.cuda.current_stream(dev), _side_stream(dev, priority=-1)
+            late = {m.data_ptr() for m, _ in self._deferred if any(p is m for p in arena.params)}
+            hp.wait_stream(main)
+            with torch.cuda.stream(hp):
+                arena.all_reduce(group=self.group, skip_ptrs=set(self.reduced_ptrs) | late)
+            for m, fin in self._deferred:
+                vm = fin(True)  # main stream waits for the side stream's colour kernel
+                if vm is None:
+                    continue
+                for p, v in zip(arena.params, arena.views):
+                    if p is m:
+                        v.add_(vm)
+                        break
+                else:  # not an arena parameter: reduce and accumulate on the tensor itself
+                    dist.all_reduce(vm, group=self.group)
+                    m.grad = vm if m.grad is None else m.grad + vm
+            self._deferred.clear()
+            main.wait_stream(hp)  # the two all-reduce kernels share the handshake flags: strictly ordered
+            if late:
+                arena.all_reduce(group=self.group, only_ptrs=late)
+            if average:
+                for v in arena.views:
+                    v.div_(W)
+            return
         works = arena.all_reduce(group=self.group, async_op=True, skip_ptrs=self.reduced_ptrs)
         pending = [(m, fin(True)) for m, fin in self._deferred]
         self._deferred.clear()
         for w in works or ():
             w.wait()
-        W = dist.get_world_size(self.group)
         if average:
             for p, v in zip(arena.params, arena.views):
                 v.div_(W)
@@ -292,16 +324,17 @@ class GradArena:
             else:
                 v.copy_(g)
 
-    def all_reduce(self, group=None, average: bool = False, async_op: bool = False, skip_ptrs=()):
+    def all_reduce(self, group=None, average: bool = False, async_op: bool = False, skip_ptrs=(), only_ptrs=None):
         """SUM over ranks (optionally / world_size); a no-op outside a process group.
         Parameters whose data_ptr() is in `skip_ptrs` already hold a global gradient
         (`camera_parallel`) and are left out: the arena is reduced as the maximal contiguous runs
-        of the remaining segments (one collective when the skipped parameter is the last one)."""
+        of the remaining segments (one collective when the skipped parameter is the last one).
+        `only_ptrs`: reduce just the segments of these parameters."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return None
         runs, start = [], None
         for p, o in zip(self.params, self.offsets):
-            if p.data_ptr() in skip_ptrs:
+            if p.data_ptr() in skip_ptrs or (only_ptrs is not None and p.data_ptr() not in only_ptrs):
                 if start is not None:
                     runs.append((start, o))
                     start = None

@@ -57,7 +57,7 @@ class _Profiler:
         "quat_scale_to_covar_preci_bwd": 1, "world_to_cam_fwd": 1, "world_to_cam_bwd": 1, "proj_fwd": 1, "proj_bwd": 1,
         "selective_adam_update": 1, "compute_relocation": 1, "sh_colors_staged_fwd": 1, "sh_colors_staged_bwd": 1,
         "splat_activations_fwd": 1, "splat_activations_bwd": 1, "l1_ssim_fwd": 2, "l1_ssim_bwd": 1,
-        "peer_publish_cotangents": 1, "peer_barrier": 1, "peer_allreduce_f32": 1, "sh_colors_bwd_peer": 1,
+        "projection_bwd_state": 1, "strategy_update_state": 1, "peer_publish_cotangents": 1, "peer_barrier": 1, "peer_allreduce_f32": 1, "sh_colors_bwd_peer": 1,
         "sh_colors_staged_bwd_peer": 1,
     }
 
@@ -115,13 +115,14 @@ def _stream(device: torch.device):
 _PINNED = threading.local()
 
 
-def _side_stream(device) -> "torch.cuda.Stream":
-    side = getattr(_PINNED, "streams", None)
-    if side is None:
-        side = _PINNED.streams = {}
-    st = side.get(device)
+_SIDE_STREAMS: dict = {}  # process-wide (autograd engine threads and the caller must see the same streams)
+
+
+def _side_stream(device, priority: int = 0) -> "torch.cuda.Stream":
+    key = (torch.device(device), priority)
+    st = _SIDE_STREAMS.get(key)
     if st is None:
-        st = side[device] = torch.cuda.Stream(device=device)
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=device, priority=priority)
     return st
 
 
@@ -218,6 +219,12 @@ class gradient_sink:
         for p, _ in self.pairs:
             _GRAD_SINK.pop(p.data_ptr(), None)
         return False
+
+
+# densification-state sink (set by splat_one_b200.strategy.strategy_state_sink): while active, the unpacked
+# projection backward also updates the running grad2d / count / radii statistics of the reference's
+# DefaultStrategy.  Process-wide for the same reason as _GRAD_SINK.
+_STRATEGY_SINK: dict = {}
 
 
 # camera-parallel mode (set by splat_one_b200.distributed.camera_parallel): process group + the
@@ -413,25 +420,26 @@ def _camera_parallel_colour_bwd(cp, means, campos, colors, v_colors, C, outs, v_
             run_peer(peer.bases_dev, 4 * peer.slot_off[slot], Cm, peer.hdr, outs, v_means, r * Cm, r * Cm + C, W * Cm)
             return v_means
         # overlapped: the colour kernel (NVLink reads of the peers' cotangents + the SH gradient write) runs on a
-        # side stream next to the projection backward and the arena all-reduce of the main stream; its direction
-        # gradient is summed over ALL cameras (already global) and added in camera_parallel.finish()
+        # side stream next to the projection backward and the arena all-reduce; its direction gradient covers
+        # THIS rank's cameras and is added to the means segment in camera_parallel.finish(), ahead of that
+        # segment's all-reduce
         main, side = torch.cuda.current_stream(means.device), _side_stream(means.device)
         alias = tuple(None if o is None else o.detach() for o in outs)
         side.wait_stream(main)
         with torch.cuda.stream(side):
             vm = torch.empty_like(means) if v_means is not None else None
-            run_peer(peer.bases_dev, 4 * peer.slot_off[slot], Cm, peer.hdr, alias, vm, 0, W * Cm, W * Cm)
+            run_peer(peer.bases_dev, 4 * peer.slot_off[slot], Cm, peer.hdr, alias, vm, r * Cm, r * Cm + C, W * Cm)
             done = torch.cuda.Event()
             done.record(side)
 
         def join(all_cameras: bool, _keep=(colors, v_colors)):
-            assert all_cameras, "the overlapped peer exchange always sums the direction gradient over all cameras"
             cur = torch.cuda.current_stream(means.device)
             cur.wait_event(done)
             if vm is not None:
                 vm.record_stream(cur)
             return vm
 
+        join.local = True  # the returned direction gradient is this rank's share, not the global sum
         deferred.append((means, join))
         return None
     g_local = torch.where(colors > 0, v_colors, torch.zeros_like(v_colors))  # [C,N,3], zero where invisible
@@ -857,7 +865,18 @@ class _FullyFusedProjection(torch.autograd.Function):
         v_quats = _grad_out(quats) if covars is None else None
         v_scales = _grad_out(scales) if covars is None else None
         v_viewmats = torch.zeros_like(viewmats) if ctx.needs_input_grad[4] else None
-        if N:
+        sink = _STRATEGY_SINK.get("state") if _STRATEGY_SINK else None
+        if N and sink is not None and sink.accepts(C, N, ctx.width, ctx.height):
+            # DefaultStrategy._update_state folded into this kernel (splat_one_b200/strategy.py)
+            sx, sy, inv = sink.scales(C)
+            native("projection_bwd_state", lib, dev, C, N, _ptr(means), _ptr(covars), _ptr(quats), _ptr(scales),
+                   _ptr(viewmats), _ptr(Ks), ctx.width, ctx.height, ctx.eps2d, ctx.camera_model, _ptr(radii),
+                   _ptr(conics), _ptr(compensations), _ptr(v_means2d.contiguous()), _ptr(v_depths.contiguous()),
+                   _ptr(v_conics.contiguous()), _ptr(v_compensations), _ptr(v_means), _ptr(v_covars), _ptr(v_quats),
+                   _ptr(v_scales), _ptr(v_viewmats), sx, sy, inv, _ptr(sink.grad2d), _ptr(sink.count),
+                   _ptr(sink.radii))
+            sink.updates += 1
+        elif N:
             native("projection_bwd", lib, dev, C, N, _ptr(means), _ptr(covars), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks),
                     ctx.width, ctx.height, ctx.eps2d, ctx.camera_model, _ptr(radii), _ptr(conics),
                     _ptr(compensations), _ptr(v_means2d.contiguous()), _ptr(v_depths.contiguous()),

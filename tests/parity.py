@@ -41,3 +41,27 @@ def assert_grad_close(got, ref, rtol=GRAD_RTOL, what="grad", frac_ok=0.999):
     frac = ok.double().mean().item() if ok.numel() else 1.0
     assert frac >= frac_ok, f"{what}: only {frac:.5f} of entries within {rtol} (scale {scale:.3e}, max err {err.max():.3e})"
     assert err.max().item() <= 20 * rtol * scale, f"{what}: max err {err.max().item():.3e} vs scale {scale:.3e}"
+
+
+def ssim_constant_images_closed_form(a: float, b: float, H: int, W: int, padding: str = "valid") -> float:
+    """Known answer for SSIM (Wang et al. 2004; 11-tap Gaussian sigma 1.5, C1 = 0.01^2, C2 = 0.03^2, zero-padded
+    local statistics — the algorithm fused-ssim publishes) on two CONSTANT images with values a and b, derived
+    by hand and evaluated in float64 without any convolution code.  With window mass m(p) inside the image at
+    pixel p: mu1 = a m, mu2 = b m, sigma1^2 = a^2 m (1 - m), sigma2^2 = b^2 m (1 - m), sigma12 = a b m (1 - m).
+    "valid" crops 5 border pixels (m = 1 everywhere that is left): SSIM = (2ab + C1) / (a^2 + b^2 + C1)."""
+    import numpy as np
+
+    x = np.arange(11, dtype=np.float64) - 5
+    g = np.exp(-x * x / (2 * 1.5 ** 2))
+    g /= g.sum()
+
+    def mass(n):
+        return np.array([g[max(0, 5 - i):min(11, n + 5 - i)].sum() for i in range(n)])
+
+    m = mass(H)[:, None] * mass(W)[None, :]
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    s = ((2 * a * b * m * m + C1) * (2 * a * b * m * (1 - m) + C2)) / (
+        ((a * a + b * b) * m * m + C1) * ((a * a + b * b) * m * (1 - m) + C2))
+    if padding == "valid":
+        s = s[5:-5, 5:-5]
+    return float(s.mean())

@@ -18,7 +18,7 @@ def _header_symbols():
 def test_library_loads_and_exports_every_header_symbol():
     lib = _lib.get_lib()
     syms = _header_symbols()
-    assert len(syms) == 59
+    assert len(syms) == 61
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/b200splat.h but not exported"
     assert lib.b200splat_abi_version() == _lib.ABI_VERSION

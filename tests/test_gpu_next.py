@@ -3,6 +3,9 @@ pure-PyTorch compositing, and (2) the §8(f) operators: rasterize_to_indices_in_
 accumulate and the un-fused projection chain, against reference-generated vectors and the
 CPU oracle.  Everything goes through the public Python API -> C ABI of libb200splat.so."""
 import math
+import os
+
+import numpy as np
 
 import pytest
 import torch
@@ -303,3 +306,71 @@ def test_compute_relocation_matches_oracle():
     e = S.compute_relocation(torch.zeros(0, device=DEV), torch.zeros(0, 3, device=DEV),
                              torch.zeros(0, device=DEV, dtype=torch.int64), _g(binoms))
     assert e[0].shape == (0,) and e[1].shape == (0, 3)
+
+
+# ------------------------------------------------------------------------------------------------
+# f3: DefaultStrategy._update_state — stand-alone kernel and the form folded into the projection backward
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["unpacked", "packed"])
+def test_strategy_update_state_matches_reference_outputs(mode):
+    """tests/golden/strategy_state.npz = outputs of the reference's own DefaultStrategy._update_state."""
+    from types import SimpleNamespace
+
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "strategy_state.npz"))
+    N, C, W, H = int(G["N"]), int(G["C"]), int(G["width"]), int(G["height"])
+    state = {"grad2d": None, "count": None, "radii": None}
+    for call in range(2):
+        grads = torch.from_numpy(G[f"{mode}_grads{call}"]).to(DEV)
+        info = dict(width=W, height=H, n_cameras=C if mode == "unpacked" else 1,
+                    radii=torch.from_numpy(G[f"{mode}_radii{call}"]).to(DEV),
+                    gaussian_ids=torch.from_numpy(G[f"{mode}_ids{call}"]).to(DEV) if mode == "packed" else None,
+                    means2d=SimpleNamespace(grad=grads, absgrad=grads.abs()))
+        S.update_strategy_state(state, info, packed=mode == "packed", n_gaussians=N)
+        assert torch.allclose(state["grad2d"].cpu(), torch.from_numpy(G[f"{mode}_grad2d_after{call}"]), rtol=2e-6, atol=1e-9)
+        assert torch.equal(state["count"].cpu(), torch.from_numpy(G[f"{mode}_count_after{call}"]))
+        assert torch.equal(state["radii"].cpu(), torch.from_numpy(G[f"{mode}_radii_after{call}"]))
+
+
+@pytest.mark.parametrize("n_cams", [1, 3])
+def test_strategy_state_folded_into_projection_backward(n_cams):
+    """`strategy_state_sink` around backward() == the reference sequence: retain means2d.grad, then
+    _update_state (restated in oracle/strategy_ref.py, itself pinned to the reference's outputs), and
+    == the stand-alone kernel; the parameter gradients are untouched by the sink."""
+    from oracle import strategy_ref as SRf
+
+    from splat_one_b200 import synthetic
+
+    W_, H_, N_ = 320, 240, 30000
+    sc = synthetic.pinhole_scene(N_, W_, H_, seed=5, n_cameras=n_cams)
+    names = ("means", "quats", "scales", "opacities", "sh")
+    g = torch.Generator().manual_seed(8)
+    vc = torch.randn(n_cams, H_, W_, 3, generator=g).to(DEV)
+    va = torch.randn(n_cams, H_, W_, 1, generator=g).to(DEV)
+
+    def run(sink_state):
+        P = [sc[k].to(DEV).requires_grad_() for k in names]
+        rc, ra, meta = S.rasterization(*P, sc["viewmats"].to(DEV), sc["Ks"].to(DEV), W_, H_, sh_degree=3, packed=False)
+        meta["means2d"].retain_grad()
+        if sink_state is not None:
+            with S.strategy_state_sink(sink_state, N_, W_, H_, DEV) as sink:
+                torch.autograd.backward([rc, ra], [vc, va])
+            assert sink.updates == 1
+        else:
+            torch.autograd.backward([rc, ra], [vc, va])
+        return P, meta
+
+    fused = {"grad2d": None, "count": None, "radii": None}
+    for _ in range(2):  # two steps: accumulation and the running maximum
+        P1, meta1 = run(fused)
+    ref = [torch.zeros(N_), torch.zeros(N_), torch.zeros(N_)]
+    alone = {"grad2d": None, "count": None, "radii": None}
+    for _ in range(2):
+        P0, meta0 = run(None)
+        SRf.update_state(*ref, meta0["means2d"].grad.cpu(), meta0["radii"].cpu(), W_, H_, n_cams)
+        S.update_strategy_state(alone, meta0)
+    for a, b, n in zip(P0, P1, names):  # same kernels; the raster backward's atomics reorder fp32 sums run to run
+        assert_grad_close(b.grad, a.grad, what=f"{n} with the state sink", frac_ok=1.0)
+    for k, r in zip(("grad2d", "count", "radii"), ref):
+        assert torch.allclose(fused[k].cpu(), r, rtol=1e-5, atol=1e-7), k
+        assert torch.allclose(alone[k].cpu(), r, rtol=1e-5, atol=1e-7), k
+    assert int((fused["count"] > 0).sum()) > 1000

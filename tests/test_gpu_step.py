@@ -99,6 +99,24 @@ def test_l1_ssim_loss_matches_oracle(C, H, W):
     assert abs(loss2.item() - loss.item()) < 1e-7
 
 
+@pytest.mark.parametrize("a,b", [(0.3, 0.7), (0.05, 0.9)])
+def test_l1_ssim_kernel_known_answer_on_constant_images(a, b):
+    """The fused L1 + SSIM kernel against the hand-derived closed form for constant images
+    (tests/parity.py::ssim_constant_images_closed_form), not against any restated convolution."""
+    from parity import ssim_constant_images_closed_form as kat
+
+    H, W = 45, 70
+    x = torch.full((1, H, W, 3), a, device=DEV)
+    y = torch.full((1, H, W, 3), b, device=DEV)
+    loss, terms = S.l1_ssim_loss(x, y, 0.2, return_terms=True)
+    ssim = kat(a, b, H, W, "valid")
+    # 3e-4: with zero true variance the fp32 rounding noise of E[x^2] - mu^2 (~1e-7) is measured against
+    # C2 = 9e-4; the fp32 oracle shows the same spread (tests/test_oracle_step.py)
+    assert abs(terms[2].item() - ssim) < 3e-4, (terms[2].item(), ssim)
+    assert abs(terms[1].item() - abs(a - b)) < 1e-6
+    assert abs(loss.item() - (0.8 * abs(a - b) + 0.2 * (1 - ssim))) < 1e-4
+
+
 def test_rasterize_splats_and_loss_match_oracle_step():
     """One whole step (activations -> split SH -> rasterization -> L1+SSIM -> backward) against
     the oracle step on the same raw parameters."""

@@ -133,3 +133,31 @@ def test_relocation_and_adam_oracle_known_answers():
     assert torch.equal(np_[1], p[1]) and torch.equal(nm[1], z[1])
     m, v = 0.1 * g[0], 0.001 * g[0] ** 2
     torch.testing.assert_close(np_[0], p[0] - 0.1 * m / (v.sqrt() + 1e-8), rtol=1e-4, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# f3: DefaultStrategy._update_state restatement against outputs of the reference's own method
+# ------------------------------------------------------------------------------------------------
+def _strategy_golden():
+    import os
+
+    import numpy as np
+
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "strategy_state.npz"))
+
+
+@pytest.mark.parametrize("mode", ["unpacked", "packed"])
+def test_strategy_state_oracle_matches_reference_outputs(mode):
+    from oracle import strategy_ref as SRf
+
+    G = _strategy_golden()
+    N, C, W, H = int(G["N"]), int(G["C"]), int(G["width"]), int(G["height"])
+    grad2d, count, radii = torch.zeros(N), torch.zeros(N), torch.zeros(N)
+    for call in range(2):
+        grads = torch.from_numpy(G[f"{mode}_grads{call}"])
+        rad = torch.from_numpy(G[f"{mode}_radii{call}"])
+        ids = torch.from_numpy(G[f"{mode}_ids{call}"]) if mode == "packed" else None
+        SRf.update_state(grad2d, count, radii, grads, rad, W, H, C if mode == "unpacked" else 1, ids)
+        assert torch.allclose(grad2d, torch.from_numpy(G[f"{mode}_grad2d_after{call}"]), rtol=1e-6, atol=1e-9)
+        assert torch.equal(count, torch.from_numpy(G[f"{mode}_count_after{call}"]))
+        assert torch.equal(radii, torch.from_numpy(G[f"{mode}_radii_after{call}"]))

@@ -51,6 +51,24 @@ def test_ssim_identities():
     assert abs(w[5].item() - 0.26601171493530273) < 1e-7 and abs(w[0].item() - 0.001028380123898387) < 1e-9
 
 
+@pytest.mark.parametrize("a,b", [(0.3, 0.7), (0.05, 0.9), (0.5, 0.5)])
+def test_ssim_known_answer_on_constant_images(a, b):
+    """Closed-form known answer (tests/parity.py::ssim_constant_images_closed_form): pins the window, the
+    constants, the zero padding of the local statistics ("same": border pixels see a partial window) and the
+    5-pixel "valid" crop, independently of any convolution code."""
+    from parity import ssim_constant_images_closed_form as kat
+
+    H, W = 23, 37
+    # float64: on constant images the variances are differences of equal numbers, and fp32 rounding noise
+    # (~1e-7) is measured against C2 = 9e-4
+    x = torch.full((1, 3, H, W), a, dtype=torch.float64)
+    y = torch.full((1, 3, H, W), b, dtype=torch.float64)
+    assert abs(SR.fused_ssim(x, y, "valid").item() - kat(a, b, H, W, "valid")) < 1e-10
+    assert abs(SR.fused_ssim(x, y, "same").item() - kat(a, b, H, W, "same")) < 1e-10
+    assert abs(SR.fused_ssim(x.float(), y.float(), "valid").item() - kat(a, b, H, W, "valid")) < 3e-4
+    assert abs(kat(a, b, H, W, "valid") - (2 * a * b + 1e-4) / (a * a + b * b + 1e-4)) < 1e-12
+
+
 def test_loss_composition_and_gradient_flows_to_first_argument_only():
     g = torch.Generator().manual_seed(5)
     a = torch.rand(1, 20, 22, 3, generator=g, requires_grad=True)
