@@ -116,9 +116,11 @@ template <bool MULTICAST, int WT, int U>
 __global__ void __launch_bounds__(kArThreads, 2)
 peer_allreduce_kernel(const unsigned long long *__restrict__ bases, unsigned long long mc_base, unsigned long long off,
                       uint64_t n4, const unsigned long long *__restrict__ flag_bases, unsigned long long flag_off,
-                      uint32_t W, uint32_t rank) {
+                      uint32_t W, uint32_t rank, int dev_mode) {
+    // dev_mode (tools/peer_bench.py, tuning builds only): 1 = no handshakes, 2 = handshakes only
     const uint32_t slot = 1 + blockIdx.x;
-    meet_peers(flag_bases, flag_off, W, rank, slot);          // every arena is complete
+    if (dev_mode != 1) meet_peers(flag_bases, flag_off, W, rank, slot);          // every arena is complete
+    if (dev_mode == 2) n4 = 0;
     const uint64_t per = (n4 + W - 1) / W;
     const uint64_t lo = (uint64_t)rank * per, hi = lo + per < n4 ? lo + per : n4;
     const uint64_t step = (uint64_t)gridDim.x * kArThreads;
@@ -187,7 +189,7 @@ peer_allreduce_kernel(const unsigned long long *__restrict__ bases, unsigned lon
             }
         }
     }
-    meet_peers(flag_bases, flag_off, W, rank, slot);          // every slice has landed everywhere
+    if (dev_mode != 1) meet_peers(flag_bases, flag_off, W, rank, slot);          // every slice has landed everywhere
 }
 
 }  // namespace b2s
@@ -236,9 +238,16 @@ extern "C" int b200splat_peer_allreduce_f32(uint32_t world, uint32_t rank, const
     if (world == 1 || n_floats == 0) return 0;
     const unsigned long long *b = reinterpret_cast<const unsigned long long *>(peer_bases);
     const unsigned long long *f = reinterpret_cast<const unsigned long long *>(flag_bases);
+    int blocks = kArBlocks, dev_mode = 0;
+#ifdef B2S_TUNING
+    if (tuning_variant() >= 3000 && tuning_variant() < 6000) {
+        dev_mode = (tuning_variant() - 3000) / 1000;
+        blocks = tuning_variant() % 1000;
+    }
+#endif
 #define B2S_AR(MC, WT, U)                                                                              \
-    peer_allreduce_kernel<MC, WT, U><<<kArBlocks, kArThreads, 0, (cudaStream_t)stream>>>(              \
-        b, multicast_base, offset_bytes, n_floats / 4, f, flag_offset_bytes, world, rank)
+    peer_allreduce_kernel<MC, WT, U><<<blocks, kArThreads, 0, (cudaStream_t)stream>>>(                 \
+        b, multicast_base, offset_bytes, n_floats / 4, f, flag_offset_bytes, world, rank, dev_mode)
     if (multicast_base != 0) B2S_AR(true, 0, 4);
     else if (world == 2) B2S_AR(false, 2, 4);
     else if (world == 4) B2S_AR(false, 4, 2);

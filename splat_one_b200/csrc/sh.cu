@@ -223,14 +223,18 @@ sh_colors_fwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, int per_v
     if (e >= (uint64_t)C * N) return;
     const uint32_t c = e / N, n = e % N;
     float r = 0.f, g = 0.f, b = 0.f;
-    if (radii[e] > 0) {
-        const float *row = coeffs + (per_view ? e : (uint64_t)n) * K * 3;
-        float cf[NB * 3];
-        load_row<NB>(row, cf, ((K * 3) % 4 == 0) && ((reinterpret_cast<uintptr_t>(coeffs) & 15) == 0));
+    // the radius, the coefficient row and the mean are requested together (the row of an invisible
+    // Gaussian is wasted bandwidth, but a visible one makes one DRAM round trip instead of two)
+    const int32_t radius = __ldcs(radii + e);
+    const float *row = coeffs + (per_view ? e : (uint64_t)n) * K * 3;
+    float cf[NB * 3];
+    load_row<NB>(row, cf, ((K * 3) % 4 == 0) && ((reinterpret_cast<uintptr_t>(coeffs) & 15) == 0));
+    float mx = 0.f, my = 0.f, mz = 0.f;
+    if (NB > 1) { mx = __ldg(means + 3 * n); my = __ldg(means + 3 * n + 1); mz = __ldg(means + 3 * n + 2); }
+    if (radius > 0) {
         float x = 0.f, y = 0.f, z = 0.f;
         if (NB > 1) {
-            const float dx = __ldg(means + 3 * n) - campos[3 * c], dy = __ldg(means + 3 * n + 1) - campos[3 * c + 1],
-                        dz = __ldg(means + 3 * n + 2) - campos[3 * c + 2];
+            const float dx = mx - campos[3 * c], dy = my - campos[3 * c + 1], dz = mz - campos[3 * c + 2];
             const float inorm = rsqrtf(dx * dx + dy * dy + dz * dz);
             x = dx * inorm; y = dy * inorm; z = dz * inorm;
         }
@@ -282,7 +286,7 @@ constexpr int kPeerCamBatch = 4;
 // One thread per Gaussian, loop over cameras: v_coeffs (shared table) and v_means are
 // written once, without atomics.  The clamp passes gradient where the clamped colour > 0.
 template <int NB, int CB>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, NB <= 16 ? 2 : 1)   // degree 4 (75 + 75 live values) keeps 1 block
 sh_colors_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, int per_view, const float *__restrict__ means,
                      const CamSource src, const float *__restrict__ coeffs,
                      const int32_t *__restrict__ radii, const float *__restrict__ colors,
@@ -309,16 +313,36 @@ sh_colors_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, int per_v
             for (uint32_t k = NB * 3; k < K * 3; k++) vrow[k] = 0.f;
         }
     };
+    // Every load of a camera batch — cotangents, clamp mask, radius, camera centre — and the coefficient row are
+    // issued BEFORE anything is consumed: gating them on `visible` (as the arithmetic is) made four dependent
+    // DRAM round trips per thread (ncu r2: 56 % long-scoreboard stalls at 16 warps per SM).  The loads of
+    // Gaussians that turn out invisible are wasted bandwidth only.
+    const bool want_means = v_means != nullptr && NB > 1 && means_cam_begin < means_cam_end;
+    const bool cf_vec = ((K * 3) % 4 == 0) && ((reinterpret_cast<uintptr_t>(coeffs) & 15) == 0);
+    float cf[NB * 3];
+    if (want_means && !per_view) load_row<NB>(coeffs + (uint64_t)n * K * 3, cf, cf_vec);
     for (uint32_t c0 = 0; c0 < C; c0 += CB) {
-      // the cotangents of CB cameras are requested before any is consumed: with the peer exchange
-      // they are NVLink loads (microseconds of latency)
-      float vin[CB][3];
+      float vin[CB][3], cin[CB][3], cpos[CB][3];
+      int32_t rad[CB];
 #pragma unroll
       for (int jc = 0; jc < CB; ++jc) {
           vin[jc][0] = vin[jc][1] = vin[jc][2] = 0.f;
+          cin[jc][0] = cin[jc][1] = cin[jc][2] = 1.f;
+          cpos[jc][0] = cpos[jc][1] = cpos[jc][2] = 0.f;
+          rad[jc] = 1;
           if (c0 + jc < C) {
+              const uint64_t e = (uint64_t)(c0 + jc) * N + n;
               const float *vrow = cam_cotangents(src, c0 + jc, N) + 3 * (size_t)n;
               vin[jc][0] = vrow[0]; vin[jc][1] = vrow[1]; vin[jc][2] = vrow[2];
+              if (colors != nullptr) {
+                  cin[jc][0] = __ldcs(colors + 3 * e); cin[jc][1] = __ldcs(colors + 3 * e + 1);
+                  cin[jc][2] = __ldcs(colors + 3 * e + 2);
+              }
+              if (radii != nullptr) rad[jc] = __ldcs(radii + e);
+              if (NB > 1) {
+                  const float *cp = cam_centre(src, c0 + jc);
+                  cpos[jc][0] = cp[0]; cpos[jc][1] = cp[1]; cpos[jc][2] = cp[2];
+              }
           }
       }
 #pragma unroll
@@ -328,27 +352,20 @@ sh_colors_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, int per_v
         const uint64_t e = (uint64_t)c * N + n;
         // radii == NULL / colors == NULL: v_colors is PRE-MASKED (zero where the Gaussian is
         // invisible or the colour was clamped) — the layout the camera-parallel exchange gathers
-        float vr = vin[jc][0], vg = vin[jc][1], vb = vin[jc][2];
-        if (colors != nullptr) {
-            vr = colors[3 * e] > 0.f ? vr : 0.f;
-            vg = colors[3 * e + 1] > 0.f ? vg : 0.f;
-            vb = colors[3 * e + 2] > 0.f ? vb : 0.f;
-        }
-        const bool visible = radii != nullptr ? (radii[e] > 0) : (vr != 0.f || vg != 0.f || vb != 0.f);
+        const float vr = cin[jc][0] > 0.f ? vin[jc][0] : 0.f, vg = cin[jc][1] > 0.f ? vin[jc][1] : 0.f,
+                    vb = cin[jc][2] > 0.f ? vin[jc][2] : 0.f;
+        const bool visible = radii != nullptr ? (rad[jc] > 0) : (vr != 0.f || vg != 0.f || vb != 0.f);
         if (visible) {
             float x = 0.f, y = 0.f, z = 0.f, inorm = 0.f;
             if (NB > 1) {
-                const float *cp = cam_centre(src, c);
-                const float dx = mx - cp[0], dy = my - cp[1], dz = mz - cp[2];
+                const float dx = mx - cpos[jc][0], dy = my - cpos[jc][1], dz = mz - cpos[jc][2];
                 inorm = rsqrtf(dx * dx + dy * dy + dz * dz);
                 x = dx * inorm; y = dy * inorm; z = dz * inorm;
             }
-            if (v_means != nullptr && NB > 1 && c >= means_cam_begin && c < means_cam_end) {
+            if (want_means && c >= means_cam_begin && c < means_cam_end) {
                 // the row is read with 128-bit loads (12 per Gaussian at K = 16): a scalar load per
                 // coefficient touches 32 cache lines per warp instruction and is L1-wavefront bound
-                float cf[NB * 3];
-                load_row<NB>(coeffs + (per_view ? e : (uint64_t)n) * K * 3, cf,
-                             ((K * 3) % 4 == 0) && ((reinterpret_cast<uintptr_t>(coeffs) & 15) == 0));
+                if (per_view) load_row<NB>(coeffs + e * K * 3, cf, cf_vec);
                 float vx = 0.f, vy = 0.f, vz = 0.f;
                 sh_for_each_basis<true>(deg, x, y, z, [&](int k, float B, float Bx, float By, float Bz) {
                     vc[3 * k] += B * vr; vc[3 * k + 1] += B * vg; vc[3 * k + 2] += B * vb;
@@ -655,8 +672,11 @@ sh_colors_staged_fwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, co
 // One lane per Gaussian, loop over cameras (like sh_colors_bwd_kernel: same conventions for
 // radii / colors == NULL and the means camera window); gradient rows leave through smem.
 // CFS: the coefficient rows stay in shared memory (a second buffer) and are read from there
-// inside the basis loop instead of living in 3 (NB-1) registers: 140 -> ~96 registers, 12 -> 20
-// warps per SM.  Only for odd row lengths (scalar row reads are conflict-free then).
+// inside the basis loop instead of living in 3 (NB-1) registers: 140 -> ~96 registers.  Odd row
+// lengths (the split table: 45 floats) read them conflict-free; rows that are a multiple of 4 floats (the
+// whole table: 48) keep the 16-byte-granular stride of the vector staging (52) and pay 4-way conflicts on
+// these scalar reads — still far cheaper than the thread-per-row kernel's 32-lines-per-instruction
+// global accesses (ncu r2: that kernel is L1 tag-rate bound at 0.105 ms).
 template <int NB, bool SPLIT, bool CFS, int CB>
 __global__ void __launch_bounds__(32 * kStageWarps, CFS ? 5 : 1)
 sh_colors_staged_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, const float *__restrict__ means,
@@ -701,32 +721,41 @@ sh_colors_staged_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, co
     float vmx = 0.f, vmy = 0.f, vmz = 0.f;
     const float mx = __ldg(means + 3 * (size_t)n), my = __ldg(means + 3 * (size_t)n + 1), mz = __ldg(means + 3 * (size_t)n + 2);
     for (uint32_t c0 = 0; c0 < C && mine; c0 += CB) {
-      float vin[CB][3];
+      // all loads of the camera batch are in flight before the first is consumed (see sh_colors_bwd_kernel)
+      float vin[CB][3], cin[CB][3], cpos[CB][3];
+      int32_t rad[CB];
 #pragma unroll
       for (int jc = 0; jc < CB; ++jc) {
           vin[jc][0] = vin[jc][1] = vin[jc][2] = 0.f;
+          cin[jc][0] = cin[jc][1] = cin[jc][2] = 1.f;
+          cpos[jc][0] = cpos[jc][1] = cpos[jc][2] = 0.f;
+          rad[jc] = 1;
           if (c0 + jc < C) {
+              const uint64_t e = (uint64_t)(c0 + jc) * N + n;
               const float *vrow = cam_cotangents(src, c0 + jc, N) + 3 * (size_t)n;
               vin[jc][0] = vrow[0]; vin[jc][1] = vrow[1]; vin[jc][2] = vrow[2];
+              if (colors != nullptr) {
+                  cin[jc][0] = __ldcs(colors + 3 * e); cin[jc][1] = __ldcs(colors + 3 * e + 1);
+                  cin[jc][2] = __ldcs(colors + 3 * e + 2);
+              }
+              if (radii != nullptr) rad[jc] = __ldcs(radii + e);
+              if (NB > 1) {
+                  const float *cp = cam_centre(src, c0 + jc);
+                  cpos[jc][0] = cp[0]; cpos[jc][1] = cp[1]; cpos[jc][2] = cp[2];
+              }
           }
       }
 #pragma unroll
       for (int jc = 0; jc < CB; ++jc) {
         const uint32_t c = c0 + jc;
         if (c >= C) break;
-        const uint64_t e = (uint64_t)c * N + n;
-        float vr = vin[jc][0], vg = vin[jc][1], vb = vin[jc][2];
-        if (colors != nullptr) {
-            vr = colors[3 * e] > 0.f ? vr : 0.f;
-            vg = colors[3 * e + 1] > 0.f ? vg : 0.f;
-            vb = colors[3 * e + 2] > 0.f ? vb : 0.f;
-        }
-        const bool visible = radii != nullptr ? (radii[e] > 0) : (vr != 0.f || vg != 0.f || vb != 0.f);
+        const float vr = cin[jc][0] > 0.f ? vin[jc][0] : 0.f, vg = cin[jc][1] > 0.f ? vin[jc][1] : 0.f,
+                    vb = cin[jc][2] > 0.f ? vin[jc][2] : 0.f;
+        const bool visible = radii != nullptr ? (rad[jc] > 0) : (vr != 0.f || vg != 0.f || vb != 0.f);
         if (!visible) continue;
         float x = 0.f, y = 0.f, z = 0.f, inorm = 0.f;
         if (NB > 1) {
-            const float *cp = cam_centre(src, c);
-            const float dx = mx - cp[0], dy = my - cp[1], dz = mz - cp[2];
+            const float dx = mx - cpos[jc][0], dy = my - cpos[jc][1], dz = mz - cpos[jc][2];
             inorm = rsqrtf(dx * dx + dy * dy + dz * dz);
             x = dx * inorm; y = dy * inorm; z = dz * inorm;
         }
@@ -842,6 +871,9 @@ static int launch_colors_bwd(const char *where, uint32_t C, uint32_t N, uint32_t
                              const float *means, const CamSource &src, const float *coeffs, const int32_t *radii,
                              const float *colors, float *v_coeffs, float *v_means, uint32_t means_cam_begin,
                              uint32_t means_cam_end, cudaStream_t st) {
+    // (Routing a whole [N,K,3] table with 16-byte rows through the staged kernel — coalesced row traffic, coefficient
+    // rows in shared memory — measured 0.107 ms against 0.105 ms for this kernel at config B: both sit at the same
+    // 16 warps per SM, so the thread-per-row kernel stays the path of the un-split table.)
     const unsigned grid = div_up(N, kThreads);
 #define B2S_SHC(NBV)                                                                                                  \
     do {                                                                                                              \
@@ -980,11 +1012,15 @@ static int launch_staged_bwd_cb(uint32_t C, uint32_t N, uint32_t K, uint32_t deg
                              uint32_t ce, size_t smem, cudaStream_t st) {
     const unsigned grid = div_up(N, 32 * kStageWarps);
     const uint32_t R = (K - (SPLIT ? 1 : 0)) * 3;
-    const bool cfs = stage_row_stride(R) == R && 2 * smem <= 48 * 1024;
+    (void)R;
+    const bool cfs = 2 * smem <= 100 * 1024;
 #define B2S_SHS(NBV)                                                                                                 \
     do {                                                                                                             \
         if (cfs) {                                                                                                   \
-            sh_colors_staged_bwd_kernel<NBV, SPLIT, true, CB><<<grid, 32 * kStageWarps, 2 * smem, st>>>(                 \
+            auto kern_c = sh_colors_staged_bwd_kernel<NBV, SPLIT, true, CB>;                                         \
+            if (2 * smem > 48 * 1024)                                                                                \
+                cudaFuncSetAttribute(kern_c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * smem));         \
+            kern_c<<<grid, 32 * kStageWarps, 2 * smem, st>>>(                                                        \
                 C, N, K, deg, means, src, sh0, rest, radii, colors, v_sh0, v_rest, v_means, cb, ce);                 \
         } else {                                                                                                     \
             auto kern = sh_colors_staged_bwd_kernel<NBV, SPLIT, false, CB>;                                              \
