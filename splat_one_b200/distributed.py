@@ -449,7 +449,8 @@ def sparse_allreduce(grads: Sequence[Tensor], group=None, dense_threshold: float
     out, o = [], 0
     for g, w in zip(grads, widths):
         vals = rows_cat[:, o:o + w].reshape((total,) + tuple(g.shape[1:])).contiguous()
-        out.append(torch.sparse_coo_tensor(ids_cat[None], vals, size=g.shape, is_coalesced=False))
+        out.append(torch.sparse_coo_tensor(ids_cat[None], vals, size=g.shape, is_coalesced=False,
+                                           check_invariants=False))
         o += w
     return out
 

@@ -963,7 +963,7 @@ class _FullyFusedProjectionPacked(torch.autograd.Function):
             if values is None or not sparse_grad:
                 return values
             return torch.sparse_coo_tensor(indices=gaussian_ids[None], values=values, size=like.size(),
-                                           is_coalesced=len(viewmats) == 1)
+                                           is_coalesced=len(viewmats) == 1, check_invariants=False)
 
         if sparse_grad and ctx.dense_means_grad and need[0]:
             g_means = torch.zeros_like(means).index_add_(0, gaussian_ids, v_means)
