@@ -113,7 +113,7 @@ struct SmemSink {
         float *row = buf + (cnt * NV) * ROW + lane;
 #pragma unroll
         for (int k = 0; k < NV; ++k) row[k * ROW] = nv[k];
-        if (lane == 0) gid[cnt] = g;
+        gid[cnt] = g;  // every lane stores the same word: cheaper than predicating one
         if (++cnt == SLOTS) flush(lane);
     }
 

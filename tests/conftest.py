@@ -53,3 +53,34 @@ def _build_native():
     from oracle import raster_ref
 
     raster_ref.build()
+
+
+def pytest_terminal_summary(terminalreporter, exitstatus, config):
+    """Strict-bound accounting of the parity helpers (tests/parity.py): how many compared elements fell
+    outside 1e-4 abs (images) / 1e-3 of the tensor's scale (gradients), per kind."""
+    try:
+        import parity
+    except Exception:
+        return
+    log = parity.STRICT_LOG
+    if not log:
+        return
+    import json
+
+    for kind in ("image", "grad"):
+        rows = [r for r in log if r["kind"] == kind]
+        if not rows:
+            continue
+        n = sum(r["n"] for r in rows)
+        out = sum(r["outside_strict"] for r in rows)
+        dirty = [r for r in rows if r["outside_strict"]]
+        worst = max((r["worst"] for r in rows), default=0.0)
+        terminalreporter.write_line(
+            f"parity[{kind}]: {len(rows)} comparisons, {n} elements, {out} outside the strict bound "
+            f"({out / max(n, 1):.2e}) in {len(dirty)} comparisons; worst {'abs' if kind == 'image' else 'rel-to-scale'} "
+            f"error {worst:.3e}")
+    path = os.environ.get("B200SPLAT_PARITY_LOG")
+    if path:
+        with open(path, "w") as f:
+            for r in log:
+                f.write(json.dumps(r) + "\n")
