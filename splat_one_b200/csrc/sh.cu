@@ -285,7 +285,8 @@ constexpr int kPeerCamBatch = 4;
 
 // One thread per Gaussian, loop over cameras: v_coeffs (shared table) and v_means are
 // written once, without atomics.  The clamp passes gradient where the clamped colour > 0.
-template <int NB, int CB>
+// MASKED: the cotangents arrive pre-masked (peer exchange): no radii / clamp-mask loads are compiled in.
+template <int NB, int CB, bool MASKED>
 __global__ void __launch_bounds__(kThreads, NB <= 16 ? 2 : 1)   // degree 4 (75 + 75 live values) keeps 1 block
 sh_colors_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, int per_view, const float *__restrict__ means,
                      const CamSource src, const float *__restrict__ coeffs,
@@ -319,8 +320,11 @@ sh_colors_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, int per_v
     // Gaussians that turn out invisible are wasted bandwidth only.
     const bool want_means = v_means != nullptr && NB > 1 && means_cam_begin < means_cam_end;
     const bool cf_vec = ((K * 3) % 4 == 0) && ((reinterpret_cast<uintptr_t>(coeffs) & 15) == 0);
+    // The row is hoisted only where one camera at a time is in flight (CB == 1): with CB cameras' cotangents
+    // prefetched (peer exchange) 48 more live registers across the loop spill (measured 0.233 -> 0.41 ms).
+    constexpr bool kHoistRow = CB == 1;
     float cf[NB * 3];
-    if (want_means && !per_view) load_row<NB>(coeffs + (uint64_t)n * K * 3, cf, cf_vec);
+    if (kHoistRow && want_means && !per_view) load_row<NB>(coeffs + (uint64_t)n * K * 3, cf, cf_vec);
     for (uint32_t c0 = 0; c0 < C; c0 += CB) {
       float vin[CB][3], cin[CB][3], cpos[CB][3];
       int32_t rad[CB];
@@ -334,12 +338,12 @@ sh_colors_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, int per_v
               const uint64_t e = (uint64_t)(c0 + jc) * N + n;
               const float *vrow = cam_cotangents(src, c0 + jc, N) + 3 * (size_t)n;
               vin[jc][0] = vrow[0]; vin[jc][1] = vrow[1]; vin[jc][2] = vrow[2];
-              if (colors != nullptr) {
+              if (!MASKED && colors != nullptr) {
                   cin[jc][0] = __ldcs(colors + 3 * e); cin[jc][1] = __ldcs(colors + 3 * e + 1);
                   cin[jc][2] = __ldcs(colors + 3 * e + 2);
               }
-              if (radii != nullptr) rad[jc] = __ldcs(radii + e);
-              if (NB > 1) {
+              if (!MASKED && radii != nullptr) rad[jc] = __ldcs(radii + e);
+              if (NB > 1 && kHoistRow) {
                   const float *cp = cam_centre(src, c0 + jc);
                   cpos[jc][0] = cp[0]; cpos[jc][1] = cp[1]; cpos[jc][2] = cp[2];
               }
@@ -352,12 +356,16 @@ sh_colors_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, int per_v
         const uint64_t e = (uint64_t)c * N + n;
         // radii == NULL / colors == NULL: v_colors is PRE-MASKED (zero where the Gaussian is
         // invisible or the colour was clamped) — the layout the camera-parallel exchange gathers
-        const float vr = cin[jc][0] > 0.f ? vin[jc][0] : 0.f, vg = cin[jc][1] > 0.f ? vin[jc][1] : 0.f,
-                    vb = cin[jc][2] > 0.f ? vin[jc][2] : 0.f;
-        const bool visible = radii != nullptr ? (rad[jc] > 0) : (vr != 0.f || vg != 0.f || vb != 0.f);
+        const float vr = (MASKED || cin[jc][0] > 0.f) ? vin[jc][0] : 0.f, vg = (MASKED || cin[jc][1] > 0.f) ? vin[jc][1] : 0.f,
+                    vb = (MASKED || cin[jc][2] > 0.f) ? vin[jc][2] : 0.f;
+        const bool visible = (!MASKED && radii != nullptr) ? (rad[jc] > 0) : (vr != 0.f || vg != 0.f || vb != 0.f);
         if (visible) {
             float x = 0.f, y = 0.f, z = 0.f, inorm = 0.f;
             if (NB > 1) {
+                if (!kHoistRow) {  // CB cameras in flight: the centre (a few cached words) is read on use
+                    const float *cp = cam_centre(src, c);
+                    cpos[jc][0] = cp[0]; cpos[jc][1] = cp[1]; cpos[jc][2] = cp[2];
+                }
                 const float dx = mx - cpos[jc][0], dy = my - cpos[jc][1], dz = mz - cpos[jc][2];
                 inorm = rsqrtf(dx * dx + dy * dy + dz * dz);
                 x = dx * inorm; y = dy * inorm; z = dz * inorm;
@@ -365,7 +373,7 @@ sh_colors_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, int per_v
             if (want_means && c >= means_cam_begin && c < means_cam_end) {
                 // the row is read with 128-bit loads (12 per Gaussian at K = 16): a scalar load per
                 // coefficient touches 32 cache lines per warp instruction and is L1-wavefront bound
-                if (per_view) load_row<NB>(coeffs + e * K * 3, cf, cf_vec);
+                if (per_view || !kHoistRow) load_row<NB>(coeffs + (per_view ? e : (uint64_t)n) * K * 3, cf, cf_vec);
                 float vx = 0.f, vy = 0.f, vz = 0.f;
                 sh_for_each_basis<true>(deg, x, y, z, [&](int k, float B, float Bx, float By, float Bz) {
                     vc[3 * k] += B * vr; vc[3 * k + 1] += B * vg; vc[3 * k + 2] += B * vb;
@@ -720,6 +728,7 @@ sh_colors_staged_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, co
     for (int k = 0; k < NFA; k++) vc[k] = 0.f;
     float vmx = 0.f, vmy = 0.f, vmz = 0.f;
     const float mx = __ldg(means + 3 * (size_t)n), my = __ldg(means + 3 * (size_t)n + 1), mz = __ldg(means + 3 * (size_t)n + 2);
+    constexpr bool MASKED = CB > 1;   // peer exchange: cotangents arrive pre-masked, radii / colors are NULL
     for (uint32_t c0 = 0; c0 < C && mine; c0 += CB) {
       // all loads of the camera batch are in flight before the first is consumed (see sh_colors_bwd_kernel)
       float vin[CB][3], cin[CB][3], cpos[CB][3];
@@ -734,12 +743,12 @@ sh_colors_staged_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, co
               const uint64_t e = (uint64_t)(c0 + jc) * N + n;
               const float *vrow = cam_cotangents(src, c0 + jc, N) + 3 * (size_t)n;
               vin[jc][0] = vrow[0]; vin[jc][1] = vrow[1]; vin[jc][2] = vrow[2];
-              if (colors != nullptr) {
+              if (!MASKED && colors != nullptr) {
                   cin[jc][0] = __ldcs(colors + 3 * e); cin[jc][1] = __ldcs(colors + 3 * e + 1);
                   cin[jc][2] = __ldcs(colors + 3 * e + 2);
               }
-              if (radii != nullptr) rad[jc] = __ldcs(radii + e);
-              if (NB > 1) {
+              if (!MASKED && radii != nullptr) rad[jc] = __ldcs(radii + e);
+              if (NB > 1 && !MASKED) {
                   const float *cp = cam_centre(src, c0 + jc);
                   cpos[jc][0] = cp[0]; cpos[jc][1] = cp[1]; cpos[jc][2] = cp[2];
               }
@@ -749,12 +758,16 @@ sh_colors_staged_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, co
       for (int jc = 0; jc < CB; ++jc) {
         const uint32_t c = c0 + jc;
         if (c >= C) break;
-        const float vr = cin[jc][0] > 0.f ? vin[jc][0] : 0.f, vg = cin[jc][1] > 0.f ? vin[jc][1] : 0.f,
-                    vb = cin[jc][2] > 0.f ? vin[jc][2] : 0.f;
-        const bool visible = radii != nullptr ? (rad[jc] > 0) : (vr != 0.f || vg != 0.f || vb != 0.f);
+        const float vr = (MASKED || cin[jc][0] > 0.f) ? vin[jc][0] : 0.f, vg = (MASKED || cin[jc][1] > 0.f) ? vin[jc][1] : 0.f,
+                    vb = (MASKED || cin[jc][2] > 0.f) ? vin[jc][2] : 0.f;
+        const bool visible = (!MASKED && radii != nullptr) ? (rad[jc] > 0) : (vr != 0.f || vg != 0.f || vb != 0.f);
         if (!visible) continue;
         float x = 0.f, y = 0.f, z = 0.f, inorm = 0.f;
         if (NB > 1) {
+            if (MASKED) {  // CB cameras in flight: the centre (a few cached words) is read on use
+                const float *cp = cam_centre(src, c);
+                cpos[jc][0] = cp[0]; cpos[jc][1] = cp[1]; cpos[jc][2] = cp[2];
+            }
             const float dx = mx - cpos[jc][0], dy = my - cpos[jc][1], dz = mz - cpos[jc][2];
             inorm = rsqrtf(dx * dx + dy * dy + dz * dz);
             x = dx * inorm; y = dy * inorm; z = dz * inorm;
@@ -878,10 +891,10 @@ static int launch_colors_bwd(const char *where, uint32_t C, uint32_t N, uint32_t
 #define B2S_SHC(NBV)                                                                                                  \
     do {                                                                                                              \
         if (src.bases != nullptr)                                                                                     \
-            sh_colors_bwd_kernel<NBV, kPeerCamBatch><<<grid, kThreads, 0, st>>>(                                      \
+            sh_colors_bwd_kernel<NBV, kPeerCamBatch, true><<<grid, kThreads, 0, st>>>(                                      \
                 C, N, K, deg, per_view, means, src, coeffs, radii, colors, v_coeffs, v_means, means_cam_begin, means_cam_end); \
         else                                                                                                          \
-            sh_colors_bwd_kernel<NBV, 1><<<grid, kThreads, 0, st>>>(                                                  \
+            sh_colors_bwd_kernel<NBV, 1, false><<<grid, kThreads, 0, st>>>(                                                  \
                 C, N, K, deg, per_view, means, src, coeffs, radii, colors, v_coeffs, v_means, means_cam_begin, means_cam_end); \
     } while (0)
     switch (deg) {

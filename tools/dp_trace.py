@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Developer tool: device timeline of one camera-sharded data-parallel step on rank 0
 (torchrun --nproc-per-node N tools/dp_trace.py): every device operation with duration and the
-idle gap in front of it, to see what the collectives and the host cost at N ranks."""
+idle gap in front of it, to see what the exchange and the host cost at N ranks.
+DP_EXCHANGE=peer (default: own kernels over NVLink peer memory) | nccl; DP_DEFER=1: overlapped order."""
 import os
 import sys
 
@@ -13,7 +14,7 @@ from torch.profiler import ProfilerActivity, profile  # noqa: E402
 
 import splat_one_b200 as S  # noqa: E402
 from splat_one_b200 import synthetic  # noqa: E402
-from splat_one_b200.distributed import GradArena, camera_parallel  # noqa: E402
+from splat_one_b200.distributed import GradArena, PeerExchange, arena_layout, camera_parallel  # noqa: E402
 
 world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -25,17 +26,22 @@ params = [scene[k].to(dev).requires_grad_() for k in ("means", "quats", "scales"
 vm, Ks = scene["viewmats"][rank::world].to(dev), scene["Ks"][rank::world].to(dev)
 g = torch.Generator().manual_seed(1000 + rank)
 vc, va = torch.randn(1, H, W, 3, generator=g).to(dev), torch.randn(1, H, W, 1, generator=g).to(dev)
-arena = GradArena(params)
+peer = PeerExchange(N, 1, arena_floats=arena_layout(params)[1]) if os.environ.get("DP_EXCHANGE", "peer") == "peer" else None
+defer = os.environ.get("DP_DEFER", "0") == "1"
+arena = GradArena(params, peer=peer)
 
 
 def step():
     for p in params:
         p.grad = None
     rc, ra, _ = S.rasterization(*params, vm, Ks, W, H, sh_degree=3, packed=False)
-    with arena.sink(), camera_parallel() as cp:
+    with arena.sink(), camera_parallel(peer=peer, defer=defer) as cp:
         torch.autograd.backward([rc, ra], [vc, va])
-    arena.gather_from_params()
-    arena.all_reduce(skip_ptrs=cp.reduced_ptrs)
+    if defer:
+        cp.finish(arena)
+    else:
+        arena.gather_from_params()
+        arena.all_reduce(skip_ptrs=cp.reduced_ptrs)
 
 
 for _ in range(8):
@@ -49,7 +55,8 @@ for _ in range(20):
 e1.record()
 torch.cuda.synchronize()
 if rank == 0:
-    print(f"world {world}: {e0.elapsed_time(e1) / 20:.3f} ms/step (no profiler)")
+    print(f"world {world}, exchange {'peer' if peer is not None else 'nccl'}{' overlapped' if defer else ''}: "
+          f"{e0.elapsed_time(e1) / 20:.3f} ms/step (no profiler)")
 dist.barrier()
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for _ in range(3):
@@ -66,7 +73,7 @@ if rank == 0:
     for e in last:
         s_, e_ = e.time_range.start, e.time_range.end
         gp = max(0.0, s_ - prev_end)
-        if gp > 3.0 or (e_ - s_) > 15.0 or "nccl" in e.name.lower():
+        if gp > 3.0 or (e_ - s_) > 15.0 or "nccl" in e.name.lower() or "peer" in e.name.lower():
             print(f"{s_ - t0:9.1f} {gp:7.1f} {e_ - s_:8.1f}  {e.name[:90]}")
         busy += e_ - s_
         gap += gp
