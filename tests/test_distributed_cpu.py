@@ -177,6 +177,11 @@ def _async_worker(rank, world, port, out_dir):
         assert torch.all(arena.views[1] == float(rank + 2))  # skipped: still the local value
         # sync call returns the last handle (or None) as before
         assert arena.all_reduce(skip_ptrs={p.data_ptr() for p in P}) is None
+        # only_ptrs: just that parameter's segment (the split all-reduce of the overlapped peer exchange)
+        before = [v.clone() for v in arena.views]
+        arena.all_reduce(only_ptrs={P[1].data_ptr()})
+        assert torch.equal(arena.views[0], before[0]) and torch.equal(arena.views[2], before[2])
+        assert torch.all(arena.views[1] == 2 + 3)
         if rank == 0:
             open(os.path.join(out_dir, "ok"), "w").write("ok")
     finally:
