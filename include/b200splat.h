@@ -59,7 +59,8 @@ B200SPLAT_API int b200splat_copy_small(const void *src, void *dst_pinned_host, u
  * a2  fully_fused_projection_fwd        CS/bindings.h:95-116, kernel
  *     CS/fully_fused_projection_fwd.cu:20-216.
  * covars [N,6] XOR (quats [N,4], scales [N,3]).  compensations may be NULL.
- * Outputs [C,N,...]; entries with radii==0 are left untouched except radii.
+ * Outputs [C,N,...]; EVERY entry is written: culled pairs get radii = 0 and zeros in the other outputs
+ * (the reference leaves those uninitialised), so the caller needs no zero-fill pass.
  * ---------------------------------------------------------------------------------- */
 B200SPLAT_API int b200splat_projection_fwd(
     uint32_t C, uint32_t N,

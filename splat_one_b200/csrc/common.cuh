@@ -30,6 +30,10 @@ int fail_cuda(const char *where, cudaError_t e);
         if (!(cond)) return b2s::fail(where, msg);                                      \
     } while (0)
 
+// means2d arrays are read and written as float2: an 8-byte aligned base is part of the ABI contract
+#define B2S_REQUIRE_ALIGNED8(ptr, where)                                                \
+    B2S_REQUIRE((ptr) == nullptr || (reinterpret_cast<uintptr_t>(ptr) & 7) == 0, where, #ptr " must be 8-byte aligned (it is accessed as float2)")
+
 // Developer A/B switch for kernel variants (tools/raster_bench.py); 0 = the shipped default.  The
 // environment variable is read ONCE, when the library is loaded (capi.cu); the alternative
 // instances are only compiled into builds made with B200SPLAT_TUNING=1 (-DB2S_TUNING).

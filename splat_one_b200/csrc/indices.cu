@@ -115,6 +115,7 @@ extern "C" int b200splat_raster_indices_count(uint32_t range_start, uint32_t ran
                                               int32_t *chunk_cnts, int64_t *chunk_cum, int64_t *n_elems_out,
                                               void *scan_workspace, size_t scan_workspace_bytes_, void *stream) {
     const char *where = "b200splat_raster_indices_count";
+    B2S_REQUIRE_ALIGNED8(means2d, where);
     cudaStream_t st = (cudaStream_t)stream;
     B2S_REQUIRE(tile_size >= 1 && tile_size <= 32, where, "tile_size must be in [1, 32]");
     B2S_REQUIRE(n_isects <= 0x7fffffffull, where, "n_isects exceeds int32 offsets");
@@ -145,6 +146,7 @@ extern "C" int b200splat_raster_indices_fill(uint32_t range_start, uint32_t rang
                                              const int32_t *chunk_cnts, const int64_t *chunk_cum,
                                              int64_t *gaussian_ids, int64_t *pixel_ids, void *stream) {
     const char *where = "b200splat_raster_indices_fill";
+    B2S_REQUIRE_ALIGNED8(means2d, where);
     B2S_REQUIRE(tile_size >= 1 && tile_size <= 32, where, "tile_size must be in [1, 32]");
     B2S_REQUIRE(n_isects <= 0x7fffffffull, where, "n_isects exceeds int32 offsets");
     if ((uint64_t)C * H * W == 0 || n_isects == 0 || N == 0) return 0;

@@ -130,6 +130,7 @@ extern "C" int b200splat_isect_count(int packed, uint32_t C, uint32_t N, uint32_
                                      int64_t *n_isects_out, void *scan_workspace, size_t scan_workspace_bytes_,
                                      void *stream) {
     const char *where = "b200splat_isect_count";
+    B2S_REQUIRE_ALIGNED8(means2d, where);
     cudaStream_t st = (cudaStream_t)stream;
     B2S_REQUIRE(tile_size > 0, where, "tile_size must be positive");
     const uint64_t n_elems = packed ? (uint64_t)nnz : (uint64_t)C * N;
@@ -159,6 +160,7 @@ extern "C" int b200splat_isect_fill(int packed, uint32_t C, uint32_t N, uint32_t
                                     const int64_t *cum_tiles, uint32_t tile_size, uint32_t tile_width,
                                     uint32_t tile_height, int64_t *isect_ids, int32_t *flatten_ids, void *stream) {
     const char *where = "b200splat_isect_fill";
+    B2S_REQUIRE_ALIGNED8(means2d, where);
     const uint64_t n_elems = packed ? (uint64_t)nnz : (uint64_t)C * N;
     B2S_REQUIRE(!packed || camera_ids != nullptr, where, "camera_ids required when packed");
     const uint32_t n_tiles = tile_width * tile_height;

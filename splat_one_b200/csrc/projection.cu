@@ -51,7 +51,13 @@ projection_fwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
     const M3 covar = load_covar(covars, quats, scales, gid, q, s);
     ProjOut o;
     if (!project_one(mean, covar, cam, W, H, eps2d, near_plane, far_plane, radius_clip, camera_model, false, o)) {
+        // culled rows are written as zeros HERE (the reference leaves them uninitialised): the caller needs no
+        // zero-fill pass over the outputs
         radii[idx] = 0;
+        reinterpret_cast<float2 *>(means2d)[idx] = make_float2(0.f, 0.f);
+        depths[idx] = 0.f;
+        conics[3 * idx] = 0.f; conics[3 * idx + 1] = 0.f; conics[3 * idx + 2] = 0.f;
+        if (compensations != nullptr) compensations[idx] = 0.f;
         return;
     }
     radii[idx] = (int32_t)o.radius;
@@ -374,6 +380,7 @@ extern "C" int b200splat_projection_fwd(uint32_t C, uint32_t N, const float *mea
                                         float *means2d, float *depths, float *conics, float *compensations,
                                         void *stream) {
     const char *where = "b200splat_projection_fwd";
+    B2S_REQUIRE_ALIGNED8(means2d, where);
     B2S_REQUIRE(camera_model >= 0 && camera_model <= 3, where, "unknown camera model");
     B2S_REQUIRE(covars != nullptr || (quats != nullptr && scales != nullptr), where, "covars or (quats, scales) required");
     if ((uint64_t)C * N == 0) return 0;
@@ -472,6 +479,7 @@ extern "C" int b200splat_projection_packed_fill(uint32_t C, uint32_t N, const fl
                                                 float *means2d, float *depths, float *conics, float *compensations,
                                                 void *stream) {
     const char *where = "b200splat_projection_packed_fill";
+    B2S_REQUIRE_ALIGNED8(means2d, where);
     cudaStream_t st = (cudaStream_t)stream;
     B2S_REQUIRE(C <= 65535, where, "C exceeds the grid.y limit (65535)");
     if ((uint64_t)C * N == 0) {

@@ -587,6 +587,7 @@ extern "C" int b200splat_rasterize_bwd(uint32_t C, uint32_t n_gauss, uint64_t n_
                                        float *v_means2d_abs, float *v_means2d, float *v_conics, float *v_colors,
                                        float *v_opacities, void *stream) {
     const char *where = "b200splat_rasterize_bwd";
+    B2S_REQUIRE_ALIGNED8(means2d, where);
     (void)n_gauss;
     if (records != nullptr) {
         B2S_REQUIRE(tile_size == kQTile && channels >= 1 && channels <= 4, where,

@@ -369,6 +369,7 @@ extern "C" int b200splat_rasterize_pack(uint32_t n_gauss, uint32_t channels, con
                                         const float *conics, const float *colors, const float *opacities,
                                         void *records, void *stream) {
     const char *where = "b200splat_rasterize_pack";
+    B2S_REQUIRE_ALIGNED8(means2d, where);
     B2S_REQUIRE(channels >= 1 && channels <= 4, where, "records hold at most 4 channels");
     B2S_REQUIRE((reinterpret_cast<uintptr_t>(records) & 15) == 0, where, "records must be 16-byte aligned");
     if (n_gauss == 0) return 0;
@@ -387,6 +388,7 @@ extern "C" int b200splat_rasterize_fwd(uint32_t C, uint32_t n_gauss, uint64_t n_
                                        const void *records, uint8_t *quad_masks,
                                        float *render_colors, float *render_alphas, int32_t *last_ids, void *stream) {
     const char *where = "b200splat_rasterize_fwd";
+    B2S_REQUIRE_ALIGNED8(means2d, where);
     (void)n_gauss;
     if (records != nullptr) {
         B2S_REQUIRE(tile_size == kQTile && channels >= 1 && channels <= 4, where,

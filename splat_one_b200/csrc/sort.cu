@@ -774,6 +774,7 @@ extern "C" int b200splat_isect_tile_order(int packed, uint32_t C, uint32_t N, ui
                                           int64_t *isect_ids, int32_t *flatten_ids, int32_t *offsets, void *workspace,
                                           size_t workspace_bytes, void *stream) {
     const char *where = "b200splat_isect_tile_order";
+    B2S_REQUIRE_ALIGNED8(means2d, where);
     cudaStream_t st = (cudaStream_t)stream;
     const uint64_t n_elems = packed ? (uint64_t)nnz : (uint64_t)C * N;
     B2S_REQUIRE(!packed || camera_ids != nullptr, where, "camera_ids required when packed");
@@ -815,6 +816,7 @@ extern "C" int b200splat_isect_sorted(int packed, uint32_t C, uint32_t N, uint32
                                       int32_t *flatten_ids, int32_t *offsets, void *workspace, size_t workspace_bytes,
                                       void *stream) {
     const char *where = "b200splat_isect_sorted";
+    B2S_REQUIRE_ALIGNED8(means2d, where);
     const uint64_t n_elems = packed ? (uint64_t)nnz : (uint64_t)C * N;
     B2S_REQUIRE(n_elems <= 0xffffffffull, where, "more than 2^32 (camera, Gaussian) pairs");
     if (n_isects == 0 || n_elems == 0) return 0;

@@ -321,6 +321,7 @@ extern "C" int b200splat_proj_fwd(uint32_t C, uint32_t N, const float *means, co
                                   uint32_t W, uint32_t H, int camera_model, float *means2d, float *covars2d,
                                   void *stream) {
     const char *where = "b200splat_proj_fwd";
+    B2S_REQUIRE_ALIGNED8(means2d, where);
     B2S_REQUIRE(camera_model >= 0 && camera_model <= 3, where, "unknown camera model");
     if ((uint64_t)C * N == 0) return 0;
     B2S_REQUIRE(((uintptr_t)covars2d & 15) == 0 && ((uintptr_t)means2d & 7) == 0, where,

@@ -265,6 +265,14 @@ def _grad_out(like: Tensor) -> Tensor:
     return torch.empty_like(like)
 
 
+def _aligned8(t: Optional[Tensor]) -> Optional[Tensor]:
+    """means2d arrays are accessed as float2 by the kernels (8-byte aligned base, checked at the C ABI): a
+    contiguous view that starts at an odd float offset is re-packed."""
+    if t is None or t.data_ptr() % 8 == 0:
+        return t
+    return t.clone(memory_format=torch.contiguous_format)
+
+
 def _aligned16(t: Optional[Tensor]) -> Optional[Tensor]:
     """128-bit loads need 16-byte aligned bases; views into odd offsets are re-packed."""
     if t is None or t.data_ptr() % 16 == 0:
@@ -828,13 +836,14 @@ class _FullyFusedProjection(torch.autograd.Function):
         quats = _aligned16(quats)
         C, N = viewmats.shape[0], means.shape[0]
         dev = means.device
-        # one allocation, one fill: radii | means2d | depths | conics (| compensations) as views
-        # of a zeroed flat buffer (culled entries read as zeros; the reference leaves them
-        # uninitialised, CS/fully_fused_projection_fwd.cu:256-260)
+        # one allocation: radii | means2d | depths | conics (| compensations) as views of a flat buffer;
+        # the kernel writes EVERY row (zeros for culled entries, which the reference leaves uninitialised,
+        # CS/fully_fused_projection_fwd.cu:256-260), so no fill pass is needed
         n = C * N
-        flat = torch.zeros((n * (8 if calc_compensations else 7),), device=dev, dtype=torch.float32)
-        radii = flat[:n].view(torch.int32).view(C, N)
-        means2d = flat[n:3 * n].view(C, N, 2)
+        flat = torch.empty((n * (8 if calc_compensations else 7),), device=dev, dtype=torch.float32)
+        # means2d first: it is read and written as float2 (8-byte aligned for every C*N, odd ones included)
+        means2d = flat[:2 * n].view(C, N, 2)
+        radii = flat[2 * n:3 * n].view(torch.int32).view(C, N)
         depths = flat[3 * n:4 * n].view(C, N)
         conics = flat[4 * n:7 * n].view(C, N, 3)
         compensations = flat[7 * n:8 * n].view(C, N) if calc_compensations else None
@@ -1020,7 +1029,7 @@ def _isect_tiles_begin(
         assert depths.shape == (C, N), depths.size()
         nnz = 0
 
-    means2d = means2d.contiguous()
+    means2d = _aligned8(means2d.contiguous())
     radii = radii.contiguous()
     depths = depths.contiguous()
     _check_cuda(means2d, radii, depths, camera_ids, gaussian_ids)
@@ -1402,7 +1411,7 @@ def rasterize_to_indices_in_range(
     ), f"Assert Failed: {tile_width} * {tile_size} >= {image_width}"
     assert transmittances.shape == (C, image_height, image_width), transmittances.shape
     transmittances = transmittances.contiguous()
-    means2d, conics, opacities = means2d.contiguous(), conics.contiguous(), opacities.contiguous()
+    means2d, conics, opacities = _aligned8(means2d.contiguous()), conics.contiguous(), opacities.contiguous()
     isect_offsets, flatten_ids = isect_offsets.contiguous(), flatten_ids.contiguous()
     _check_cuda(transmittances, means2d, conics, opacities, isect_offsets, flatten_ids)
     for t in (transmittances, means2d, conics, opacities):

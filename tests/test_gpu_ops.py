@@ -497,3 +497,36 @@ def test_sh_colors_bwd_premasked_camera_exchange():
     torch.testing.assert_close(v_coeffs, g_all[1], rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(v_means, g_m1, rtol=1e-4, atol=1e-6)
     assert wrapper._CAMERA_PARALLEL == {}
+
+
+def test_odd_sized_batches_and_misaligned_means2d_views():
+    """C*N odd: the projection outputs are views of one allocation and means2d is accessed as float2 by every
+    consumer — it must stay 8-byte aligned; a caller-provided means2d view at an odd float offset is re-packed
+    by the wrappers (the C ABI rejects it with an error instead of faulting)."""
+    from splat_one_b200 import synthetic
+    from splat_one_b200._lib import get_lib
+
+    sc = synthetic.pinhole_scene(1001, 160, 120, seed=3)
+    P = [sc[k].to(DEV) for k in ("means", "quats", "scales", "opacities", "sh")]
+    rc, ra, meta = S.rasterization(*P, sc["viewmats"].to(DEV), sc["Ks"].to(DEV), 160, 120, sh_degree=3, packed=False)
+    torch.cuda.synchronize()
+    assert meta["means2d"].data_ptr() % 8 == 0 and torch.isfinite(rc).all()
+    # the same intersections from a means2d view that starts at an odd float offset
+    m2 = meta["means2d"].detach()
+    buf = torch.empty(m2.numel() + 1, device=DEV)
+    odd = buf[1:].view_as(m2)
+    odd.copy_(m2)
+    assert odd.data_ptr() % 8 == 4
+    a = S.isect_tiles(m2, meta["radii"], meta["depths"].detach(), 16, 10, 8)
+    b = S.isect_tiles(odd, meta["radii"], meta["depths"].detach(), 16, 10, 8)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    lib = get_lib()
+    import ctypes
+
+    tpg = torch.empty(1001, dtype=torch.int32, device=DEV)
+    tot = torch.zeros(2, dtype=torch.int64, device=DEV)
+    rc_ = lib.b200splat_isect_count(0, 1, 1001, 0, ctypes.c_void_p(odd.data_ptr()), ctypes.c_void_p(meta["radii"].data_ptr()),
+                                    ctypes.c_void_p(meta["depths"].data_ptr()), 16, 10, 8, ctypes.c_void_p(tpg.data_ptr()), None,
+                                    ctypes.c_void_p(tot.data_ptr()), None, 0, None)
+    assert rc_ != 0 and b"8-byte aligned" in lib.b200splat_last_error()
