@@ -207,7 +207,11 @@ class PeerExchange:
     hdr, cotangents [Cm,N,3]}.  Construction is COLLECTIVE over `group` (symmetric allocation +
     rendezvous, `torch.distributed._symmetric_memory` is only the allocator/handle exchange).  Raises
     if the platform cannot map peer memory; callers fall back to the NCCL path (`camera_parallel()`
-    without `peer`, `GradArena(params)`)."""
+    without `peer`, `GradArena(params)`).  The buffer is sized for ONE (n_gaussians, cams_per_rank): after
+    densification changes the number of Gaussians build a new exchange (and arena) on every rank — a step
+    whose sizes do not match (`fits()`) silently takes the NCCL all-gather for the cotangents instead.
+    All ranks must issue the same sequence of exchange calls (the handshake flags are positional); a rank
+    that never arrives makes its peers trap after 20 s instead of hanging."""
 
     def __init__(self, n_gaussians: int, cams_per_rank: int = 1, group=None, arena_floats: int = 0,
                  device: Optional[torch.device] = None, use_multicast: Optional[bool] = None):
