@@ -297,14 +297,14 @@ def reference_cuda_leg(S, scene, dev, ms_ours: float, reps: int = 20, warm: int 
 EXCHANGE = os.environ.get("B200SPLAT_DP_EXCHANGE", "peer")
 
 
-def make_peer(n_gaussians, cams_per_rank, params, world, note=None):
+def make_peer(n_gaussians, cams_per_rank, params, world, note=None, with_arena=True):
     """PeerExchange sized for `params`, or None (with the reason in note["error"]) where unavailable."""
     if world <= 1 or EXCHANGE == "nccl":
         return None
     from splat_one_b200.distributed import PeerExchange, arena_layout
 
     try:
-        return PeerExchange(n_gaussians, cams_per_rank, arena_floats=arena_layout(params)[1],
+        return PeerExchange(n_gaussians, cams_per_rank, arena_floats=arena_layout(params)[1] if with_arena else 0,
                             use_multicast={"1": True, "0": False}.get(os.environ.get("B200SPLAT_DP_MULTICAST", "")))
     except Exception as e:  # no peer mapping on this platform: the NCCL exchange is used and the line says so
         if note is not None:
@@ -376,7 +376,8 @@ def extra_config(S, dist, name, world, rank, dev, steps: int = 10, warm: int = 3
     g = torch.Generator().manual_seed(2000 + rank)
     vc = torch.randn(1, H_, W_, 3, generator=g).to(dev)
     va = torch.randn(1, H_, W_, 1, generator=g).to(dev)
-    peer = make_peer(n, 1, P, world) if name == "C" else None
+    # C: cotangent slots + the arena in symmetric memory; E (packed + sparse): cotangent slots only
+    peer = make_peer(n, 1, P, world, with_arena=name == "C")
     arena = GradArena(P, peer=peer) if (world > 1 and name == "C") else None
     counts = []
 
@@ -389,10 +390,14 @@ def extra_config(S, dist, name, world, rank, dev, steps: int = 10, warm: int = 3
                 torch.autograd.backward([rc, ra], [vc, va])
             arena.gather_from_params()
             arena.all_reduce(skip_ptrs=cp.reduced_ptrs)
+        elif world > 1:
+            # packed colour stage: cotangent exchange (scattered to the dense layout) instead of the 1.15 GB SH
+            # all-reduce; sparse (gaussian_ids, rows) exchange or its dense fallback for the projection gradients
+            with camera_parallel(peer=peer) as cp:
+                torch.autograd.backward([rc, ra], [vc, va])
+            allreduce_mixed_gradients(P, skip_ptrs=cp.reduced_ptrs)
         else:
             torch.autograd.backward([rc, ra], [vc, va])
-            if world > 1:
-                allreduce_mixed_gradients(P)
         return meta
 
     for _ in range(warm):
@@ -415,7 +420,8 @@ def extra_config(S, dist, name, world, rank, dev, steps: int = 10, warm: int = 3
     out = {"ms_per_step": ms, "Mpix_per_s": world * H_ * W_ / (ms * 1e-3) / 1e6, "steps": steps, "warmup": warm,
            "n_gaussians": n, "image": f"{W_}x{H_}", "cameras": world, "n_isects_rank0": int(meta["flatten_ids"].numel()),
            "mode": ("unpacked, dense gradients; exchange = " + exchange_kind(peer)) if name == "C" else
-                   "packed, sparse gradients: (gaussian_ids, rows) all-gather with dense fallback above 0.4 visible"}
+                   "packed, sparse projection gradients: (gaussian_ids, rows) all-gather with dense fallback above 0.4 "
+                   "visible; SH gradient through the colour-cotangent exchange = " + exchange_kind(peer)}
     del P, sc, arena, peer
     torch.cuda.empty_cache()
     return out

@@ -549,7 +549,8 @@ B200SPLAT_API int b200splat_sh_colors_staged_bwd_peer(
  * offsets valid in each); the flag region (b200splat_peer_flag_bytes(W) bytes at flag_offset_bytes,
  * zero-initialised once by the caller) carries the release/acquire handshakes.  All ranks must issue
  * the same sequence of these calls.
- *   publish:   campos [C,3] and the cotangents masked by colors > 0 ([C,N,3]) -> this rank's block
+ *   publish:   campos [C,3] and the cotangents masked by colors > 0 ([C,N,3]; colors == NULL: already
+ *              masked) -> this rank's block
  *              (layout above; camera slots C..cams_per_block-1 are zero-filled);
  *   barrier:   returns (in stream order) once every rank has reached it: the peers' blocks are readable;
  *   allreduce: in-place SUM over ranks of n_floats fp32 at offset_bytes of every rank's buffer, two-shot

@@ -84,15 +84,17 @@ peer_publish_kernel(uint32_t C, uint64_t n3, uint32_t cams_per_block, uint32_t h
     if (tid < hdr_floats) block[tid] = tid < 3ull * C ? campos[tid] : 0.f;
     float *dst = block + hdr_floats;
     const uint64_t live4 = live / 4;
+    const float4 ones = make_float4(1.f, 1.f, 1.f, 1.f);
     for (uint64_t i = tid; i < live4; i += stride) {
-        const float4 c = __ldcs(reinterpret_cast<const float4 *>(colors) + i);
+        // colors == NULL: the cotangents are already masked (packed layout scattered to [C,N,3])
+        const float4 c = colors != nullptr ? __ldcs(reinterpret_cast<const float4 *>(colors) + i) : ones;
         float4 v = __ldcs(reinterpret_cast<const float4 *>(v_colors) + i);
         v.x = c.x > 0.f ? v.x : 0.f; v.y = c.y > 0.f ? v.y : 0.f;
         v.z = c.z > 0.f ? v.z : 0.f; v.w = c.w > 0.f ? v.w : 0.f;
         reinterpret_cast<float4 *>(dst)[i] = v;
     }
     for (uint64_t i = live4 * 4 + tid; i < total; i += stride)
-        dst[i] = i < live ? (colors[i] > 0.f ? v_colors[i] : 0.f) : 0.f;
+        dst[i] = i < live ? ((colors == nullptr || colors[i] > 0.f) ? v_colors[i] : 0.f) : 0.f;
 }
 
 __device__ __forceinline__ float4 multimem_ld_add(unsigned long long addr) {

@@ -464,10 +464,14 @@ def allreduce_mixed_gradients(params: Sequence[Tensor], arena: Optional[GradAren
     """Gradient exchange of a camera-sharded step whose parameters carry a MIX of dense and sparse
     gradients (packed mode, `sparse_grad=True`): the sparse ones (sharing `gaussian_ids`) go through
     `sparse_allreduce`, the dense ones through the flat arena.  `p.grad` of every parameter holds the
-    global sum afterwards (sparse stays sparse below the threshold)."""
+    global sum afterwards (sparse stays sparse below the threshold).  Inside `camera_parallel` the packed
+    colour stage exchanges cotangents like the un-packed one (scattered to the dense [C,N,3] layout), so pass
+    `skip_ptrs=cp.reduced_ptrs`."""
     params = list(params)
     sparse = [p for p in params if p.grad is not None and p.grad.is_sparse]
-    dense = [p for p in params if p.grad is not None and not p.grad.is_sparse]
+    # parameters whose gradient is already global (`camera_parallel.reduced_ptrs`: the SH table of the colour
+    # exchange, 81 % of the bytes) are neither copied nor reduced
+    dense = [p for p in params if p.grad is not None and not p.grad.is_sparse and p.data_ptr() not in skip_ptrs]
     if sparse:
         for p, g in zip(sparse, sparse_allreduce([p.grad for p in sparse], group=group, dense_threshold=dense_threshold)):
             p.grad = g

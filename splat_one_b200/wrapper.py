@@ -422,7 +422,7 @@ def _camera_parallel_colour_bwd(cp, means, campos, colors, v_colors, C, outs, v_
     if peer is not None and run_peer is not None and peer.fits(N, Cm) and peer.group is cp:
         slot = peer.next_slot()
         native("peer_publish_cotangents", get_lib(), means.device, C, N, Cm, peer.hdr, _ptr(campos.contiguous()),
-               _ptr(colors), _ptr(v_colors), _ptr(peer.slot_view(slot)))
+               _ptr(colors), _ptr(v_colors), _ptr(peer.slot_view(slot)))  # colors None: v_colors is pre-masked
         peer.barrier()
         if deferred is None:
             run_peer(peer.bases_dev, 4 * peer.slot_off[slot], Cm, peer.hdr, outs, v_means, r * Cm, r * Cm + C, W * Cm)
@@ -450,7 +450,8 @@ def _camera_parallel_colour_bwd(cp, means, campos, colors, v_colors, C, outs, v_
         join.local = True  # the returned direction gradient is this rank's share, not the global sum
         deferred.append((means, join))
         return None
-    g_local = torch.where(colors > 0, v_colors, torch.zeros_like(v_colors))  # [C,N,3], zero where invisible
+    # [C,N,3], zero where invisible or clamped (colors None: the caller masked it already)
+    g_local = v_colors if colors is None else torch.where(colors > 0, v_colors, torch.zeros_like(v_colors))
     campos_c = campos.contiguous()
     if Cm != C:
         g_local = torch.cat([g_local, g_local.new_zeros((Cm - C, N, 3))])
@@ -673,6 +674,7 @@ class _ShViewColorsPacked(torch.autograd.Function):
                    _ptr(campos), _ptr(coeffs), _ptr(camera_ids), _ptr(gaussian_ids), _ptr(colors))
         ctx.save_for_backward(means, campos, coeffs, camera_ids, gaussian_ids, colors)
         ctx.sh_degree = sh_degree
+        ctx.coeff_leaves = _leaf_sources(coeffs)
         return colors
 
     @staticmethod
@@ -682,6 +684,33 @@ class _ShViewColorsPacked(torch.autograd.Function):
         C, N, nnz = campos.shape[0], means.shape[0], gaussian_ids.shape[0]
         K = coeffs.shape[-2]
         per_view = int(coeffs.dim() == 4)
+        cp = _CAMERA_PARALLEL.get("group", None) if _CAMERA_PARALLEL else None
+        if cp is not None and not per_view and N and ctx.coeff_leaves is not None \
+                and _CAMERA_PARALLEL.get("deferred") is None:
+            # camera-parallel exchange for the packed layout (config E): the masked cotangents are scattered
+            # into the dense [C,N,3] layout of the un-packed exchange (12 B per Gaussian and camera; zero =
+            # invisible) and the same kernels sum the coefficient gradient over ALL ranks' cameras, instead of
+            # all-reducing 3K floats per Gaussian (1.15 GB at 6 M Gaussians, K = 16)
+            g = torch.where(colors > 0, v_colors, torch.zeros_like(v_colors))
+            g_dense = torch.zeros((C, N, 3), device=means.device, dtype=torch.float32)
+            if nnz:
+                g_dense[camera_ids, gaussian_ids] = g
+            v_coeffs = _grad_out(coeffs)
+            v_means = torch.empty_like(means) if ctx.needs_input_grad[1] else None
+
+            def run(campos_all, g_all, v_out, v_means_out, lo, hi, WC):
+                native("sh_colors_bwd", lib, means.device, WC, N, K, ctx.sh_degree, 0, _ptr(means), _ptr(campos_all),
+                       _ptr(coeffs), None, None, _ptr(g_all), _ptr(v_out[0]), _ptr(v_means_out), lo, hi)
+
+            def run_peer(bases, off_bytes, cams_per_block, hdr, v_out, v_means_out, lo, hi, WC):
+                native("sh_colors_bwd_peer", lib, means.device, WC, N, K, ctx.sh_degree, _ptr(means), _ptr(coeffs),
+                       bases, off_bytes, cams_per_block, hdr, _ptr(v_out[0]), _ptr(v_means_out), lo, hi)
+
+            _CAMERA_PARALLEL["leaves"] = ctx.coeff_leaves
+            v_means = _camera_parallel_colour_bwd(cp, means, campos, None, g_dense, C, (v_coeffs,), v_means, run, run_peer)
+            for lf in ctx.coeff_leaves:
+                _CAMERA_PARALLEL["reduced"].add(lf.data_ptr())
+            return None, v_means, None, (v_coeffs if ctx.needs_input_grad[3] else None), None, None
         v_coeffs = torch.zeros_like(coeffs)
         v_means = torch.zeros_like(means) if ctx.needs_input_grad[1] else None
         if nnz:

@@ -57,9 +57,19 @@ def _worker(rank, world, port, out_path, sh_mode, defer, n_cams, packed_sparse, 
             rc, ra, _ = S.rasterization(*P, vm, Ks, W, H, **kw)
         if dp and packed_sparse is not None:
             # packed mode, sparse gradients: (gaussian_ids, rows) exchange or its dense fallback
-            torch.autograd.backward([rc, ra], [vc, va])
+            if peer_mode is not None:
+                # ... and the SH gradient through the colour-cotangent exchange of the packed colour stage
+                if "x" not in peer_box:
+                    peer_box["x"] = PeerExchange(N, (n_cams + world - 1) // world) if peer_mode != "nccl" else None
+                with camera_parallel(peer=peer_box["x"], n_cameras_global=n_cams if uneven else None) as cp:
+                    torch.autograd.backward([rc, ra], [vc, va])
+                assert P[4].data_ptr() in cp.reduced_ptrs
+                skip = cp.reduced_ptrs
+            else:
+                torch.autograd.backward([rc, ra], [vc, va])
+                skip = ()
             assert P[1].grad.is_sparse and P[2].grad.is_sparse
-            allreduce_mixed_gradients(P, dense_threshold=packed_sparse)
+            allreduce_mixed_gradients(P, dense_threshold=packed_sparse, skip_ptrs=skip)
             assert P[1].grad.is_sparse == (packed_sparse > 1.0)
         elif dp:
             peer = None
@@ -110,6 +120,25 @@ CASES = [
     # packed + sparse_grad (config E's mode): sparse (ids, rows) exchange and its dense fallback
     ("table", False, 2, 10.0), ("table", False, 2, 0.0),
 ]
+
+
+PACKED_CP_CASES = [("table", 2, 0.0, "p2p"), ("table", 2, 10.0, "nccl"), ("cat", 3, 0.0, "p2p")]
+
+
+@pytest.mark.parametrize("sh_mode,n_cams,packed_sparse,peer_mode", PACKED_CP_CASES)
+def test_two_gpu_packed_camera_parallel_matches_single_process_batch(tmp_path, sh_mode, n_cams, packed_sparse, peer_mode):
+    """Packed + sparse_grad (config E's mode) inside camera_parallel: the packed colour stage scatters its masked
+    cotangents into the dense [C,N,3] layout and takes the same exchange as the un-packed path (peer kernels or
+    NCCL all-gather), so the SH table is never all-reduced; projection gradients go through the sparse exchange."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    out = str(tmp_path / "report.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out, sh_mode, False, n_cams, packed_sparse, peer_mode), nprocs=2, join=True)
+    for r, rep in enumerate(torch.load(out)):
+        for n, (max_rel, n_bad) in rep.items():
+            assert max_rel < 1e-3 and n_bad == 0, f"rank {r} grad {n}: max rel {max_rel:.2e}, rows outside 1e-3: {n_bad}"
 
 
 PEER_CASES = [("table", 2, "p2p", False), ("split", 2, "p2p", False), ("cat", 2, "p2p", False), ("table", 3, "p2p", False),
