@@ -3,6 +3,7 @@
 backward kernels alone on the config-B scene, for each B200SPLAT_TUNING_VARIANT given.
 
     python tools/raster_bench.py [variants...]      e.g.  python tools/raster_bench.py 0 1
+(one variant: B200SPLAT_TUNING_VARIANT=<v> python tools/raster_bench.py <v>; several: one subprocess each)
 """
 import math
 import os
@@ -53,13 +54,24 @@ def run(reps=10):
     return sorted(tf)[len(tf) // 2], sorted(tb)[len(tb) // 2], out
 
 
+# The tuning variant is read ONCE, when libb200splat.so is loaded: several variants = one process each
+# (this script re-invokes itself), built with B200SPLAT_TUNING=1 python -m splat_one_b200.build --force.
+if len(sys.argv) > 2:
+    import subprocess
+
+    for v in sys.argv[1:]:
+        env = dict(os.environ, B200SPLAT_TUNING_VARIANT="0" if v == "generic" else v)
+        subprocess.run([sys.executable, os.path.abspath(__file__), v], env=env, check=False)
+    sys.exit(0)
+
 base = None
 for v in (sys.argv[1:] or ["0"]):
     if v == "generic":
         wrapper._FORCE_GENERIC_RASTER = True
     else:
         wrapper._FORCE_GENERIC_RASTER = False
-        os.environ["B200SPLAT_TUNING_VARIANT"] = v
+        assert os.environ.get("B200SPLAT_TUNING_VARIANT", "0") == v or v == "0", \
+            "set B200SPLAT_TUNING_VARIANT before the library loads (or pass several variants)"
     f, b, out = run()
     msg = f"variant {v:8s} fwd(+pack) {f:.3f} ms   bwd(+zero-fill) {b:.3f} ms"
     if base is None:
