@@ -28,7 +28,11 @@ class camera_parallel:
     colour cotangents (3 floats per Gaussian and camera) and camera centres, and every rank
     sums the outer products over all cameras in one kernel: the SH gradient comes out of
     `backward()` already global.  `reduced_ptrs` lists the parameters (by data_ptr) this
-    happened for; `GradArena.all_reduce(skip_ptrs=...)` then leaves them out."""
+    happened for; `GradArena.all_reduce(skip_ptrs=...)` / `allreduce_mixed_gradients(skip_ptrs=...)`
+    then leave them out.  Covered colour stages: the fused un-packed one (whole table, `torch.cat([sh0,
+    shN])` of leaves, or the split `(sh0, shN)` pair) and the packed one with a whole table (its masked
+    cotangents are scattered into the dense [C,N,3] layout first); per-view tables, the packed split pair
+    and pose-gradient runs fall back to the per-rank gradient, which is then reduced like the others."""
 
     def __init__(self, group=None, defer: bool = False, n_cameras_global: Optional[int] = None,
                  peer: Optional["PeerExchange"] = None):
