@@ -548,10 +548,55 @@ __host__ __device__ __forceinline__ uint32_t stage_row_stride(uint32_t R) {
     return (R % 4 == 0) ? 4u * ((R / 4) | 1u) : (R | 1u);
 }
 
-// global span [g, g + cnt*R) -> smem rows of stride RS
+// ---- 1-D bulk copies (TMA engine, cp.async.bulk / SASS UBLKCP): when the smem rows are contiguous (RS == R:
+// the split table, 45 floats per row) a warp's 32 rows are ONE 5760-byte span on both sides, moved by a single
+// asynchronous instruction issued by lane 0 — no registers, no per-lane address arithmetic; completion through a
+// per-warp mbarrier (loads) or the bulk-group wait (stores).  Spans whose byte count is not a multiple of 16 (the
+// last warp of an odd-sized table) take the per-lane loops below.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void stage_bar_init(uint64_t *bar, unsigned lane) {
+    if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+}
+
+__device__ __forceinline__ void bulk_rows_in(float *s_dst, const float *g_src, uint32_t bytes, uint64_t *bar,
+                                             uint32_t parity, unsigned lane) {
+    const uint32_t bar_a = smem_u32(bar);
+    if (lane == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(s_dst)), "l"(g_src), "r"(bytes), "r"(bar_a) : "memory");
+    }
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(bar_a), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void bulk_rows_out(float *g_dst, const float *s_src, uint32_t bytes, unsigned lane) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // every lane's generic smem writes -> async proxy
+    __syncwarp();
+    if (lane == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g_dst), "r"(smem_u32(s_src)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem may be reused / the block may exit
+    }
+    __syncwarp();
+}
+
+// global span [g, g + cnt*R) -> smem rows of stride RS.  bar: this warp's mbarrier (nullptr: no bulk path);
+// parity: its phase, flipped here after every bulk load.
 __device__ __forceinline__ void stage_rows_in(const float *__restrict__ g, uint32_t cnt, uint32_t R, uint32_t RS,
-                                              float *s, unsigned lane, bool aligned) {
+                                              float *s, unsigned lane, bool aligned, uint64_t *bar = nullptr,
+                                              uint32_t *parity = nullptr) {
     const uint32_t total = cnt * R;
+    if (bar != nullptr && aligned && RS == R && total > 0 && (total & 3u) == 0) {
+        bulk_rows_in(s, g, total * 4u, bar, *parity, lane);
+        *parity ^= 1u;
+        return;
+    }
     if (aligned && R % 4 == 0) {
         const float4 *g4 = reinterpret_cast<const float4 *>(g);
         float4 *s4 = reinterpret_cast<float4 *>(s);
@@ -576,8 +621,12 @@ __device__ __forceinline__ void stage_rows_in(const float *__restrict__ g, uint3
 
 // smem rows -> global span (streaming stores: the gradient is read once, by the optimizer)
 __device__ __forceinline__ void stage_rows_out(float *__restrict__ g, uint32_t cnt, uint32_t R, uint32_t RS,
-                                               const float *s, unsigned lane, bool aligned) {
+                                               const float *s, unsigned lane, bool aligned, bool bulk = false) {
     const uint32_t total = cnt * R;
+    if (bulk && aligned && RS == R && total > 0 && (total & 3u) == 0) {
+        bulk_rows_out(g, s, total * 4u, lane);
+        return;
+    }
     if (aligned && R % 4 == 0) {
         float4 *g4 = reinterpret_cast<float4 *>(g);
         const float4 *s4 = reinterpret_cast<const float4 *>(s);
@@ -650,9 +699,13 @@ sh_colors_staged_fwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, co
     const uint64_t e = (uint64_t)c * N + n;
     const bool act = lane < cnt && radii[e] > 0;
     const bool aligned = (reinterpret_cast<uintptr_t>(rest) & 15) == 0;
+    __shared__ uint64_t s_bar[kStageWarps];
+    uint32_t parity = 0;
+    stage_bar_init(&s_bar[warp], lane);
     float cf[NF > 0 ? NF : 1];
     if (NF > 0) {
-        if (__any_sync(0xffffffffu, act)) stage_rows_in(rest + (size_t)n0 * R, cnt, R, RS, s, lane, aligned);
+        if (__any_sync(0xffffffffu, act))
+            stage_rows_in(rest + (size_t)n0 * R, cnt, R, RS, s, lane, aligned, &s_bar[warp], &parity);
         __syncwarp();
         if (act) row_to_regs<(NF > 0 ? NF : 1)>(s + (size_t)lane * RS, cf, R % 4 == 0);
     }
@@ -710,14 +763,18 @@ sh_colors_staged_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, co
     const bool vec = R % 4 == 0;
     const bool want_means = v_means != nullptr && NB > 1 && means_cam_begin < means_cam_end;
     // the DC basis has no direction derivative: sh0 itself is never read here
+    __shared__ uint64_t s_bar[kStageWarps];
+    uint32_t parity = 0;
+    stage_bar_init(&s_bar[warp], lane);
     float cf[CFS ? 1 : NFA];
     if (want_means && NF > 0) {
         if (CFS) {
             stage_rows_in(rest + (size_t)n0 * R, cnt, R, RS, const_cast<float *>(scf) - (size_t)lane * RS, lane,
-                          (reinterpret_cast<uintptr_t>(rest) & 15) == 0);
+                          (reinterpret_cast<uintptr_t>(rest) & 15) == 0, &s_bar[warp], &parity);
             __syncwarp();
         } else {
-            stage_rows_in(rest + (size_t)n0 * R, cnt, R, RS, s, lane, (reinterpret_cast<uintptr_t>(rest) & 15) == 0);
+            stage_rows_in(rest + (size_t)n0 * R, cnt, R, RS, s, lane, (reinterpret_cast<uintptr_t>(rest) & 15) == 0,
+                          &s_bar[warp], &parity);
             __syncwarp();
             row_to_regs<CFS ? 1 : NFA>(s + (size_t)lane * RS, cf, vec);
             __syncwarp();  // the buffer is reused for the gradient rows below
@@ -799,7 +856,7 @@ sh_colors_staged_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, uint32_t deg, co
             else for (uint32_t k = 0; k < R; k++) s[(size_t)lane * RS + k] = 0.f;
         }
         __syncwarp();
-        stage_rows_out(v_rest + (size_t)n0 * R, cnt, R, RS, s, lane, (reinterpret_cast<uintptr_t>(v_rest) & 15) == 0);
+        stage_rows_out(v_rest + (size_t)n0 * R, cnt, R, RS, s, lane, (reinterpret_cast<uintptr_t>(v_rest) & 15) == 0, true);
     }
     if (!mine) return;
     if (SPLIT) { v_sh0[3 * (size_t)n] = vdc[0]; v_sh0[3 * (size_t)n + 1] = vdc[1]; v_sh0[3 * (size_t)n + 2] = vdc[2]; }
